@@ -1,0 +1,198 @@
+"""ctypes binding of libm1b200.so (include/m1b200.h) and DLPack device-pointer export.
+
+There is deliberately no fallback: if the shared library is missing the import of any compute
+entry point raises, and every call fails loudly on a machine without an sm_100 GPU.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libm1b200.so")
+
+M1_MAX_SRC = 8
+M1_MAX_OUT = 2
+F32, BF16 = 0, 1
+CONV_FWD, CONV_TRANSPOSED = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    """m1_conv_desc of include/m1b200.h"""
+    _fields_ = [
+        ("mode", C.c_int32), ("batch", C.c_int32),
+        ("in_dhw", C.c_int32 * 3), ("out_dhw", C.c_int32 * 3),
+        ("kernel", C.c_int32 * 3), ("stride", C.c_int32 * 3), ("pad", C.c_int32 * 3),
+        ("nsrc", C.c_int32), ("src_c", C.c_int32 * M1_MAX_SRC),
+        ("nout", C.c_int32), ("out_c", C.c_int32 * M1_MAX_OUT),
+        ("w_stride_tap", C.c_int64 * M1_MAX_OUT), ("w_stride_red", C.c_int64 * M1_MAX_OUT),
+        ("w_stride_out", C.c_int64 * M1_MAX_OUT),
+        ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("engine", C.c_int32),
+    ]
+
+
+class Dropout(C.Structure):
+    """m1_dropout of include/m1b200.h"""
+    _fields_ = [("u", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_uint64),
+                ("rate", C.c_float)]
+
+
+class M1Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/m1b200.h declares
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_PP = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "m1_last_error": (C.c_char_p, []),
+    "m1_version": (_I, []),
+    "m1_ctx_create": (_I, [_I, C.POINTER(C.c_void_p)]),
+    "m1_ctx_destroy": (_I, [_P]),
+    "m1_ctx_launch_count": (_L, [_P, _I]),
+    "m1_conv3d_tc_supported": (_I, [C.POINTER(ConvDesc)]),
+    "m1_conv3d": (_I, [_P, C.POINTER(ConvDesc), _PP, _PP, _P, _PP, _PP, _P]),
+    "m1_conv3d_packed_bytes": (_L, [C.POINTER(ConvDesc)]),
+    "m1_conv3d_pack_weights": (_I, [_P, C.POINTER(ConvDesc), _PP, _P, _P]),
+    "m1_conv3d_wgrad": (_I, [_P, C.POINTER(ConvDesc), _PP, _PP, _PP, _PP, _P]),
+    "m1_inorm_stats": (_I, [_P, _P, _I, _I, _L, _I, _F, _P, _P]),
+    "m1_inorm_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _P]),
+    "m1_inorm_act_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P]),
+    "m1_se_squeeze": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _P]),
+    "m1_se_excite_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "m1_se_excite_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "m1_se_gate_fwd": (_I, [_P] + [_P] * 9 + [C.POINTER(Dropout), _I, _I, _L, _I, _P, _P]),
+    "m1_se_gate_bwd_reduce": (_I, [_P] + [_P] * 10 + [C.POINTER(Dropout), _I, _I, _L, _I, _P, _P, _P]),
+    "m1_se_gate_bwd_apply": (_I, [_P] + [_P] * 10 + [C.POINTER(Dropout), _P, _P, _I, _I, _L, _I]
+                             + [_P] * 6 + [_P]),
+    "m1_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "m1_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P,
+                         _P, _P, _P]),
+    "m1_latent_fwd": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _I, _P, _P]),
+    "m1_latent_bwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _I, _I, _P, _P]),
+    "m1_kl_fwd": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
+    "m1_kl_bwd": (_I, [_P, _P, _P, _I, _L, _I, _F, _P, _P, _P]),
+    "m1_softmax_focal": (_I, [_P, _P, _I, _P, _I, _P, _F, _I, _P, _P, _I, _P, _I, _I, _F, _P, _P,
+                              _F, _P]),
+    "m1_adam_amsgrad": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "m1_cast": (_I, [_P, _P, _I, _P, _I, _L, _P]),
+    "m1_copy_channels": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _L, _P]),
+    "m1_axpy": (_I, [_P, _P, _I, _F, _P, _L, _P]),
+    "m1_decision_fusion": (_I, [_P, _P, _P, _I, _L, _P, _P]),
+}
+
+
+def lib():
+    """Loads libm1b200.so (once). Raises if it has not been built - there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise M1Error(
+                f"{LIB_PATH} not found: build it with prostatemr_3d-cad-cspca_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); m1b200 has no CPU / PyTorch fallback")
+        handle = C.CDLL(LIB_PATH)
+        missing = [name for name in SIGNATURES if not hasattr(handle, name)]
+        if missing and os.environ.get("M1_BRINGUP") == "1":   # kernel bring-up only
+            for name in missing:
+                SIGNATURES.pop(name)
+            missing = []
+        if missing:
+            raise M1Error(f"{LIB_PATH} lacks symbols declared in include/m1b200.h: {missing}")
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise M1Error(lib().m1_last_error().decode())
+
+
+# ---- DLPack zero-copy pointer export -------------------------------------------------------
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int32),
+                ("dtype", _DLDataType), ("shape", C.POINTER(C.c_int64)),
+                ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+_KDL_CUDA = 2
+
+
+def dlpack_device_ptr(obj, expect_cuda=True):
+    """Device pointer of any object exporting ``__dlpack__`` (torch / cupy / jax / TF-experimental
+    tensors), without copying: reads DLManagedTensor.dl_tensor.{data,byte_offset}."""
+    capsule = obj.__dlpack__()
+    raw = C.pythonapi.PyCapsule_GetPointer(capsule, b"dltensor")
+    dl = C.cast(raw, C.POINTER(_DLTensor)).contents
+    if expect_cuda and dl.device.device_type != _KDL_CUDA:
+        raise M1Error("m1b200 kernels need CUDA device memory (DLPack device_type "
+                      f"{dl.device.device_type}); there is no CPU path")
+    ptr = (dl.data or 0) + dl.byte_offset
+    # the capsule still owns the DLManagedTensor; dropping it calls the deleter (no copy was made)
+    del capsule
+    return ptr
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous(), "m1b200 kernels take dense tensors"
+        return dlpack_device_ptr(t.detach(), expect_cuda=True) if t.numel() else None
+    return dlpack_device_ptr(t)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise M1Error(f"unsupported activation dtype {t.dtype}")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*[p if p else None for p in ptrs])
+    return C.cast(arr, C.POINTER(C.c_void_p))
+
+
+def current_stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Context:
+    """m1_ctx wrapper: one per GPU / process."""
+    _instances = {}
+
+    def __init__(self, device):
+        self.device = device
+        h = C.c_void_p()
+        check(lib().m1_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = torch.cuda.current_device()
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def launch_count(self, reset=False):
+        return lib().m1_ctx_launch_count(self.handle, 1 if reset else 0)

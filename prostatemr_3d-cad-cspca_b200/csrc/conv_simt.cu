@@ -1,0 +1,392 @@
+// conv_simt.cu — generic fp32-accumulating gather convolution on the CUDA cores.
+//
+// This is the engine for (a) precision='fp32' (the 1e-4 parity mode of the north star: tensor
+// cores have no fp32 multiply), (b) every launch shape the tcgen05 engine does not take yet
+// (strided / transposed / tiny-channel layers) and (c) the weight gradient.  One kernel covers
+// Conv3D, Conv3DTranspose and both of their data gradients through the two gather modes of
+// m1_conv_desc; it never materialises the channel concatenations of the reference.
+//
+// Reference call-sites: tf.keras.layers.Conv3D / Conv3DTranspose, R:networks.py:472,496-553,
+// R:network_blocks.py:37-46,100-103,275 (TF SAME padding; Conv3DTranspose = exact adjoint).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int BM = 64;   // output voxels per block
+constexpr int BN = 64;   // produced channels per block
+constexpr int BK = 16;   // reduced channels per step
+constexpr int TH = 128;  // threads
+
+struct SimtParams {
+  int mode;
+  int batch;
+  int Di, Hi, Wi, Do, Ho, Wo;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int nsrc;
+  const void* src[M1_MAX_SRC];
+  int src_c[M1_MAX_SRC];
+  int nout;
+  void* out[M1_MAX_OUT];
+  int out_c[M1_MAX_OUT];
+  const float* w[M1_MAX_OUT];
+  const float* bias[M1_MAX_OUT];
+  int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
+  int accumulate;
+  int n_total;
+  int64_t out_vox;  // batch * Do*Ho*Wo
+};
+
+// input voxel index (within the batch-flattened gathered grid) for output voxel (n,d,h,w) and tap
+// (a,b,c); -1 when the tap falls into the SAME padding / between the stride phases
+__device__ __forceinline__ int64_t gather_index(const SimtParams& p, int n, int d, int h, int w,
+                                                int a, int b, int c) {
+  int id, ih, iw;
+  if (p.mode == M1_CONV_FWD) {
+    id = d * p.sd + a - p.pd;
+    ih = h * p.sh + b - p.ph;
+    iw = w * p.sw + c - p.pw;
+  } else {
+    id = d + p.pd - a;
+    ih = h + p.ph - b;
+    iw = w + p.pw - c;
+    if (id < 0 || ih < 0 || iw < 0) return -1;
+    if (id % p.sd || ih % p.sh || iw % p.sw) return -1;
+    id /= p.sd; ih /= p.sh; iw /= p.sw;
+  }
+  if (id < 0 || id >= p.Di || ih < 0 || ih >= p.Hi || iw < 0 || iw >= p.Wi) return -1;
+  return (((int64_t)n * p.Di + id) * p.Hi + ih) * p.Wi + iw;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ SimtParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  __shared__ int vn[BM], vd[BM], vh[BM], vw[BM];
+  __shared__ int64_t vin[BM];
+
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tx = tid % 8, ty = tid / 8;  // 8 channel groups x 16 voxel groups
+
+  if (tid < BM) {
+    int64_t m = m0 + tid;
+    if (m < p.out_vox) {
+      int w = (int)(m % p.Wo); m /= p.Wo;
+      int h = (int)(m % p.Ho); m /= p.Ho;
+      int d = (int)(m % p.Do); m /= p.Do;
+      vn[tid] = (int)m; vd[tid] = d; vh[tid] = h; vw[tid] = w;
+    } else {
+      vn[tid] = -1;
+    }
+  }
+  __syncthreads();
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int taps = p.kd * p.kh * p.kw;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+    __syncthreads();
+    if (tid < BM) vin[tid] = vn[tid] < 0 ? -1 : gather_index(p, vn[tid], vd[tid], vh[tid], vw[tid], a, b, c);
+    __syncthreads();
+    // skip taps that touch nothing in this tile (common for transposed gathers)
+    int any = 0;
+    if (tid < BM) any = vin[tid] >= 0;
+    any = __syncthreads_or(any);
+    if (!any) continue;
+
+    int r_base = 0;  // reduced-channel offset over the virtual concatenation
+    for (int s = 0; s < p.nsrc; ++s) {
+      const int C = p.src_c[s];
+      const T* src = reinterpret_cast<const T*>(p.src[s]);
+      for (int c0 = 0; c0 < C; c0 += BK) {
+        // ---- A tile: 64 voxels x 16 channels; thread -> voxel tid/2, channels (tid%2)*8..+8
+        {
+          const int v = tid >> 1, cb = (tid & 1) * 8;
+          const int64_t iv = vin[v];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int ch = c0 + cb + q;
+            float x = 0.f;
+            if (iv >= 0 && ch < C) x = ld_f<T>(src + iv * C + ch);
+            As[cb + q][v] = x;
+          }
+        }
+        // ---- W tile: 16 reduced channels x 64 produced channels
+        for (int e = tid; e < BK * BN; e += TH) {
+          const int kk = e / BN, nn = e % BN;
+          const int ch = c0 + kk;
+          int n = n0 + nn;
+          float x = 0.f;
+          if (ch < C && n < p.n_total) {
+            int j = 0;
+            if (p.nout > 1 && n >= p.out_c[0]) { n -= p.out_c[0]; j = 1; }
+            x = p.w[j][tap * p.st[j] + (int64_t)(r_base + ch) * p.sr[j] + (int64_t)n * p.so[j]];
+          }
+          Ws[kk][nn] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          float av[4], wv[8];
+          const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 8 + 4]);
+          wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+          wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+      r_base += C;
+    }
+  }
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= p.out_vox) continue;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      int n = n0 + tx * 8 + jj;
+      if (n >= p.n_total) continue;
+      int j = 0;
+      if (p.nout > 1 && n >= p.out_c[0]) { n -= p.out_c[0]; j = 1; }
+      float v = acc[i][jj];
+      if (p.bias[j]) v += p.bias[j][n];
+      T* dst = reinterpret_cast<T*>(p.out[j]) + m * p.out_c[j] + n;
+      if (p.accumulate) v += ld_f<T>(dst);
+      st_f<T>(dst, v);
+    }
+  }
+}
+
+// ---- weight gradient ----------------------------------------------------------------------
+// dW[tap, r, n] += sum_o G(o, tap)[r] * dY[o, n];  block = (64 r x 64 n) tile of one tap over a
+// slab of output voxels, fp32 atomics into dW.
+constexpr int WV = 16;  // voxels per step
+
+struct WgradParams {
+  SimtParams g;          // geometry + gathered tensors (out/w unused)
+  const void* dout;      // [out_vox][Cn]
+  int Cn;
+  int src_index;         // which gathered tensor this launch differentiates
+  int r_base;            // its offset in the concatenation
+  float* dw;
+  int64_t st, sr, so;
+  int64_t vox_per_block;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TH) wgrad_simt_kernel(const __grid_constant__ WgradParams q) {
+  const SimtParams& p = q.g;
+  __shared__ float Gs[WV][BM + 4];
+  __shared__ float Ys[WV][BN + 4];
+  __shared__ int64_t vin[WV];
+
+  const int tid = threadIdx.x;
+  const int C = p.src_c[q.src_index];
+  const T* src = reinterpret_cast<const T*>(p.src[q.src_index]);
+  const T* dy = reinterpret_cast<const T*>(q.dout);
+  const int r_tiles = (C + BM - 1) / BM;
+  const int r0 = (blockIdx.x % r_tiles) * BM;
+  const int n0 = (blockIdx.x / r_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+  const int64_t v_begin = (int64_t)blockIdx.z * q.vox_per_block;
+  const int64_t v_end = min(v_begin + q.vox_per_block, p.out_vox);
+  const int tx = tid % 8, ty = tid / 8;
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int64_t v0 = v_begin; v0 < v_end; v0 += WV) {
+    if (tid < WV) {
+      int64_t m = v0 + tid;
+      int64_t iv = -1;
+      if (m < v_end) {
+        int w = (int)(m % p.Wo); m /= p.Wo;
+        int h = (int)(m % p.Ho); m /= p.Ho;
+        int d = (int)(m % p.Do); m /= p.Do;
+        iv = gather_index(p, (int)m, d, h, w, a, b, c);
+      }
+      vin[tid] = iv;
+    }
+    __syncthreads();
+    for (int e = tid; e < WV * BM; e += TH) {
+      const int vv = e / BM, rr = e % BM;
+      const int64_t iv = vin[vv];
+      float x = 0.f;
+      if (iv >= 0 && r0 + rr < C) x = ld_f<T>(src + iv * C + r0 + rr);
+      Gs[vv][rr] = x;
+    }
+    for (int e = tid; e < WV * BN; e += TH) {
+      const int vv = e / BN, nn = e % BN;
+      const int64_t m = v0 + vv;
+      float x = 0.f;
+      if (m < v_end && n0 + nn < q.Cn && vin[vv] >= 0) x = ld_f<T>(dy + m * q.Cn + n0 + nn);
+      Ys[vv][nn] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int vv = 0; vv < WV; ++vv) {
+      float gv[4], yv[8];
+      const float4 g4 = *reinterpret_cast<const float4*>(&Gs[vv][ty * 4]);
+      gv[0] = g4.x; gv[1] = g4.y; gv[2] = g4.z; gv[3] = g4.w;
+      const float4 y0 = *reinterpret_cast<const float4*>(&Ys[vv][tx * 8]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&Ys[vv][tx * 8 + 4]);
+      yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w;
+      yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], yv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= C) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx * 8 + j;
+      if (n >= q.Cn) continue;
+      if (acc[i][j] != 0.f)
+        atomicAdd(q.dw + tap * q.st + (int64_t)(q.r_base + r) * q.sr + (int64_t)n * q.so, acc[i][j]);
+    }
+  }
+}
+
+// column sums: dbias[n] += sum_rows x[row][n]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t rows, int C, int64_t rows_per_block,
+                              float* __restrict__ out) {
+  extern __shared__ float sacc[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(r_begin + rows_per_block, rows);
+  if (C <= (int)blockDim.x && blockDim.x % C == 0) {
+    const int ch = threadIdx.x % C;
+    const int lanes = blockDim.x / C;
+    float a = 0.f;
+    for (int64_t r = r_begin + threadIdx.x / C; r < r_end; r += lanes) a += ld_f<T>(x + r * C + ch);
+    atomicAdd(&sacc[ch], a);
+  } else {
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float a = 0.f;
+      for (int64_t r = r_begin; r < r_end; ++r) a += ld_f<T>(x + r * C + ch);
+      sacc[ch] += a;  // each channel owned by exactly one thread on this path
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, sacc[i]);
+}
+
+int fill_params(const m1_conv_desc* d, SimtParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->mode = d->mode;
+  p->batch = d->batch;
+  p->Di = d->in_dhw[0]; p->Hi = d->in_dhw[1]; p->Wi = d->in_dhw[2];
+  p->Do = d->out_dhw[0]; p->Ho = d->out_dhw[1]; p->Wo = d->out_dhw[2];
+  p->kd = d->kernel[0]; p->kh = d->kernel[1]; p->kw = d->kernel[2];
+  p->sd = d->stride[0]; p->sh = d->stride[1]; p->sw = d->stride[2];
+  p->pd = d->pad[0]; p->ph = d->pad[1]; p->pw = d->pad[2];
+  M1_CHECK(d->nsrc >= 1 && d->nsrc <= M1_MAX_SRC, "conv: nsrc %d out of range", d->nsrc);
+  M1_CHECK(d->nout >= 1 && d->nout <= M1_MAX_OUT, "conv: nout %d out of range", d->nout);
+  p->nsrc = d->nsrc;
+  p->nout = d->nout;
+  p->n_total = 0;
+  for (int s = 0; s < d->nsrc; ++s) p->src_c[s] = d->src_c[s];
+  for (int j = 0; j < d->nout; ++j) {
+    p->out_c[j] = d->out_c[j];
+    p->st[j] = d->w_stride_tap[j]; p->sr[j] = d->w_stride_red[j]; p->so[j] = d->w_stride_out[j];
+    p->n_total += d->out_c[j];
+  }
+  p->accumulate = d->accumulate;
+  p->out_vox = (int64_t)d->batch * p->Do * p->Ho * p->Wo;
+  return 0;
+}
+
+}  // namespace
+
+int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
+                   const float* const* w, const float* const* bias, void* const* outs,
+                   cudaStream_t st) {
+  SimtParams p;
+  if (fill_params(d, &p)) return 1;
+  for (int s = 0; s < d->nsrc; ++s) p.src[s] = srcs[s];
+  for (int j = 0; j < d->nout; ++j) {
+    p.out[j] = outs[j];
+    p.w[j] = w[j];
+    p.bias[j] = bias ? bias[j] : nullptr;
+  }
+  dim3 grid((unsigned)cdiv64(p.out_vox, BM), (unsigned)((p.n_total + BN - 1) / BN));
+  if (d->act_dtype == M1_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, TH, 0, st>>>(p);
+  else conv_simt_kernel<float><<<grid, TH, 0, st>>>(p);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
+                               const void* const* douts, float* const* dw, float* const* dbias,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  WgradParams q;
+  memset(&q, 0, sizeof(q));
+  if (fill_params(d, &q.g)) return 1;
+  for (int s = 0; s < d->nsrc; ++s) q.g.src[s] = srcs[s];
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  const int64_t out_vox = q.g.out_vox;
+  for (int j = 0; j < d->nout; ++j) {
+    q.dout = douts[j];
+    q.Cn = d->out_c[j];
+    q.dw = dw[j];
+    q.st = d->w_stride_tap[j]; q.sr = d->w_stride_red[j]; q.so = d->w_stride_out[j];
+    int r_base = 0;
+    for (int s = 0; s < d->nsrc; ++s) {
+      q.src_index = s;
+      q.r_base = r_base;
+      const int C = d->src_c[s];
+      const int tiles = ((C + BM - 1) / BM) * ((q.Cn + BN - 1) / BN);
+      // split the voxel reduction so that the launch has ~8 blocks per SM
+      int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, tiles * taps));
+      int64_t vpb = cdiv64(out_vox, want);
+      vpb = std::max<int64_t>(256, cdiv64(vpb, WV) * WV);
+      q.vox_per_block = vpb;
+      dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)cdiv64(out_vox, vpb));
+      if (d->act_dtype == M1_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, TH, 0, st>>>(q);
+      else wgrad_simt_kernel<float><<<grid, TH, 0, st>>>(q);
+      M1_LAUNCH_CHECK(ctx);
+      r_base += C;
+    }
+    if (dbias && dbias[j]) {
+      const int C = q.Cn;
+      const int64_t rpb = std::max<int64_t>(64, cdiv64(out_vox, (int64_t)ctx->num_sms * 4));
+      const unsigned blocks = (unsigned)cdiv64(out_vox, rpb);
+      if (d->act_dtype == M1_BF16)
+        colsum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(douts[j]), out_vox, C, rpb, dbias[j]);
+      else
+        colsum_kernel<float><<<blocks, 256, C * sizeof(float), st>>>(
+            reinterpret_cast<const float*>(douts[j]), out_vox, C, rpb, dbias[j]);
+      M1_LAUNCH_CHECK(ctx);
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,527 @@
+// conv_tc.cu — K1/K2: stride-1 3-D convolution (and the data gradient of one) as an implicit
+// GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged
+// by TMA (cp.async.bulk.tensor) straight from the NDHWC activation tensors.
+//
+// Replaces tf.keras.layers.Conv3D at R:network_blocks.py:37-46 (conv1||conv4, conv2, conv3 of
+// every SEResNetBottleNeck), R:networks.py:472 and the Conv3DBackpropInputV2 of their autodiff.
+//
+// GEMM view   D[M = 128 output voxels, N = produced channels] += A[M, K] * B[N, K]^T
+//   M tile  = a (bd x bh x bw) brick of output voxels of ONE volume (<= 128 voxels)
+//   K       = taps x gathered channels, walked as "k-steps" of ck in {16,32,64} channels of one
+//             tap of one gathered tensor (the channel concatenation of the reference is never
+//             materialised: every gathered tensor has its own tensor map)
+//   A tile  = one 5-D TMA box (ck, bw, bh, bd, 1) whose corner is shifted by the tap offset;
+//             out-of-volume voxels are zero-filled by TMA == TF "SAME" padding
+//   B tile  = one 3-D TMA box (ck, n_tile, 1) of the bf16 K-major weight pack [tap][N][K]
+// Both land in shared memory in the canonical K-major swizzled UMMA layout (rows of ck*2 bytes,
+// 8-row swizzle atoms), so one tcgen05.mma per 16 channels consumes them with no data movement
+// by threads.  One CTA = one M tile x one N tile; several CTAs are co-resident per SM so that the
+// epilogue of one overlaps the main loop of another.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct TcParams {
+  CUtensorMap tmA[M1_MAX_SRC];
+  CUtensorMap tmB;
+  int nsrc;
+  int src_chunks[M1_MAX_SRC];  // channels / ck of each gathered tensor
+  int src_koff[M1_MAX_SRC];    // first K index of the tensor inside a weight-pack row
+  int kd, kh, kw;              // taps
+  int od, oh, ow;              // gather offset of tap 0 (per dim)
+  int sgn;                     // +1: in = o + off0 + k ; -1: in = o + off0 - k
+  int bd, bh, bw;              // brick
+  int td, th, tw;              // bricks per dim
+  int Do, Ho, Wo;
+  int n_tile;
+  int n_total;                 // real produced channels (the weight pack is zero-padded to 16)
+  int ck;
+  int group, stages;
+  uint32_t a_alloc, slot_bytes;
+  uint32_t tx_per_kstep;
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  uint32_t desc_hi;            // upper 32 bits of the UMMA shared-memory descriptors
+  int nout;
+  void* out[M1_MAX_OUT];
+  int out_c[M1_MAX_OUT];
+  const float* bias[M1_MAX_OUT];
+  int out_bf16;
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // barriers + TMEM slot live in the first 1 KiB after alignment; tiles follow, 1 KiB aligned
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_base;                 // stages x 8 B
+  const uint32_t bar_empty = smem_base + 8u * 16u;     // stages x 8 B (<= 16 stages)
+  const uint32_t bar_accum = smem_base + 8u * 32u;
+  const uint32_t tmem_slot = smem_base + 8u * 33u;
+  const uint32_t tiles = smem_base + 1024u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates -----------------------------------------------------------------
+  int t = blockIdx.x;
+  const int tw_i = t % p.tw; t /= p.tw;
+  const int th_i = t % p.th; t /= p.th;
+  const int td_i = t % p.td; t /= p.td;
+  const int n_img = t;
+  const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  // ---- one-time setup -------------------------------------------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     tmem_slot),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + 8u * 33u);
+
+  int total_chunks = 0;
+  for (int s = 0; s < p.nsrc; ++s) total_chunks += p.src_chunks[s];
+  const int taps = p.kd * p.kh * p.kw;
+  const int ksteps = taps * total_chunks;
+  const int nstage_iters = (ksteps + p.group - 1) / p.group;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int tap = 0, src = 0, chunk = 0;
+      int kd_i = 0, kh_i = 0, kw_i = 0;
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < nstage_iters; ++it) {
+        const int g = min(p.group, ksteps - it * p.group);
+        mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+        const uint32_t full = bar_full + 8u * stage;
+        mbar_expect_tx(full, p.tx_per_kstep * (uint32_t)g);
+        for (int j = 0; j < g; ++j) {
+          const uint32_t slot = tiles + (stage * p.group + j) * p.slot_bytes;
+          const int c_in = chunk * p.ck;
+          tma_load_5d(slot, &p.tmA[src], full, c_in, w0 + p.ow + p.sgn * kw_i,
+                      h0 + p.oh + p.sgn * kh_i, d0 + p.od + p.sgn * kd_i, n_img);
+          tma_load_3d(slot + p.a_alloc, &p.tmB, full, p.src_koff[src] + c_in, n0, tap);
+          // advance (chunk, src, tap)
+          if (++chunk == p.src_chunks[src]) {
+            chunk = 0;
+            if (++src == p.nsrc) {
+              src = 0;
+              ++tap;
+              if (++kw_i == p.kw) {
+                kw_i = 0;
+                if (++kh_i == p.kh) { kh_i = 0; ++kd_i; }
+              }
+            }
+          }
+        }
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      uint32_t stage = 0, phase = 0;
+      const uint64_t hi = (uint64_t)p.desc_hi << 32;
+      const int k16s = p.ck / 16;
+      uint32_t acc = 0;
+      for (int it = 0; it < nstage_iters; ++it) {
+        const int g = min(p.group, ksteps - it * p.group);
+        mbar_wait(bar_full + 8u * stage, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int j = 0; j < g; ++j) {
+          const uint32_t slot = tiles + (stage * p.group + j) * p.slot_bytes;
+          const uint64_t a_lo = (uint64_t)((slot >> 4) & 0x3FFFu);
+          const uint64_t b_lo = (uint64_t)(((slot + p.a_alloc) >> 4) & 0x3FFFu);
+          for (int k = 0; k < k16s; ++k) {
+            // 16 channels = 32 bytes further along the swizzled row: +2 in 16-byte units
+            umma_bf16(tmem_base, hi | (a_lo + 2u * k), hi | (b_lo + 2u * k), p.idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bar_empty + 8u * stage);
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_accum);
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: TMEM -> registers -> (+bias) -> global, all four warps =====
+  mbar_wait(bar_accum, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int r = threadIdx.x;  // row of the tile == TMEM lane
+    const int lw = r % p.bw;
+    const int lh = (r / p.bw) % p.bh;
+    const int ld = r / (p.bw * p.bh);
+    const int d = d0 + ld, h = h0 + lh, w = w0 + lw;
+    const bool valid = (ld < p.bd) && d < p.Do && h < p.Ho && w < p.Wo;
+    const int64_t vox = (((int64_t)n_img * p.Do + d) * p.Ho + h) * p.Wo + w;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int j = 0; j < p.n_tile; j += 8) {
+      uint32_t v[8];
+      tmem_ld8(lane_addr + (uint32_t)j, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      int gc = n0 + j;
+      if (!valid || gc >= p.n_total) continue;
+      int o = 0;
+      if (p.nout > 1 && gc >= p.out_c[0]) { gc -= p.out_c[0]; o = 1; }
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+      if (p.bias[o] != nullptr) {
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias[o] + gc);
+        const float4 b1 = *reinterpret_cast<const float4*>(p.bias[o] + gc + 4);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      const int64_t off = vox * p.out_c[o] + gc;
+      if (p.out_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[o]) + off;
+        if (p.accumulate) {
+          uint4 old = *reinterpret_cast<const uint4*>(dst);
+          const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] += __low2float(ob[i]);
+            f[2 * i + 1] += __high2float(ob[i]);
+          }
+        }
+        uint4 pk;
+        __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pb[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        *reinterpret_cast<uint4*>(dst) = pk;
+      } else {
+        float* dst = reinterpret_cast<float*>(p.out[o]) + off;
+        if (p.accumulate) {
+          const float4 o0 = *reinterpret_cast<const float4*>(dst);
+          const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
+          f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
+          f[4] += o1.x; f[5] += o1.y; f[6] += o1.z; f[7] += o1.w;
+        }
+        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// fp32 master weights -> bf16 [tap][n_total][k_total]
+__global__ void pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                    int n0c, int n_real, int n_total, int k_total, int taps, int64_t st0,
+                                    int64_t sr0, int64_t so0, int64_t st1, int64_t sr1,
+                                    int64_t so1, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)taps * n_total * k_total;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % k_total);
+    const int n = (int)((i / k_total) % n_total);
+    const int tap = (int)(i / ((int64_t)k_total * n_total));
+    float v = 0.f;
+    if (n < n0c) v = w0[tap * st0 + r * sr0 + n * so0];
+    else if (n < n_real) v = w1[tap * st1 + r * sr1 + (n - n0c) * so1];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Plan {
+  int ck, n_real, n_total, k_total, n_tile, n_tiles;   // n_total = n_real padded to 16
+  int bd, bh, bw, td, th, tw;
+  int group, stages;
+  uint32_t a_alloc, b_alloc, slot_bytes, smem_bytes, tmem_cols;
+};
+
+bool make_plan(const m1_conv_desc* d, Plan* pl) {
+  if (d->act_dtype != M1_BF16) return false;
+  for (int i = 0; i < 3; ++i) {
+    if (d->stride[i] != 1) return false;
+    if (d->in_dhw[i] != d->out_dhw[i]) return false;
+  }
+  if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
+  int ck = 64, k_total = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const int c = d->src_c[s];
+    if (c % 16) return false;
+    while (c % ck) ck >>= 1;
+    k_total += c;
+  }
+  int n_total = 0;
+  for (int j = 0; j < d->nout; ++j) {
+    if (d->out_c[j] % 8) return false;
+    n_total += d->out_c[j];
+  }
+  const int n_real = n_total;
+  n_total = (n_total + 15) & ~15;
+  // N tile: largest divisor of n_total that is a multiple of 16 and <= 256
+  int n_tile = 0;
+  for (int c = 256; c >= 16; c -= 16)
+    if (n_total % c == 0) { n_tile = c; break; }
+  if (!n_tile) return false;
+  // brick: maximise useful voxels / 128 over all (bd,bh,bw) with bd*bh*bw <= 128
+  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
+  double best = -1;
+  int bbd = 1, bbh = 1, bbw = 1;
+  for (int bd = 1; bd <= 128 && bd <= D; ++bd)
+    for (int bh = 1; bd * bh <= 128 && bh <= H; ++bh) {
+      int bw = 128 / (bd * bh);
+      if (bw > W) bw = W;
+      if (bw < 1) continue;
+      const int64_t tiles = (int64_t)((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
+      const double eff = (double)D * H * W / (128.0 * tiles);
+      // prefer wide bricks (longer contiguous runs) on ties
+      const double score = eff + 1e-6 * bw;
+      if (score > best) { best = score; bbd = bd; bbh = bh; bbw = bw; }
+    }
+  pl->ck = ck; pl->n_real = n_real; pl->n_total = n_total; pl->k_total = k_total; pl->n_tile = n_tile;
+  pl->n_tiles = n_total / n_tile;
+  pl->bd = bbd; pl->bh = bbh; pl->bw = bbw;
+  pl->td = (D + bbd - 1) / bbd; pl->th = (H + bbh - 1) / bbh; pl->tw = (W + bbw - 1) / bbw;
+  pl->a_alloc = 128u * ck * 2u;
+  pl->b_alloc = ((uint32_t)n_tile * ck * 2u + 1023u) & ~1023u;
+  pl->slot_bytes = pl->a_alloc + pl->b_alloc;
+  uint32_t cols = 32;
+  while ((int)cols < n_tile) cols <<= 1;
+  pl->tmem_cols = cols;
+  // k-steps per stage: aim at >= 64 channels of work per barrier round trip
+  pl->group = 64 / ck;
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  const int ksteps = taps * (k_total / ck);
+  // co-residency target: as many CTAs/SM as TMEM allows (<=4), smem split accordingly
+  int ctas = 512 / (int)cols;
+  if (ctas > 4) ctas = 4;
+  const uint32_t budget = (227u * 1024u) / ctas - 2048u;
+  int stages = (int)(budget / (pl->slot_bytes * pl->group));
+  if (stages > 12) stages = 12;
+  const int iters = (ksteps + pl->group - 1) / pl->group;
+  if (stages > iters) stages = iters;
+  if (stages < 2) {
+    // not enough room at this co-residency: fall back to 1 CTA/SM
+    stages = (int)((227u * 1024u - 2048u) / (pl->slot_bytes * pl->group));
+    if (stages > 12) stages = 12;
+    if (stages > iters) stages = iters;
+    if (stages < 1) return false;
+  }
+  pl->stages = stages;
+  pl->smem_bytes = 2048u + (uint32_t)stages * pl->group * pl->slot_bytes;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int m1_conv3d_tc_supported(const m1_conv_desc* d) {
+  Plan pl;
+  return make_plan(d, &pl) ? 1 : 0;
+}
+
+extern "C" int64_t m1_conv3d_packed_bytes(const m1_conv_desc* d) {
+  Plan pl;
+  if (!make_plan(d, &pl)) return 0;
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  return (int64_t)taps * pl.n_total * pl.k_total * 2;
+}
+
+extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* const* w,
+                                      void* w_packed, void* stream) {
+  Plan pl;
+  M1_CHECK(make_plan(d, &pl), "m1_conv3d_pack_weights: launch not supported by the tcgen05 engine");
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  const int64_t total = (int64_t)taps * pl.n_total * pl.k_total;
+  const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 8);
+  const int j1 = d->nout > 1 ? 1 : 0;
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      w[0], w[j1], d->out_c[0], pl.n_real, pl.n_total, pl.k_total, taps, d->w_stride_tap[0],
+      d->w_stride_red[0], d->w_stride_out[0], d->w_stride_tap[j1], d->w_stride_red[j1],
+      d->w_stride_out[j1], reinterpret_cast<__nv_bfloat16*>(w_packed));
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
+                 const void* w_packed, const float* const* bias, void* const* outs,
+                 cudaStream_t st) {
+  Plan pl;
+  M1_CHECK(make_plan(d, &pl), "m1_conv3d: launch not supported by the tcgen05 engine");
+  M1_CHECK(w_packed != nullptr, "m1_conv3d: tcgen05 engine needs the bf16 weight pack");
+  M1_CHECK(ctx->encode_tiled != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+
+  static_assert(sizeof(TcParams) < 4000, "kernel parameter block too large");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const CUtensorMapSwizzle swz = pl.ck == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : pl.ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
+  int koff = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const cuuint64_t C = (cuuint64_t)d->src_c[s];
+    cuuint64_t dims[5] = {C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {C * 2, C * 2 * W, C * 2 * W * H, C * 2 * W * H * D};
+    cuuint32_t box[5] = {(cuuint32_t)pl.ck, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh,
+                         (cuuint32_t)pl.bd, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d: gathered tensor %d not 16-byte aligned", s);
+    CUresult r = encode(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]),
+                        dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, src %d) failed: %d", s, (int)r);
+    p.src_chunks[s] = d->src_c[s] / pl.ck;
+    p.src_koff[s] = koff;
+    koff += d->src_c[s];
+  }
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)pl.k_total, (cuuint64_t)pl.n_total, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)pl.k_total * 2, (cuuint64_t)pl.k_total * 2 * pl.n_total};
+    cuuint32_t box[3] = {(cuuint32_t)pl.ck, (cuuint32_t)pl.n_tile, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed),
+                        dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  p.nsrc = d->nsrc;
+  p.kd = d->kernel[0]; p.kh = d->kernel[1]; p.kw = d->kernel[2];
+  if (d->mode == M1_CONV_FWD) {
+    p.sgn = 1; p.od = -d->pad[0]; p.oh = -d->pad[1]; p.ow = -d->pad[2];
+  } else {
+    p.sgn = -1; p.od = d->pad[0]; p.oh = d->pad[1]; p.ow = d->pad[2];
+  }
+  p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw;
+  p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
+  p.Do = D; p.Ho = H; p.Wo = W;
+  p.n_tile = pl.n_tile;
+  p.n_total = pl.n_real;
+  p.ck = pl.ck;
+  p.group = pl.group;
+  p.stages = pl.stages;
+  p.a_alloc = pl.a_alloc;
+  p.slot_bytes = pl.slot_bytes;
+  p.tx_per_kstep = (uint32_t)(pl.bd * pl.bh * pl.bw) * pl.ck * 2u + (uint32_t)pl.n_tile * pl.ck * 2u;
+  p.tmem_cols = pl.tmem_cols;
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.n_tile >> 3) << 17) |
+            ((128u >> 4) << 24);
+  // smem descriptor high word: SBO = 8 rows * ck*2 bytes (>>4) at [32,46), version 1 at [46,48),
+  // layout type at [61,64): 2 = SW128, 4 = SW64, 6 = SW32; LBO (unused for swizzled K-major) = 1
+  const uint32_t sbo = (8u * pl.ck * 2u) >> 4;
+  const uint32_t layout = pl.ck == 64 ? 2u : pl.ck == 32 ? 4u : 6u;
+  p.desc_hi = sbo | (1u << 14) | (layout << 29);
+  p.nout = d->nout;
+  for (int j = 0; j < d->nout; ++j) {
+    p.out[j] = outs[j];
+    p.out_c[j] = d->out_c[j];
+    p.bias[j] = bias ? bias[j] : nullptr;
+    M1_CHECK(((uintptr_t)outs[j] & 15) == 0, "m1_conv3d: produced tensor %d not 16-byte aligned", j);
+  }
+  p.out_bf16 = 1;
+  p.accumulate = d->accumulate;
+
+  static int smem_set = 0;
+  if (smem_set < (int)pl.smem_bytes) {
+    M1_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  dim3 grid((unsigned)(d->batch * pl.td * pl.th * pl.tw), (unsigned)pl.n_tiles);
+  conv_tc_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}

@@ -1,0 +1,172 @@
+"""K1/K2/K3 parity: the CUDA convolution engines against the CPU oracle (tests may import oracle/)."""
+import pytest
+import torch
+
+from oracle import m1_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(batch, dhw, cins, couts, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn((batch, *dhw, c), generator=g) for c in cins]
+    cin = sum(cins)
+    ws = [torch.randn((*k, cin, co), generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5 for co in couts]
+    bs = [torch.randn((co,), generator=g) * 0.1 for co in couts]
+    return xs, ws, bs
+
+
+def _run_fwd(ctx, xs, ws, bs, k, s, dtype, engine):
+    from m1b200 import ops, _lib
+    dev = 'cuda'
+    batch, dhw = xs[0].shape[0], xs[0].shape[1:4]
+    geo = [ops.same_pads(dhw[i], k[i], s[i]) for i in range(3)]
+    out_dhw = [g[0] for g in geo]
+    pad = [g[1] for g in geo]
+    cin = sum(x.shape[-1] for x in xs)
+    code = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+    d = ops.conv_desc(_lib.CONV_FWD, batch, dhw, out_dhw, k, s, pad, [x.shape[-1] for x in xs],
+                      [w.shape[-1] for w in ws], [(cin * w.shape[-1], w.shape[-1], 1) for w in ws],
+                      act_dtype=code, engine=engine)
+    xd = [x.to(dev, dtype).contiguous() for x in xs]
+    wd = [w.to(dev).contiguous() for w in ws]
+    bd = [b.to(dev).contiguous() for b in bs]
+    outs = [torch.full((batch, *out_dhw, w.shape[-1]), float('nan'), device=dev, dtype=dtype) for w in ws]
+    packed = None
+    if engine == _lib.ENGINE_TCGEN05:
+        assert ops.conv3d_tc_supported(d)
+        packed = ops.conv3d_pack_weights(ctx, d, wd)
+    ops.conv3d(ctx, d, xd, wd, bd, outs, packed)
+    torch.cuda.synchronize()
+    return [o.float().cpu() for o in outs]
+
+
+def _ref_fwd(xs, ws, bs, s, dtype):
+    x = torch.cat(xs, -1)
+    if dtype == torch.bfloat16:  # the engine sees bf16-rounded operands
+        x = x.bfloat16().float()
+        ws = [w.bfloat16().float() for w in ws]
+    return [O.conv3d_same(x.double(), w.double(), b.double(), s).float() for w, b in zip(ws, bs)]
+
+
+SIMT_CASES = [
+    # dhw, cins, couts, kernel, stride
+    ((4, 10, 12), [3], [8], (1, 3, 3), (1, 1, 1)),
+    ((4, 10, 12), [5, 7], [6, 9], (3, 3, 3), (1, 1, 1)),
+    ((4, 10, 12), [8], [16], (1, 3, 3), (1, 2, 2)),
+    ((6, 10, 12), [8], [16], (3, 3, 3), (2, 2, 2)),
+    ((5, 9, 11), [4], [4], (3, 3, 3), (2, 2, 2)),       # odd sizes: SAME pads (1,1)
+    ((4, 8, 8), [6], [6], (2, 2, 2), (2, 2, 2)),        # attention theta conv with sub-sampling
+    ((4, 8, 8), [16], [2], (1, 1, 1), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("dhw,cins,couts,k,s", SIMT_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_fwd_simt(ctx, dhw, cins, couts, k, s, dtype):
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k)
+    got = _run_fwd(ctx, xs, ws, bs, k, s, dtype, _lib.ENGINE_SIMT)
+    ref = _ref_fwd(xs, ws, bs, s, dtype)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape
+        assert torch.isfinite(g).all()
+        assert (g - r).abs().max().item() < tol, (g - r).abs().max().item()
+
+
+TC_CASES = [
+    ((4, 16, 16), [64], [32], (1, 3, 3)),               # one source, SW128, exact bricks
+    ((4, 16, 16), [64], [16, 64], (3, 3, 3)),           # fused conv1||conv4 split
+    ((6, 20, 20), [128, 64], [32, 128], (3, 3, 3)),     # virtual concat, ragged bricks (20 % 8 != 0)
+    ((4, 16, 32), [32, 32, 32], [8, 32], (1, 3, 3)),    # 32-channel sources -> SW64 k-steps
+    ((4, 16, 16), [16, 48], [16], (3, 3, 3)),           # 16-channel granularity -> SW32
+    ((5, 10, 10), [128], [64, 256], (3, 3, 3)),         # N = 320 -> two N tiles; res4-like tiny grid
+    ((2, 8, 16), [64], [64], (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("dhw,cins,couts,k", TC_CASES)
+def test_conv_fwd_tcgen05(ctx, dhw, cins, couts, k):
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k, seed=1)
+    got = _run_fwd(ctx, xs, ws, bs, k, (1, 1, 1), torch.bfloat16, _lib.ENGINE_TCGEN05)
+    ref = _ref_fwd(xs, ws, bs, (1, 1, 1), torch.bfloat16)
+    for g, r in zip(got, ref):
+        assert torch.isfinite(g).all(), "non-finite output (unwritten voxels?)"
+        err = (g - r).abs().max().item()
+        assert err < 2e-2, err
+
+
+def _run_transposed(ctx, x, w, b, k, s, dtype, engine=None):
+    """Conv3DTranspose forward: gather mode TRANSPOSED, Keras kernel (kd,kh,kw,Cout,Cin)."""
+    from m1b200 import ops, _lib
+    dev = 'cuda'
+    batch, in_dhw = x.shape[0], x.shape[1:4]
+    out_dhw = [in_dhw[i] * s[i] for i in range(3)]
+    pad = [ops.same_pads(out_dhw[i], k[i], s[i])[1] for i in range(3)]
+    cout, cin = w.shape[-2], w.shape[-1]
+    code = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+    d = ops.conv_desc(_lib.CONV_TRANSPOSED, batch, in_dhw, out_dhw, k, s, pad, [cin], [cout],
+                      [(cout * cin, 1, cin)], act_dtype=code,
+                      engine=_lib.ENGINE_SIMT if engine is None else engine)
+    out = torch.full((batch, *out_dhw, cout), float('nan'), device=dev, dtype=dtype)
+    ops.conv3d(ctx, d, [x.to(dev, dtype).contiguous()], [w.to(dev).contiguous()],
+               [b.to(dev).contiguous()], [out])
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize("dhw,k,s", [((3, 5, 6), (3, 3, 3), (2, 2, 2)), ((4, 5, 6), (3, 3, 3), (1, 2, 2)),
+                                     ((4, 5, 6), (1, 3, 3), (1, 2, 2)), ((3, 4, 4), (3, 3, 3), (1, 1, 1))])
+def test_conv_transpose_simt(ctx, dhw, k, s):
+    g = torch.Generator().manual_seed(3)
+    cin, cout = 6, 5
+    x = torch.randn((2, *dhw, cin), generator=g)
+    w = torch.randn((*k, cout, cin), generator=g) * 0.2
+    b = torch.randn((cout,), generator=g) * 0.1
+    got = _run_transposed(ctx, x, w, b, k, s, torch.float32)
+    ref = O.conv3d_transpose_same(x.double(), w.double(), b.double(), s).float()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("k,s", [((3, 3, 3), (1, 1, 1)), ((3, 3, 3), (2, 2, 2)), ((1, 3, 3), (1, 2, 2))])
+def test_conv_wgrad_dgrad_simt(ctx, k, s):
+    """dgrad (TRANSPOSED gather of dy) and wgrad against autograd of the oracle conv."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(4)
+    dhw, cins, cout = (4, 6, 8), [5, 4], 7
+    xs = [torch.randn((2, *dhw, c), generator=g, dtype=torch.float64, requires_grad=True) for c in cins]
+    cin = sum(cins)
+    w = (torch.randn((*k, cin, cout), generator=g, dtype=torch.float64) * 0.2).requires_grad_()
+    b = torch.zeros(cout, dtype=torch.float64, requires_grad=True)
+    y = O.conv3d_same(torch.cat(xs, -1), w, b, s)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    dev = 'cuda'
+    out_dhw = list(y.shape[1:4])
+    pad = [ops.same_pads(dhw[i], k[i], s[i])[1] for i in range(3)]
+    # wgrad
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, out_dhw, k, s, pad, cins, [cout], [(cin * cout, cout, 1)],
+                      act_dtype=_lib.F32, engine=_lib.ENGINE_SIMT)
+    dw = torch.zeros(w.shape, device=dev)
+    db = torch.zeros(cout, device=dev)
+    ops.conv3d_wgrad(ctx, d, [x.detach().float().to(dev).contiguous() for x in xs],
+                     [dy.float().to(dev).contiguous()], [dw], [db])
+    torch.cuda.synchronize()
+    assert (dw.cpu().double() - w.grad).abs().max().item() < 1e-3
+    assert (db.cpu().double() - b.grad).abs().max().item() < 1e-3
+    # dgrad per gathered tensor: produced = that tensor's channels, reduced = cout
+    off = 0
+    for x in xs:
+        c = x.shape[-1]
+        dd = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, out_dhw, dhw, k, s, pad, [cout], [c],
+                           [(cin * cout, 1, cout)], act_dtype=_lib.F32, engine=_lib.ENGINE_SIMT)
+        dx = torch.full(x.shape, float('nan'), device=dev)
+        wv = w.detach().float().to(dev).contiguous()
+        wslice = wv.view(-1)[off * cout:]  # first reduced... weights of channels [off, off+c)
+        ops.conv3d(ctx, dd, [dy.float().to(dev).contiguous()], [wslice], None, [dx])
+        torch.cuda.synchronize()
+        assert (dx.cpu().double() - x.grad).abs().max().item() < 1e-3
+        off += c

@@ -1,0 +1,230 @@
+"""Known-answer tests that pin the CPU oracle — the reference ships no tests, so
+these closed forms / identities are the only pins ("parity unpinned" by reference fixtures)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import m1_oracle as O
+
+README_CFG = dict(filters=(32, 64, 128, 256, 512),
+                  strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (2, 2, 2)),
+                  kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)))
+TINY = dict(filters=(8, 8, 16, 16, 32), strides=README_CFG['strides'], kernel_sizes=README_CFG['kernel_sizes'],
+            se_reduction=(4, 4, 4, 4, 4))
+
+
+def test_same_pads_tf_semantics():
+    assert O.same_pads(160, 3, 1) == (160, 1, 1)
+    assert O.same_pads(160, 3, 2) == (80, 0, 1)      # even input, k3 s2: (0,1)
+    assert O.same_pads(9, 3, 2) == (5, 1, 1)         # odd input
+    assert O.same_pads(20, 1, 1) == (20, 0, 0)
+    assert O.same_pads(8, 2, 2) == (4, 0, 0)
+
+
+@pytest.mark.parametrize("k,s", [((1, 3, 3), (1, 1, 1)), ((1, 3, 3), (1, 2, 2)), ((3, 3, 3), (1, 2, 2)),
+                                 ((3, 3, 3), (2, 2, 2)), ((3, 3, 3), (1, 1, 1))])
+def test_transpose_is_exact_adjoint(k, s):
+    """<conv_SAME(x), y> == <x, convT_SAME(y)> for every (kernel, stride) pair M1 uses."""
+    g = torch.Generator().manual_seed(0)
+    cin, cout = 3, 4
+    big = (4, 8, 6)
+    small = tuple(b // st for b, st in zip(big, s))
+    x = torch.randn((2, *big, cin), generator=g, dtype=torch.float64)
+    y = torch.randn((2, *small, cout), generator=g, dtype=torch.float64)
+    w = torch.randn((*k, cin, cout), generator=g, dtype=torch.float64)
+    lhs = (O.conv3d_same(x, w, None, s) * y).sum()
+    # the ConvT whose forward conv has kernel w: Keras ConvT layout (k, Cout_T=cin, Cin_T=cout) == w
+    rhs = (x * O.conv3d_transpose_same(y, w, None, s)).sum()
+    assert abs(lhs - rhs) < 1e-10 * max(1.0, abs(lhs))
+
+
+def test_transpose_not_pytorch_idiom():
+    """k3 s2 SAME ConvT keeps [0:2N] of the full scatter (drops the LAST element)."""
+    x = torch.zeros((1, 1, 1, 2, 1), dtype=torch.float64)
+    x[0, 0, 0, 0, 0] = 1.0
+    w = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64).view(1, 1, 3, 1, 1)
+    y = O.conv3d_transpose_same(x, w, None, (1, 1, 2))
+    assert y.flatten().tolist() == [1.0, 2.0, 3.0, 0.0]
+
+
+def test_instance_norm_moments_and_q6():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((2, 3, 5, 7, 4), generator=g, dtype=torch.float64) * 3 + 1
+    gamma = torch.tensor([1.0, 2.0, 0.5, -1.0], dtype=torch.float64)
+    beta = torch.tensor([0.0, 1.0, -2.0, 0.3], dtype=torch.float64)
+    y = O.instance_norm(x, gamma, beta)
+    var = x.var(dim=(1, 2, 3), unbiased=False)
+    assert torch.allclose(y.mean(dim=(1, 2, 3)), beta.expand(2, 4), atol=1e-12)       # Q6: GAP(IN(x)) == beta
+    assert torch.allclose(y.var(dim=(1, 2, 3), unbiased=False), gamma ** 2 * var / (var + 1e-3), atol=1e-10)
+
+
+def test_dropout_semantics():
+    x = torch.ones(1000, dtype=torch.float64)
+    u = torch.linspace(0, 1, 1001)[:-1].double()
+    y = O.dropout(x, 0.25, u)
+    assert (y[u < 0.25] == 0).all() and torch.allclose(y[u >= 0.25], torch.tensor(1 / 0.75, dtype=torch.float64))
+    assert O.dropout(x, 0.0, u) is x
+
+
+def test_kl_closed_form_matches_torch_distributions():
+    g = torch.Generator().manual_seed(2)
+    mq, mp = torch.randn((2, 3, 4, 5, 3), generator=g).double(), torch.randn((2, 3, 4, 5, 3), generator=g).double()
+    sq = torch.exp(torch.clamp(torch.randn(mq.shape, generator=g).double(), -0.1, 0.1))
+    sp = torch.exp(torch.clamp(torch.randn(mq.shape, generator=g).double(), -0.1, 0.1))
+    ours = O.kl_mvn_diag((mq, sq), (mp, sp))
+    D = torch.distributions
+    ref = D.kl_divergence(D.Independent(D.Normal(mq, sq), 1), D.Independent(D.Normal(mp, sp), 1))
+    assert torch.allclose(ours, ref, atol=1e-12)
+    assert O.kl_mvn_diag((mq, sq), (mq, sq)).abs().max() < 1e-14
+
+
+def test_focal_reduces_to_cross_entropy():
+    """gamma=0, alpha=1 -> categorical CE summed over voxels (train_model.py:91)."""
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((2, 2, 3, 4, 2), generator=g).double()
+    p = torch.softmax(logits, -1)
+    lab = (torch.rand((2, 2, 3, 4), generator=g) > 0.7).long()
+    y = torch.nn.functional.one_hot(lab, 2).double()
+    fl = O.focal_loss(y, p, alpha=(1.0, 1.0), gamma=0.0)
+    ce = torch.nn.functional.cross_entropy(logits.reshape(-1, 2), lab.reshape(-1), reduction='sum') / 2
+    assert abs(fl - ce) < 1e-9
+    assert O.focal_loss(y, y.clone(), (0.75, 0.25), 2.0) < 1e-10        # perfect prediction
+    p8 = torch.cat([p, p, p, p], -1)                                     # 4 identical heads -> same value
+    assert abs(O.focal_loss(y, p8, (0.75, 0.25), 2.0) - O.focal_loss(y, p, (0.75, 0.25), 2.0)) < 1e-12
+
+
+def test_decision_fusion_truth_table():
+    a = torch.tensor([0.0, 1.0, 0.2, 0.9], dtype=torch.float64)
+    b = torch.tensor([0.0, 1.0, 0.7, 0.1], dtype=torch.float64)
+    prior, ident = O.decision_fusion(a, b, 'identity')
+    assert torch.equal(prior[..., 1], a) and torch.equal(ident[..., 1], b)
+    _, nor = O.decision_fusion(a, b, 'noisy-or')
+    assert torch.allclose(nor[..., 1], 1 - (1 - a) * (1 - b))
+    _, bay = O.decision_fusion(a, b, 'bayes')
+    assert torch.allclose(bay[..., 1], (a * b + 1e-9) / (a * b + 1e-9 + (1 - a) * (1 - b)))
+    assert torch.allclose(bay.sum(-1), torch.ones(4, dtype=torch.float64))
+
+
+def _run_core(cfg, dims=(4, 16, 16), cin=3, **kw):
+    ps = O.ParamStore(dtype=torch.float32, seed=0)
+    x = torch.randn((1, *dims, cin), generator=torch.Generator().manual_seed(0))
+    noise = O.Noise(0, torch.float32)
+    return ps, O.m1core(ps, 'net', cfg, x, noise=noise, **kw)
+
+
+def test_summary_shapes_and_concat_widths_readme_config():
+    """M1Core.summary shape list (R:networks.py:761-782) for the README configuration."""
+    cfg = O.default_config(dense_skip=True, probabilistic=True, prob_latent_dims=(3, 2, 1, 0), **README_CFG)
+    ps = O.ParamStore(dtype=torch.float32)
+    x = torch.zeros((1, 4, 32, 32, 3))
+    out = O.m1core(ps, 'prior', cfg, x, noise=O.Noise(0, torch.float32), training=False)
+    assert out['summary_shapes'] == [(4, 32, 32, 32), (4, 16, 16, 64), (4, 8, 8, 128), (2, 4, 4, 256), (1, 2, 2, 512)]
+    assert out['concat_widths'] == [160, 256, 384, 512]
+    shp = {n: tuple(t.shape) for n, t in ps.p.items()}
+    assert shp['prior/sersp3/conv4/kernel'] == (3, 3, 3, 768, 256)
+    assert shp['prior/sersp2/conv4/kernel'] == (3, 3, 3, 512, 128)
+    assert shp['prior/sersp1/conv4/kernel'] == (1, 3, 3, 320, 64)
+    assert shp['prior/sersp0/conv4/kernel'] == (1, 3, 3, 192, 32)
+    assert shp['prior/dec_hi3/kernel'] == (3, 3, 3, 256, 515)
+    assert shp['prior/dec_hi1/kernel'] == (3, 3, 3, 64, 129)
+    # parameter counts of SURVEY.md §8c(12): prior full pass; the survey's 33 617 512 includes the three
+    # deep-supervision heads (130 + 258 + 514 = 902 parameters), which are dead in the reference (Q3)
+    assert ps.num_params(('kernel', 'bias', 'se_kernel', 'se_bias')) == 33617512 - 902
+    assert ps.num_params(('gamma', 'beta')) == 10624
+    cfg_ds = dict(cfg, deep_supervision=True)
+    ps_ds = O.ParamStore(dtype=torch.float32)
+    O.m1core(ps_ds, 'prior', cfg_ds, x, noise=O.Noise(0, torch.float32), training=False)
+    assert ps_ds.num_params(('kernel', 'bias', 'se_kernel', 'se_bias')) == 33617512
+
+
+def test_param_count_deterministic_cfg1():
+    cfg = O.default_config(**README_CFG)
+    ps = O.ParamStore(dtype=torch.float32)
+    O.m1_deterministic(ps, cfg, torch.zeros((1, 4, 32, 32, 3)), O.Noise(0, torch.float32), training=False)
+    assert ps.num_params(('kernel', 'bias', 'se_kernel', 'se_bias')) == 17517642
+
+
+def test_partial_pass_is_prefix_of_full_pass():
+    """The Keras-pruned partial pass yields the same latent distributions as the full pass and
+    creates only the live layers."""
+    cfg = O.default_config(dense_skip=True, probabilistic=True, prob_latent_dims=(3, 2, 1, 0),
+                           dropout_mode='monte-carlo', **TINY)
+    ps = O.ParamStore(dtype=torch.float64, seed=1)
+    x = torch.randn((2, 4, 16, 16, 3), generator=torch.Generator().manual_seed(5)).double()
+    noise = O.Noise(3)
+    full = O.m1core(ps, 'n', cfg, x, noise=noise, pass_name='a')
+    names_full = set(ps.p)
+    ps2 = O.ParamStore(dtype=torch.float64, seed=1)
+    part = O.m1core(ps2, 'n', cfg, x, noise=noise, pass_name='a', stop='latents')
+    for (m1, s1), (m2, s2) in zip(full['prob_distributions'], part['prob_distributions']):
+        assert torch.equal(m1, m2) and torch.equal(s1, s2)
+    assert len(part['prob_distributions']) == 3
+    dead = names_full - set(ps2.p)
+    for layer in ('att0', 'att1', 'sersd2', 'sersd1', 'sersd0', 'convtd1', 'convtd0', 'sersp1', 'sersp0',
+                  'logits', 'dec_hi1', 'dec_hi0', 'convtd3_up2', 'convtd2_up1'):
+        assert any(('/' + layer + '/') in d for d in dead), layer
+    for layer in ('att3', 'att2', 'convtd3', 'convtd3_up1', 'sersd3', 'convtd2', 'dec_hi3', 'sersp3',
+                  'dec_hi2', 'sersp2', 'mu_logsig1'):
+        assert any(('/' + layer + '/') in d for d in ps2.p), layer
+
+
+def test_latent_modes_and_q3_q4():
+    cfg = O.default_config(dense_skip=True, probabilistic=True, deep_supervision=True,
+                           prob_latent_dims=(3, 2, 1, 0), dropout_mode='monte-carlo', **TINY)
+    ps = O.ParamStore(dtype=torch.float64, seed=2)
+    x, y = O.synthetic_batch(2, (4, 16, 16), dtype=torch.float64)
+    noise = O.Noise(7)
+    out = O.m1_probabilistic(ps, cfg, x, noise)
+    assert out['prob_softmax'].shape[-1] == 2                      # Q3: DS heads are dead in prob mode
+    assert out['prob_kl'].ndim == 0 and out['prob_kl'] > 0
+    qm = out['passes']['q_mean']
+    for z, (mu, _) in zip(qm['prob_used_latents'], qm['prob_distributions']):
+        assert torch.equal(z, mu)                                  # prob_mean=True -> z = mu
+    # Q4: the posterior input's 4th channel is the LAST IMAGE channel, so the label never matters
+    x2 = x.clone()
+    x2[..., 3] = 1 - x2[..., 3]
+    out2 = O.m1_probabilistic(ps, cfg, x2, noise)
+    assert torch.equal(out['prob_softmax'], out2['prob_softmax']) and torch.equal(out['prob_kl'], out2['prob_kl'])
+    out8 = O.m1_probabilistic(ps, cfg, x, noise, ds_in_prob='intended')
+    assert out8['prob_softmax'].shape[-1] == 8
+
+
+def test_gradcheck_blocks_fp64():
+    g = torch.Generator().manual_seed(11)
+    ps = O.ParamStore(dtype=torch.float64, seed=3)
+    x = torch.randn((1, 2, 4, 4, 3), generator=g, dtype=torch.float64, requires_grad=True)
+    O.se_block(ps, 'b', x, 8, (1, 3, 3), (1, 1, 1), 4)              # materialise the weights
+    for t in ps.p.values():
+        t.requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a: O.se_block(ps, 'b', a, 8, (1, 3, 3), (1, 1, 1), 4), (x,),
+                                    eps=1e-6, atol=1e-5)
+    gsig = torch.randn((1, 1, 2, 2, 6), generator=g, dtype=torch.float64, requires_grad=True)
+    O.attention_gate(ps, 'a', x, gsig, 3, (1, 1, 1))
+    for t in ps.p.values():
+        t.requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a, b: O.attention_gate(ps, 'a', a, b, 3, (1, 1, 1))[0], (x, gsig),
+                                    eps=1e-6, atol=1e-5)
+
+
+def test_adam_amsgrad_and_schedule():
+    w = torch.tensor([1.0, -2.0], dtype=torch.float64)
+    g = torch.tensor([0.5, -0.25], dtype=torch.float64)
+    m = v = vh = torch.zeros(2, dtype=torch.float64)
+    w1, m1, v1, vh1 = O.adam_amsgrad_step(w, g, m, v, vh, 1, 1e-3)
+    # first step of Adam moves every weight by ~lr against the gradient sign
+    assert torch.allclose(w1, w - 1e-3 * torch.sign(g), atol=1e-8)
+    w2, m2, v2, vh2 = O.adam_amsgrad_step(w1, g * 0.1, m1, v1, vh1, 2, 1e-3)
+    assert torch.equal(vh2, torch.maximum(vh1, v2)) and (vh2 >= v2).all()
+    lr0 = O.cosine_decay_restarts(0, 1e-3, 100, 2.0, 1.0, 1e-3)
+    assert abs(lr0 - 1e-3) < 1e-12
+    assert abs(O.cosine_decay_restarts(100, 1e-3, 100, 2.0, 1.0, 1e-3) - 1e-3) < 1e-12   # restart
+    assert abs(O.cosine_decay_restarts(50, 1e-3, 100, 2.0, 1.0, 1e-3) - 1e-3 * (0.999 * 0.5 + 0.001)) < 1e-12
+
+
+def test_orthogonal_init_is_orthogonal():
+    w = O.init_orthogonal((3, 3, 3, 16, 8), 1.0, 0).reshape(-1, 8)
+    assert np.allclose(w.T @ w, np.eye(8), atol=1e-10)
+    b = O.init_truncated_normal((1000,), 1e-3, 0)
+    assert np.abs(b).max() <= 2e-3
