@@ -59,7 +59,8 @@ typedef struct {
    * (one weight tensor per output). */
   int64_t w_stride_tap[M1_MAX_OUT], w_stride_red[M1_MAX_OUT], w_stride_out[M1_MAX_OUT];
   int32_t accumulate;                 /* 1: out += result (gradient accumulation) */
-  int32_t act_dtype;                  /* m1_dtype of gathered and produced tensors */
+  int32_t act_dtype;                  /* m1_dtype of the gathered tensors */
+  int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
 } m1_conv_desc;
 

@@ -28,7 +28,8 @@ class ConvDesc(C.Structure):
         ("nout", C.c_int32), ("out_c", C.c_int32 * M1_MAX_OUT),
         ("w_stride_tap", C.c_int64 * M1_MAX_OUT), ("w_stride_red", C.c_int64 * M1_MAX_OUT),
         ("w_stride_out", C.c_int64 * M1_MAX_OUT),
-        ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("engine", C.c_int32),
+        ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("engine", C.c_int32),
     ]
 
 
@@ -44,45 +45,52 @@ class M1Error(RuntimeError):
 
 _lib = None
 
-# name -> (restype, argtypes); every symbol include/m1b200.h declares
-_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+# name -> (restype, argtypes), PARSED from include/m1b200.h so the binding cannot drift from the ABI
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "m1b200.h")
 _PP = C.POINTER(C.c_void_p)
-SIGNATURES = {
-    "m1_last_error": (C.c_char_p, []),
-    "m1_version": (_I, []),
-    "m1_ctx_create": (_I, [_I, C.POINTER(C.c_void_p)]),
-    "m1_ctx_destroy": (_I, [_P]),
-    "m1_ctx_launch_count": (_L, [_P, _I]),
-    "m1_conv3d_tc_supported": (_I, [C.POINTER(ConvDesc)]),
-    "m1_conv3d": (_I, [_P, C.POINTER(ConvDesc), _PP, _PP, _P, _PP, _PP, _P]),
-    "m1_conv3d_packed_bytes": (_L, [C.POINTER(ConvDesc)]),
-    "m1_conv3d_pack_weights": (_I, [_P, C.POINTER(ConvDesc), _PP, _P, _P]),
-    "m1_conv3d_wgrad": (_I, [_P, C.POINTER(ConvDesc), _PP, _PP, _PP, _PP, _P]),
-    "m1_inorm_stats": (_I, [_P, _P, _I, _I, _L, _I, _F, _P, _P]),
-    "m1_inorm_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _P]),
-    "m1_inorm_act_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P]),
-    "m1_se_squeeze": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _P]),
-    "m1_se_excite_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
-    "m1_se_excite_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "m1_se_gate_fwd": (_I, [_P] + [_P] * 9 + [C.POINTER(Dropout), _I, _I, _L, _I, _P, _P]),
-    "m1_se_gate_bwd_reduce": (_I, [_P] + [_P] * 10 + [C.POINTER(Dropout), _I, _I, _L, _I, _P, _P, _P]),
-    "m1_se_gate_bwd_apply": (_I, [_P] + [_P] * 10 + [C.POINTER(Dropout), _P, _P, _I, _I, _L, _I]
-                             + [_P] * 6 + [_P]),
-    "m1_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
-    "m1_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P,
-                         _P, _P, _P]),
-    "m1_latent_fwd": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _I, _P, _P]),
-    "m1_latent_bwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _I, _I, _P, _P]),
-    "m1_kl_fwd": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
-    "m1_kl_bwd": (_I, [_P, _P, _P, _I, _L, _I, _F, _P, _P, _P]),
-    "m1_softmax_focal": (_I, [_P, _P, _I, _P, _I, _P, _F, _I, _P, _P, _I, _P, _I, _I, _F, _P, _P,
-                              _F, _P]),
-    "m1_adam_amsgrad": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
-    "m1_cast": (_I, [_P, _P, _I, _P, _I, _L, _P]),
-    "m1_copy_channels": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _L, _P]),
-    "m1_axpy": (_I, [_P, _P, _I, _F, _P, _L, _P]),
-    "m1_decision_fusion": (_I, [_P, _P, _P, _I, _L, _P, _P]),
-}
+
+
+def _ctype_of(decl):
+    d = " ".join(decl.replace("const", " ").split())
+    if "*" in d:
+        base = d.split("*")[0].strip()
+        stars = d.count("*")
+        if base == "m1_conv_desc":
+            return C.POINTER(ConvDesc)
+        if base == "m1_dropout":
+            return C.POINTER(Dropout)
+        if stars >= 2:
+            return _PP
+        if base == "char":
+            return C.c_char_p
+        return C.c_void_p
+    base = d.split()[0] if d.split() else "void"
+    return {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float": C.c_float,
+            "uint64_t": C.c_uint64, "void": None}[base]
+
+
+def parse_header(path=HEADER_PATH):
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = text[text.index("typedef struct m1_ctx m1_ctx;"):]
+    sigs = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(m1_\w+)\s*\(([^;{}]*?)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if ret.startswith("typedef"):
+            continue
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                # drop the parameter name (last identifier) unless the declarator ends with '*'
+                a = re.sub(r"\b\w+$", "", a) if not a.endswith("*") else a
+                argtypes.append(_ctype_of(a))
+        sigs[name] = (_ctype_of(ret), argtypes)
+    return sigs
+
+
+SIGNATURES = parse_header()
 
 
 def lib():

@@ -1,0 +1,432 @@
+// attn_latent_loss.cu — K6 additive attention gate, K7 probabilistic latent heads + analytic KL,
+// K8 softmax + focal loss (forward and backward in one pass).
+//   K6  GridAttentionBlock3D.call                R:network_blocks.py:106-130
+//   K7  mu/log-sigma heads, sample, KL(q||p)     R:networks.py:637-649 (x4), :373-385
+//   K8  softmax + Focal.FL / Focal.loss          R:networks.py:388-390,751-755; losses.py:32-49
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int TB = 256;
+
+struct Grid3 { int d, h, w; };
+
+// ---------------------------------------------------------------------------------------------
+// K6 forward: one warp per theta voxel -> psi; then y = up(psi) * x elementwise
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_psi_kernel(const T* __restrict__ theta, const T* __restrict__ phi,
+                                                     const float* __restrict__ w_psi,
+                                                     const float* __restrict__ b_psi, int batch, Grid3 tg, Grid3 gg,
+                                                     int F, float* __restrict__ psi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (TB / 32);
+  const int64_t tvox = (int64_t)tg.d * tg.h * tg.w;
+  const int sd = tg.d / gg.d, sh = tg.h / gg.h, sw = tg.w / gg.w;
+  for (int64_t v = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5); v < (int64_t)batch * tvox; v += warps) {
+    const int n = (int)(v / tvox);
+    int64_t r = v % tvox;
+    const int x = (int)(r % tg.w); r /= tg.w;
+    const int y = (int)(r % tg.h);
+    const int z = (int)(r / tg.h);
+    const int64_t gv = (((int64_t)n * gg.d + min(z / sd, gg.d - 1)) * gg.h + min(y / sh, gg.h - 1)) * gg.w +
+                       min(x / sw, gg.w - 1);
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) {
+      const float f = lrelu(ld_f<T>(theta + v * F + c) + ld_f<T>(phi + gv * F + c), M1_LRELU_SLOPE);
+      s = fmaf(f, w_psi[c], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) psi[v] = 1.f / (1.f + __expf(-(s + b_psi[0])));
+  }
+}
+
+__device__ __forceinline__ int64_t psi_index(int64_t xv, int n_unused, Grid3 xg, Grid3 tg, int64_t* n_out) {
+  int64_t r = xv;
+  const int x = (int)(r % xg.w); r /= xg.w;
+  const int y = (int)(r % xg.h); r /= xg.h;
+  const int z = (int)(r % xg.d); r /= xg.d;
+  const int n = (int)r;
+  const int sd = xg.d / tg.d, sh = xg.h / tg.h, sw = xg.w / tg.w;
+  *n_out = n;
+  return (((int64_t)n * tg.d + min(z / sd, tg.d - 1)) * tg.h + min(y / sh, tg.h - 1)) * tg.w + min(x / sw, tg.w - 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_apply_kernel(const T* __restrict__ x, const float* __restrict__ psi,
+                                                       Grid3 xg, Grid3 tg, int Cx, T* __restrict__ y,
+                                                       int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    int64_t n;
+    const int64_t pv = psi_index(i / Cx, 0, xg, tg, &n);
+    st_f<T>(y + i, ld_f<T>(x + i) * psi[pv]);
+  }
+}
+
+// dx (+)= dy * up(psi)
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_bwd_x_kernel(const T* __restrict__ dy, const float* __restrict__ psi,
+                                                       Grid3 xg, Grid3 tg, int Cx, T* __restrict__ dx, int acc,
+                                                       int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    int64_t n;
+    const int64_t pv = psi_index(i / Cx, 0, xg, tg, &n);
+    float v = ld_f<T>(dy + i) * psi[pv];
+    if (acc) v += ld_f<T>(dx + i);
+    st_f<T>(dx + i, v);
+  }
+}
+
+// one warp per theta voxel: dpsi = sum over its x block of <dy, x>; ds = dpsi psi (1-psi);
+// dtheta = ds w_psi lrelu'(theta+phi); dphi += dtheta (atomics, fp32); dw_psi/db_psi via smem
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ dy, const T* __restrict__ theta,
+                                                         const T* __restrict__ phi, const float* __restrict__ w_psi,
+                                                         const float* __restrict__ psi, const T* __restrict__ x,
+                                                         int batch, Grid3 tg, Grid3 gg, Grid3 xg, int F, int Cx,
+                                                         T* __restrict__ dtheta, float* __restrict__ dphi,
+                                                         float* __restrict__ dw_psi, float* __restrict__ db_psi) {
+  extern __shared__ float sdw[];  // F + 1
+  for (int i = threadIdx.x; i <= F; i += TB) sdw[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (TB / 32);
+  const int64_t tvox = (int64_t)tg.d * tg.h * tg.w;
+  const int sd = tg.d / gg.d, sh = tg.h / gg.h, sw = tg.w / gg.w;
+  const int ud = xg.d / tg.d, uh = xg.h / tg.h, uw = xg.w / tg.w;
+  for (int64_t v = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5); v < (int64_t)batch * tvox; v += warps) {
+    const int n = (int)(v / tvox);
+    int64_t r = v % tvox;
+    const int tx = (int)(r % tg.w); r /= tg.w;
+    const int ty = (int)(r % tg.h);
+    const int tz = (int)(r / tg.h);
+    // dpsi over the x voxels that read this psi (nearest up-sampling by (ud,uh,uw))
+    float dpsi = 0.f;
+    for (int a = 0; a < ud; ++a)
+      for (int b = 0; b < uh; ++b)
+        for (int c = 0; c < uw; ++c) {
+          const int64_t xv = (((int64_t)n * xg.d + tz * ud + a) * xg.h + ty * uh + b) * xg.w + tx * uw + c;
+          for (int ch = lane; ch < Cx; ch += 32)
+            dpsi = fmaf(ld_f<T>(dy + xv * Cx + ch), ld_f<T>(x + xv * Cx + ch), dpsi);
+        }
+    // x voxels beyond tg*u (floor ratio remainder) map to the last psi: handled only when grids divide
+    dpsi = warp_sum(dpsi);
+    const float p = psi[v];
+    const float ds = dpsi * p * (1.f - p);
+    const int64_t gv = (((int64_t)n * gg.d + min(tz / sd, gg.d - 1)) * gg.h + min(ty / sh, gg.h - 1)) * gg.w +
+                       min(tx / sw, gg.w - 1);
+    for (int c = lane; c < F; c += 32) {
+      const float pre = ld_f<T>(theta + v * F + c) + ld_f<T>(phi + gv * F + c);
+      const float f = lrelu(pre, M1_LRELU_SLOPE);
+      const float dth = ds * w_psi[c] * (pre > 0.f ? 1.f : M1_LRELU_SLOPE);
+      st_f<T>(dtheta + v * F + c, dth);
+      atomicAdd(dphi + gv * F + c, dth);
+      atomicAdd(&sdw[c], ds * f);
+    }
+    if (lane == 0) atomicAdd(&sdw[F], ds);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F; i += TB) atomicAdd(dw_psi + i, sdw[i]);
+  if (threadIdx.x == 0) atomicAdd(db_psi, sdw[F]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 latent heads
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clip01(float ls) { return fminf(fmaxf(ls, -0.1f), 0.1f); }
+__device__ __forceinline__ float in_clip(float ls) { return (ls >= -0.1f && ls <= 0.1f) ? 1.f : 0.f; }
+
+template <typename T>
+__global__ void latent_fwd_kernel(const float* __restrict__ ml, const float* __restrict__ eps, int mode, int L,
+                                  int zc, T* __restrict__ z, int64_t rows) {
+  const int64_t total = rows * zc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / zc;
+    const int c = (int)(i % zc);
+    float v = 0.f;
+    if (c < L) {
+      const float mu = ml[r * 2 * L + c];
+      v = mu;
+      if (mode == 0) v = fmaf(__expf(clip01(ml[r * 2 * L + L + c])), eps[r * L + c], mu);
+    }
+    st_f<T>(z + i, v);
+  }
+}
+
+template <typename T>
+__global__ void latent_bwd_kernel(const T* __restrict__ dz, const float* __restrict__ ml,
+                                  const float* __restrict__ eps, int mode, int L, int zc, float* __restrict__ dml,
+                                  int64_t rows) {
+  const int64_t total = rows * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / L;
+    const int c = (int)(i % L);
+    const float g = ld_f<T>(dz + r * zc + c);
+    dml[r * 2 * L + c] += g;
+    if (mode == 0) {
+      const float ls = ml[r * 2 * L + L + c];
+      dml[r * 2 * L + L + c] += g * eps[r * L + c] * __expf(clip01(ls)) * in_clip(ls);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TB) kl_fwd_kernel(const float* __restrict__ q, const float* __restrict__ p, int L,
+                                                   int64_t rows, float scale, float* __restrict__ out) {
+  __shared__ float sm[TB / 32];
+  float acc[1] = {0.f};
+  const int64_t total = rows * L;
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    const int64_t r = i / L;
+    const int c = (int)(i % L);
+    const float mq = q[r * 2 * L + c], mp = p[r * 2 * L + c];
+    const float lq = clip01(q[r * 2 * L + L + c]), lp = clip01(p[r * 2 * L + L + c]);
+    const float dm = mq - mp;
+    acc[0] += (lp - lq) + (__expf(2.f * lq) + dm * dm) * 0.5f * __expf(-2.f * lp) - 0.5f;
+  }
+  block_sum<1, TB>(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(out, acc[0] * scale);
+}
+
+__global__ void kl_bwd_kernel(const float* __restrict__ q, const float* __restrict__ p, int L, int64_t rows,
+                              float scale, float* __restrict__ dq, float* __restrict__ dp) {
+  const int64_t total = rows * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / L;
+    const int c = (int)(i % L);
+    const int64_t im = r * 2 * L + c, is = im + L;
+    const float mq = q[im], mp = p[im];
+    const float rq = q[is], rp = p[is];
+    const float lq = clip01(rq), lp = clip01(rp);
+    const float dm = mq - mp;
+    const float vq = __expf(2.f * lq), ivp = __expf(-2.f * lp);
+    const float gm = scale * dm * ivp;
+    dq[im] += gm;
+    dp[im] -= gm;
+    dq[is] += scale * (-1.f + vq * ivp) * in_clip(rq);
+    dp[is] += scale * (1.f - (vq + dm * dm) * ivp) * in_clip(rp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 softmax + focal, one thread per label voxel (nc <= 8 classes)
+// ---------------------------------------------------------------------------------------------
+constexpr int MAXC = 8;
+struct FocalArgs {
+  float alpha[MAXC];
+  float gamma;
+  int nc;
+  Grid3 lg, up;
+  int batch;
+  int prob_c, head_off;
+  float loss_scale;   // head_weight / batch
+  float grad_scale;   // upstream * head_weight / batch
+};
+
+template <typename TY>
+__global__ void __launch_bounds__(TB) softmax_focal_kernel(const float* __restrict__ logits, const TY* __restrict__ y,
+                                                          FocalArgs a, float* __restrict__ prob,
+                                                          float* __restrict__ loss_out,
+                                                          float* __restrict__ dlogits) {
+  __shared__ float sm[TB / 32];
+  const Grid3 xg{a.lg.d * a.up.d, a.lg.h * a.up.h, a.lg.w * a.up.w};
+  const int64_t total = (int64_t)a.batch * xg.d * xg.h * xg.w;
+  const bool upsampled = a.up.d * a.up.h * a.up.w > 1;
+  float acc[1] = {0.f};
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    int64_t r = i;
+    const int xw = (int)(r % xg.w); r /= xg.w;
+    const int xh = (int)(r % xg.h); r /= xg.h;
+    const int xd = (int)(r % xg.d); r /= xg.d;
+    const int64_t lv = ((r * a.lg.d + xd / a.up.d) * a.lg.h + xh / a.up.h) * a.lg.w + xw / a.up.w;
+    float l[MAXC], p[MAXC], g[MAXC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < a.nc) { l[c] = logits[lv * a.nc + c]; mx = fmaxf(mx, l[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < a.nc) { p[c] = expf(l[c] - mx); sum += p[c]; }
+    const float inv = 1.f / sum;
+    float psum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < a.nc) {
+        p[c] *= inv;
+        psum += p[c];
+        if (prob) prob[i * a.prob_c + a.head_off + c] = p[c];
+      }
+    float fl = 0.f, dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < a.nc) {
+        const float yt = y ? ld_f<TY>(y + i * a.nc + c) : 0.f;   // y == NULL: softmax only
+        const float qn = p[c] / psum;                                  // y_pred /= sum(y_pred)
+        const float q = fminf(fmaxf(qn, 1e-7f), 1.f - 1e-7f);          // clip(eps, 1-eps)
+        const float om = 1.f - q;
+        const float pw = powf(om, a.gamma);
+        const float nl = -logf(q);
+        const float wgt = a.alpha[c] * yt * yt;
+        fl = fmaf(wgt * pw, nl, fl);
+        // d/dq [(1-q)^gamma * (-log q)], zero outside the clip range
+        const float inside = (qn >= 1e-7f && qn <= 1.f - 1e-7f) ? 1.f : 0.f;
+        const float dpw = a.gamma == 0.f ? 0.f : a.gamma * powf(om, a.gamma - 1.f);
+        g[c] = wgt * inside * (-dpw * nl - pw / q);
+        dot = fmaf(p[c], g[c], dot);
+      }
+    acc[0] += fl;
+    if (dlogits) {
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < a.nc) {
+          const float d = a.grad_scale * p[c] * (g[c] - dot);
+          if (upsampled) atomicAdd(dlogits + lv * a.nc + c, d);
+          else dlogits[lv * a.nc + c] = d;
+        }
+    }
+  }
+  block_sum<1, TB>(acc, sm);
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, acc[0] * a.loss_scale);
+}
+
+inline unsigned nblocks(const m1_ctx* ctx, int64_t total, int per = TB) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(total, per), (int64_t)ctx->num_sms * 16));
+}
+inline Grid3 g3(const int32_t* p) { return Grid3{p[0], p[1], p[2]}; }
+
+}  // namespace
+
+extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, const float* w_psi,
+                           const float* b_psi, const void* x, int dtype, int batch, const int32_t* tg,
+                           const int32_t* gg, const int32_t* xg, int F, int Cx, float* psi, void* y,
+                           void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const Grid3 T3 = g3(tg), G3 = g3(gg), X3 = g3(xg);
+  M1_CHECK(T3.d % G3.d == 0 && T3.h % G3.h == 0 && T3.w % G3.w == 0 && X3.d % T3.d == 0 && X3.h % T3.h == 0 &&
+               X3.w % T3.w == 0,
+           "m1_attn_fwd: grids must nest by integer factors");
+  const int64_t tv = (int64_t)batch * T3.d * T3.h * T3.w;
+  const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
+  if (dtype == M1_BF16) {
+    using T = __nv_bfloat16;
+    attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, batch,
+                                                                T3, G3, F, psi);
+    M1_LAUNCH_CHECK(ctx);
+    attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total);
+  } else {
+    using T = float;
+    attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, batch,
+                                                                T3, G3, F, psi);
+    M1_LAUNCH_CHECK(ctx);
+    attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total);
+  }
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const void* phi, const float* w_psi,
+                           const float* psi, const void* x, int dtype, int batch, const int32_t* tg,
+                           const int32_t* gg, const int32_t* xg, int F, int Cx, void* dx, int acc_dx,
+                           void* dtheta, float* dphi, float* dw_psi, float* db_psi, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const Grid3 T3 = g3(tg), G3 = g3(gg), X3 = g3(xg);
+  const int64_t tv = (int64_t)batch * T3.d * T3.h * T3.w;
+  const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
+  if (dtype == M1_BF16) {
+    using T = __nv_bfloat16;
+    attn_bwd_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(
+        (const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, batch, T3, G3, X3, F, Cx, (T*)dtheta,
+        dphi, dw_psi, db_psi);
+    M1_LAUNCH_CHECK(ctx);
+    attn_bwd_x_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total);
+  } else {
+    using T = float;
+    attn_bwd_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(
+        (const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, batch, T3, G3, X3, F, Cx, (T*)dtheta,
+        dphi, dw_psi, db_psi);
+    M1_LAUNCH_CHECK(ctx);
+    attn_bwd_x_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total);
+  }
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_latent_fwd(m1_ctx* ctx, const float* ml, const float* eps, int mode, int batch, int64_t voxels,
+                             int L, int zdtype, int zc, void* z, void* stream) {
+  M1_CHECK(mode == 1 || eps != nullptr, "m1_latent_fwd: sampling mode needs eps");
+  M1_CHECK(zc >= L, "m1_latent_fwd: zc < L");
+  const int64_t rows = (int64_t)batch * voxels;
+  if (zdtype == M1_BF16)
+    latent_fwd_kernel<__nv_bfloat16><<<nblocks(ctx, rows * zc), TB, 0, (cudaStream_t)stream>>>(
+        ml, eps, mode, L, zc, (__nv_bfloat16*)z, rows);
+  else
+    latent_fwd_kernel<float><<<nblocks(ctx, rows * zc), TB, 0, (cudaStream_t)stream>>>(ml, eps, mode, L, zc,
+                                                                                       (float*)z, rows);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_latent_bwd(m1_ctx* ctx, const void* dz, const float* ml, const float* eps, int mode, int batch,
+                             int64_t voxels, int L, int zdtype, int zc, float* dml, void* stream) {
+  const int64_t rows = (int64_t)batch * voxels;
+  if (zdtype == M1_BF16)
+    latent_bwd_kernel<__nv_bfloat16><<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dz, ml, eps, mode, L, zc, dml, rows);
+  else
+    latent_bwd_kernel<float><<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>((const float*)dz, ml, eps,
+                                                                                      mode, L, zc, dml, rows);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_kl_fwd(m1_ctx* ctx, const float* ml_q, const float* ml_p, int batch, int64_t voxels, int L,
+                         float* kl_out, void* stream) {
+  const int64_t rows = (int64_t)batch * voxels;
+  kl_fwd_kernel<<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(ml_q, ml_p, L, rows, 1.f / (float)batch,
+                                                                         kl_out);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_kl_bwd(m1_ctx* ctx, const float* ml_q, const float* ml_p, int batch, int64_t voxels, int L,
+                         float scale, float* dml_q, float* dml_p, void* stream) {
+  const int64_t rows = (int64_t)batch * voxels;
+  kl_bwd_kernel<<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(ml_q, ml_p, L, rows,
+                                                                         scale / (float)batch, dml_q, dml_p);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, const void* y_true, int ydtype,
+                                const float* alpha, float gamma, int batch, const int32_t* lg, const int32_t* up,
+                                int nc, float* prob, int prob_c, int head_off, float head_weight, float* loss_out,
+                                void* dlogits, float grad_scale, void* stream) {
+  M1_CHECK(ldtype == M1_F32, "m1_softmax_focal: logits must be fp32");
+  M1_CHECK(nc >= 1 && nc <= MAXC, "m1_softmax_focal: nc %d out of range", nc);
+  FocalArgs a;
+  for (int c = 0; c < MAXC; ++c) a.alpha[c] = (alpha && c < nc) ? alpha[c] : 0.f;   // alpha is a HOST array
+  a.gamma = gamma;
+  a.nc = nc;
+  a.lg = g3(lg);
+  a.up = g3(up);
+  a.batch = batch;
+  a.prob_c = prob_c;
+  a.head_off = head_off;
+  a.loss_scale = head_weight / (float)batch;
+  a.grad_scale = grad_scale * head_weight / (float)batch;
+  const int64_t total = (int64_t)batch * a.lg.d * a.up.d * a.lg.h * a.up.h * a.lg.w * a.up.w;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_true == nullptr) {
+    // inference: softmax only (labels absent) - reuse the kernel with zero weights
+    M1_CHECK(prob != nullptr, "m1_softmax_focal: nothing to do");
+  }
+  if (ydtype == M1_BF16)
+    softmax_focal_kernel<__nv_bfloat16><<<nblocks(ctx, total), TB, 0, st>>>(
+        (const float*)logits, (const __nv_bfloat16*)y_true, a, prob, loss_out, (float*)dlogits);
+  else
+    softmax_focal_kernel<float><<<nblocks(ctx, total), TB, 0, st>>>((const float*)logits, (const float*)y_true, a,
+                                                                    prob, loss_out, (float*)dlogits);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}

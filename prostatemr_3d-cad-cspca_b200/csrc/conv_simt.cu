@@ -58,7 +58,7 @@ __device__ __forceinline__ int64_t gather_index(const SimtParams& p, int n, int 
   return (((int64_t)n * p.Di + id) * p.Hi + ih) * p.Wi + iw;
 }
 
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ SimtParams p) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ S
       if (p.nout > 1 && n >= p.out_c[0]) { n -= p.out_c[0]; j = 1; }
       float v = acc[i][jj];
       if (p.bias[j]) v += p.bias[j][n];
-      T* dst = reinterpret_cast<T*>(p.out[j]) + m * p.out_c[j] + n;
-      if (p.accumulate) v += ld_f<T>(dst);
-      st_f<T>(dst, v);
+      TO* dst = reinterpret_cast<TO*>(p.out[j]) + m * p.out_c[j] + n;
+      if (p.accumulate) v += ld_f<TO>(dst);
+      st_f<TO>(dst, v);
     }
   }
 }
@@ -188,7 +188,7 @@ struct WgradParams {
   int64_t vox_per_block;
 };
 
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(TH) wgrad_simt_kernel(const __grid_constant__ WgradParams q) {
   const SimtParams& p = q.g;
   __shared__ float Gs[WV][BM + 4];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(TH) wgrad_simt_kernel(const __grid_constant__ 
   const int tid = threadIdx.x;
   const int C = p.src_c[q.src_index];
   const T* src = reinterpret_cast<const T*>(p.src[q.src_index]);
-  const T* dy = reinterpret_cast<const T*>(q.dout);
+  const TO* dy = reinterpret_cast<const TO*>(q.dout);
   const int r_tiles = (C + BM - 1) / BM;
   const int r0 = (blockIdx.x % r_tiles) * BM;
   const int n0 = (blockIdx.x / r_tiles) * BN;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TH) wgrad_simt_kernel(const __grid_constant__ 
       const int vv = e / BN, nn = e % BN;
       const int64_t m = v0 + vv;
       float x = 0.f;
-      if (m < v_end && n0 + nn < q.Cn && vin[vv] >= 0) x = ld_f<T>(dy + m * q.Cn + n0 + nn);
+      if (m < v_end && n0 + nn < q.Cn && vin[vv] >= 0) x = ld_f<TO>(dy + m * q.Cn + n0 + nn);
       Ys[vv][nn] = x;
     }
     __syncthreads();
@@ -337,8 +337,11 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
     p.bias[j] = bias ? bias[j] : nullptr;
   }
   dim3 grid((unsigned)cdiv64(p.out_vox, BM), (unsigned)((p.n_total + BN - 1) / BN));
-  if (d->act_dtype == M1_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, TH, 0, st>>>(p);
-  else conv_simt_kernel<float><<<grid, TH, 0, st>>>(p);
+  const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
+  if (ib && ob) conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
+  else if (ib) conv_simt_kernel<__nv_bfloat16, float><<<grid, TH, 0, st>>>(p);
+  else if (ob) conv_simt_kernel<float, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
+  else conv_simt_kernel<float, float><<<grid, TH, 0, st>>>(p);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -370,8 +373,11 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       vpb = std::max<int64_t>(256, cdiv64(vpb, WV) * WV);
       q.vox_per_block = vpb;
       dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)cdiv64(out_vox, vpb));
-      if (d->act_dtype == M1_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, TH, 0, st>>>(q);
-      else wgrad_simt_kernel<float><<<grid, TH, 0, st>>>(q);
+      const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
+      if (ib && ob) wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, TH, 0, st>>>(q);
+      else if (ib) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, TH, 0, st>>>(q);
+      else if (ob) wgrad_simt_kernel<float, __nv_bfloat16><<<grid, TH, 0, st>>>(q);
+      else wgrad_simt_kernel<float, float><<<grid, TH, 0, st>>>(q);
       M1_LAUNCH_CHECK(ctx);
       r_base += C;
     }
@@ -379,7 +385,7 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       const int C = q.Cn;
       const int64_t rpb = std::max<int64_t>(64, cdiv64(out_vox, (int64_t)ctx->num_sms * 4));
       const unsigned blocks = (unsigned)cdiv64(out_vox, rpb);
-      if (d->act_dtype == M1_BF16)
+      if (d->out_dtype == M1_BF16)
         colsum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>(
             reinterpret_cast<const __nv_bfloat16*>(douts[j]), out_vox, C, rpb, dbias[j]);
       else

@@ -329,7 +329,7 @@ struct Plan {
 };
 
 bool make_plan(const m1_conv_desc* d, Plan* pl) {
-  if (d->act_dtype != M1_BF16) return false;
+  if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
   for (int i = 0; i < 3; ++i) {
     if (d->stride[i] != 1) return false;
     if (d->in_dhw[i] != d->out_dhw[i]) return false;

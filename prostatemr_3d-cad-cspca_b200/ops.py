@@ -21,7 +21,7 @@ def same_pads(size, k, s):
 
 
 def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w_strides,
-              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO):
+              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO, out_dtype=None):
     d = ConvDesc()
     d.mode = mode
     d.batch = batch
@@ -40,6 +40,7 @@ def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w
         d.w_stride_tap[j], d.w_stride_red[j], d.w_stride_out[j] = w_strides[j]
     d.accumulate = 1 if accumulate else 0
     d.act_dtype = act_dtype
+    d.out_dtype = act_dtype if out_dtype is None else out_dtype
     d.engine = engine
     return d
 
@@ -77,3 +78,160 @@ def conv3d_wgrad(ctx, d, srcs, douts, dws, dbiases):
     check(lib().m1_conv3d_wgrad(ctx.handle, C.byref(d), ptr_array([ptr(s) for s in srcs]),
                                 ptr_array([ptr(g) for g in douts]),
                                 ptr_array([ptr(g) for g in dws]), db, current_stream()))
+
+
+# ---- K4 instance norm ----------------------------------------------------------------------
+def _nvc(x):
+    """(batch, voxels, C) of an NDHWC tensor."""
+    return x.shape[0], x.numel() // (x.shape[0] * x.shape[-1]), x.shape[-1]
+
+
+def inorm_stats(ctx, x, stats, eps=1e-3):
+    n, v, c = _nvc(x)
+    check(lib().m1_inorm_stats(ctx.handle, ptr(x), dtype_code(x), n, v, c, eps, ptr(stats), current_stream()))
+
+
+def inorm_act_fwd(ctx, x, stats, gamma, beta, slope, y):
+    n, v, c = _nvc(x)
+    check(lib().m1_inorm_act_fwd(ctx.handle, ptr(x), ptr(stats), ptr(gamma), ptr(beta), dtype_code(x), n, v, c,
+                                 slope, ptr(y), current_stream()))
+
+
+def inorm_act_bwd(ctx, dy, x, stats, gamma, beta, slope, dx, accumulate, dgamma, dbeta):
+    n, v, c = _nvc(x)
+    check(lib().m1_inorm_act_bwd(ctx.handle, ptr(dy), ptr(x), ptr(stats), ptr(gamma), ptr(beta), dtype_code(x),
+                                 n, v, c, slope, ptr(dx), 1 if accumulate else 0, ptr(dgamma), ptr(dbeta),
+                                 current_stream()))
+
+
+# ---- K5 squeeze-excite -----------------------------------------------------------------------
+def make_dropout(rate, u=None, seed=0, stream_id=0):
+    d = Dropout()
+    d.u = ptr(u) if u is not None else None
+    d.seed = seed
+    d.stream_id = stream_id
+    d.rate = rate
+    return d
+
+
+def se_squeeze(ctx, raw3, stats3, gamma3, beta3, pool):
+    n, v, c = _nvc(raw3)
+    check(lib().m1_se_squeeze(ctx.handle, ptr(raw3), ptr(stats3), ptr(gamma3), ptr(beta3), dtype_code(raw3),
+                              n, v, c, ptr(pool), current_stream()))
+
+
+def se_excite_fwd(ctx, pool, w6, b6, w7, b7, hidden, gate):
+    n, c = pool.shape
+    cr = hidden.shape[-1]
+    check(lib().m1_se_excite_fwd(ctx.handle, ptr(pool), ptr(w6), ptr(b6), ptr(w7), ptr(b7), n, c, cr,
+                                 ptr(hidden), ptr(gate), current_stream()))
+
+
+def se_excite_bwd(ctx, dgate, pool, hidden, gate, w6, w7, dpool, dw6, db6, dw7, db7):
+    n, c = pool.shape
+    cr = hidden.shape[-1]
+    check(lib().m1_se_excite_bwd(ctx.handle, ptr(dgate), ptr(pool), ptr(hidden), ptr(gate), ptr(w6), ptr(w7),
+                                 n, c, cr, ptr(dpool), ptr(dw6), ptr(db6), ptr(dw7), ptr(db7), current_stream()))
+
+
+def se_gate_fwd(ctx, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, out):
+    n, v, c = _nvc(raw3)
+    check(lib().m1_se_gate_fwd(ctx.handle, ptr(raw3), ptr(raw4), ptr(st3), ptr(st4), ptr(g3), ptr(b3), ptr(g4),
+                               ptr(b4), ptr(gate), C.byref(drop), dtype_code(raw3), n, v, c, ptr(out),
+                               current_stream()))
+
+
+def se_gate_bwd_reduce(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, red, dgate):
+    n, v, c = _nvc(raw3)
+    check(lib().m1_se_gate_bwd_reduce(ctx.handle, ptr(dout), ptr(raw3), ptr(raw4), ptr(st3), ptr(st4), ptr(g3),
+                                      ptr(b3), ptr(g4), ptr(b4), ptr(gate), C.byref(drop), dtype_code(raw3),
+                                      n, v, c, ptr(red), ptr(dgate), current_stream()))
+
+
+def se_gate_bwd_apply(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, red, dpool, draw3, draw4,
+                      dg3, db3, dg4, db4):
+    n, v, c = _nvc(raw3)
+    check(lib().m1_se_gate_bwd_apply(ctx.handle, ptr(dout), ptr(raw3), ptr(raw4), ptr(st3), ptr(st4), ptr(g3),
+                                     ptr(b3), ptr(g4), ptr(b4), ptr(gate), C.byref(drop), ptr(red), ptr(dpool),
+                                     dtype_code(raw3), n, v, c, ptr(draw3), ptr(draw4), ptr(dg3), ptr(db3),
+                                     ptr(dg4), ptr(db4), current_stream()))
+
+
+# ---- K6 attention gate -----------------------------------------------------------------------
+def _grid(t):
+    return (C.c_int32 * 3)(*t.shape[1:4])
+
+
+def attn_fwd(ctx, theta, phi, w_psi, b_psi, x, psi, y):
+    check(lib().m1_attn_fwd(ctx.handle, ptr(theta), ptr(phi), ptr(w_psi), ptr(b_psi), ptr(x), dtype_code(x),
+                            x.shape[0], _grid(theta), _grid(phi), _grid(x), theta.shape[-1], x.shape[-1],
+                            ptr(psi), ptr(y), current_stream()))
+
+
+def attn_bwd(ctx, dy, theta, phi, w_psi, psi, x, dx, acc_dx, dtheta, dphi, dw_psi, db_psi):
+    check(lib().m1_attn_bwd(ctx.handle, ptr(dy), ptr(theta), ptr(phi), ptr(w_psi), ptr(psi), ptr(x),
+                            dtype_code(x), x.shape[0], _grid(theta), _grid(phi), _grid(x), theta.shape[-1],
+                            x.shape[-1], ptr(dx), 1 if acc_dx else 0, ptr(dtheta), ptr(dphi), ptr(dw_psi),
+                            ptr(db_psi), current_stream()))
+
+
+# ---- K7 latent heads / KL --------------------------------------------------------------------
+def latent_fwd(ctx, ml, eps, mode, z):
+    n, v, c2 = _nvc(ml)
+    check(lib().m1_latent_fwd(ctx.handle, ptr(ml), ptr(eps), mode, n, v, c2 // 2, dtype_code(z), z.shape[-1],
+                              ptr(z), current_stream()))
+
+
+def latent_bwd(ctx, dz, ml, eps, mode, dml):
+    n, v, c2 = _nvc(ml)
+    check(lib().m1_latent_bwd(ctx.handle, ptr(dz), ptr(ml), ptr(eps), mode, n, v, c2 // 2, dtype_code(dz),
+                              dz.shape[-1], ptr(dml), current_stream()))
+
+
+def kl_fwd(ctx, ml_q, ml_p, kl_out):
+    n, v, c2 = _nvc(ml_q)
+    check(lib().m1_kl_fwd(ctx.handle, ptr(ml_q), ptr(ml_p), n, v, c2 // 2, ptr(kl_out), current_stream()))
+
+
+def kl_bwd(ctx, ml_q, ml_p, scale, dml_q, dml_p):
+    n, v, c2 = _nvc(ml_q)
+    check(lib().m1_kl_bwd(ctx.handle, ptr(ml_q), ptr(ml_p), n, v, c2 // 2, scale, ptr(dml_q), ptr(dml_p),
+                          current_stream()))
+
+
+# ---- K8 softmax + focal ----------------------------------------------------------------------
+def softmax_focal(ctx, logits, y_true, alpha, gamma, up, prob, head_off, head_weight, loss_out, dlogits,
+                  grad_scale):
+    nc = logits.shape[-1]
+    al = (C.c_float * nc)(*[float(a) for a in alpha]) if alpha is not None else None
+    check(lib().m1_softmax_focal(
+        ctx.handle, ptr(logits), F32, ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
+        C.cast(al, C.c_void_p) if al is not None else None, gamma, logits.shape[0], _grid(logits),
+        (C.c_int32 * 3)(*up), nc, ptr(prob), prob.shape[-1] if prob is not None else 0, head_off, head_weight,
+        ptr(loss_out), ptr(dlogits), grad_scale, current_stream()))
+
+
+# ---- K9 optimizer + utilities ----------------------------------------------------------------
+def adam_amsgrad(ctx, w, g, m, v, vhat, lr_t, b1, b2, eps, l2, gscale, l2_out=None):
+    check(lib().m1_adam_amsgrad(ctx.handle, ptr(w), ptr(g), ptr(m), ptr(v), ptr(vhat), w.numel(), lr_t, b1, b2,
+                                eps, l2, gscale, ptr(l2_out), current_stream()))
+
+
+def cast(ctx, src, dst):
+    check(lib().m1_cast(ctx.handle, ptr(src), dtype_code(src), ptr(dst), dtype_code(dst), src.numel(),
+                        current_stream()))
+
+
+def copy_channels(ctx, src, src_off, dst, dst_off, c):
+    rows = src.numel() // src.shape[-1]
+    check(lib().m1_copy_channels(ctx.handle, ptr(src), dtype_code(src), src.shape[-1], src_off, ptr(dst),
+                                 dtype_code(dst), dst.shape[-1], dst_off, c, rows, current_stream()))
+
+
+def axpy(ctx, x, a, y):
+    check(lib().m1_axpy(ctx.handle, ptr(x), dtype_code(x), a, ptr(y), x.numel(), current_stream()))
+
+
+def decision_fusion(ctx, prior, follow, strategy, out):
+    check(lib().m1_decision_fusion(ctx.handle, ptr(prior), ptr(follow), strategy, follow.numel(), ptr(out),
+                                   current_stream()))

@@ -11,7 +11,7 @@ from oracle import m1_oracle as O
 README_CFG = dict(filters=(32, 64, 128, 256, 512),
                   strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (2, 2, 2)),
                   kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)))
-TINY = dict(filters=(8, 8, 16, 16, 32), strides=README_CFG['strides'], kernel_sizes=README_CFG['kernel_sizes'],
+TINY = dict(filters=(8, 16, 24, 32, 48), strides=README_CFG['strides'], kernel_sizes=README_CFG['kernel_sizes'],
             se_reduction=(4, 4, 4, 4, 4))
 
 
