@@ -100,6 +100,11 @@ int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* cons
 int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                     const void* const* douts, float* const* dw, float* const* dbias, void* stream);
 
+/* BiasAddGrad on its own: dbias[n] += sum_rows dout[row][n] (Conv3DTranspose layers, whose
+ * weight gradient runs with the operand roles swapped) */
+int m1_bias_grad(m1_ctx* ctx, const void* dout, int dtype, int64_t rows, int C, float* dbias,
+                 void* stream);
+
 /* ---- K4: tfa.layers.InstanceNormalization (eps 1e-3, biased variance) + LeakyReLU(0.1) ----
  * R:networks.py:473,576; R:network_blocks.py:38-44,55,58,104.  stats = [batch][C][2] = mean,rstd */
 int m1_inorm_stats(m1_ctx* ctx, const void* x, int dtype, int batch, int64_t voxels, int C,
@@ -194,7 +199,8 @@ int m1_kl_bwd(m1_ctx* ctx, const float* ml_q, const float* ml_p, int batch, int6
               int L, float scale, float* dml_q, float* dml_p, void* stream);
 
 /* ---- K8: softmax + focal loss, R:networks.py:388-390,751-755 and L:32-49 --------------------
- * logits [batch][lg][nc] (activation dtype or fp32), nearest-upsampled by `up` to the label grid
+ * logits [batch][lg][nc] fp32 (ldtype M1_F32; ldtype 2 = the tensor already holds probabilities,
+ * the softmax is skipped - Focal.FL called on predictions), nearest-upsampled by `up` to the label grid
  * xg = lg*up (deep-supervision heads: the 1x1x1 conv commutes with the nearest upsample);
  * softmax written to prob[..., head_off : head_off+nc] of a [batch][xg][prob_c] fp32 tensor;
  * loss_out[0] += head_weight * mean_b sum_{voxels,c} alpha_c y (1-p)^gamma (-log p), p clipped
@@ -220,6 +226,10 @@ int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int ddtype, int
 int m1_copy_channels(m1_ctx* ctx, const void* src, int sdtype, int src_c, int src_off, void* dst,
                      int ddtype, int dst_c, int dst_off, int c, int64_t rows, void* stream);
 int m1_axpy(m1_ctx* ctx, const void* x, int dtype, float a, void* y, int64_t n, void* stream);
+/* out[i] ~ N(0,1) from Philox4x32-10(seed, stream_id, i/4) + Box-Muller: the latent noise of
+ * tfp MultivariateNormalDiag.sample() (R:networks.py:647,671,695) when no eps is injected */
+int m1_philox_normal(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, float* out, int64_t n,
+                     void* stream);
 /* decision fusion of the cascaded model, R:networks.py:209-223 (strategy 0 identity, 1 noisy-or,
  * 2 bayes): out [rows][2] = [1-j, j] */
 int m1_decision_fusion(m1_ctx* ctx, const float* prior, const float* follow, int strategy,

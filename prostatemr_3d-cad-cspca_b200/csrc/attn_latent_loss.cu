@@ -219,6 +219,7 @@ struct FocalArgs {
   Grid3 lg, up;
   int batch;
   int prob_c, head_off;
+  int from_probs;     // input already holds probabilities (Focal.FL called directly)
   float loss_scale;   // head_weight / batch
   float grad_scale;   // upstream * head_weight / batch
 };
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(TB) softmax_focal_kernel(const float* __restri
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-      if (c < a.nc) { p[c] = expf(l[c] - mx); sum += p[c]; }
-    const float inv = 1.f / sum;
+      if (c < a.nc) { p[c] = a.from_probs ? l[c] : expf(l[c] - mx); sum += p[c]; }
+    const float inv = a.from_probs ? 1.f : 1.f / sum;
     float psum = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
@@ -402,7 +403,8 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
                                 const float* alpha, float gamma, int batch, const int32_t* lg, const int32_t* up,
                                 int nc, float* prob, int prob_c, int head_off, float head_weight, float* loss_out,
                                 void* dlogits, float grad_scale, void* stream) {
-  M1_CHECK(ldtype == M1_F32, "m1_softmax_focal: logits must be fp32");
+  M1_CHECK(ldtype == M1_F32 || ldtype == 2, "m1_softmax_focal: logits must be fp32 (ldtype 2: fp32 probabilities)");
+  M1_CHECK(ldtype != 2 || dlogits == nullptr, "m1_softmax_focal: no gradient in probability mode");
   M1_CHECK(nc >= 1 && nc <= MAXC, "m1_softmax_focal: nc %d out of range", nc);
   FocalArgs a;
   for (int c = 0; c < MAXC; ++c) a.alpha[c] = (alpha && c < nc) ? alpha[c] : 0.f;   // alpha is a HOST array
@@ -413,6 +415,7 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
   a.batch = batch;
   a.prob_c = prob_c;
   a.head_off = head_off;
+  a.from_probs = ldtype == 2;
   a.loss_scale = head_weight / (float)batch;
   a.grad_scale = grad_scale * head_weight / (float)batch;
   const int64_t total = (int64_t)batch * a.lg.d * a.up.d * a.lg.h * a.up.h * a.lg.w * a.up.w;

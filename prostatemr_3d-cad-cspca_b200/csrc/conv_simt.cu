@@ -396,3 +396,18 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
   }
   return 0;
 }
+
+extern "C" int m1_bias_grad(m1_ctx* ctx, const void* dout, int dtype, int64_t rows, int C, float* dbias,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rpb = std::max<int64_t>(64, cdiv64(rows, (int64_t)ctx->num_sms * 4));
+  const unsigned blocks = (unsigned)cdiv64(rows, rpb);
+  if (dtype == M1_BF16)
+    colsum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dout), rows, C, rpb, dbias);
+  else
+    colsum_kernel<float><<<blocks, 256, C * sizeof(float), st>>>(reinterpret_cast<const float*>(dout), rows, C,
+                                                                  rpb, dbias);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}

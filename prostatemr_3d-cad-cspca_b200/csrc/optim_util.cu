@@ -87,6 +87,26 @@ __global__ void fusion_kernel(const float* __restrict__ prior, const float* __re
   }
 }
 
+__global__ void philox_normal_kernel(uint64_t seed, uint64_t stream_id, float* __restrict__ out, int64_t n) {
+  const int64_t n4 = (n + 3) / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float u[4];
+    philox_uniform4(seed, stream_id, (uint64_t)i, u);
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float r = sqrtf(-2.f * logf(fmaxf(u[2 * k], 5.9604645e-8f)));
+      float sn, cs;
+      sincosf(6.28318530718f * u[2 * k + 1], &sn, &cs);
+      z[2 * k] = r * cs;
+      z[2 * k + 1] = r * sn;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i * 4 + k < n) out[i * 4 + k] = z[k];
+  }
+}
+
 inline unsigned nb(const m1_ctx* ctx, int64_t n) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(n, TB), (int64_t)ctx->num_sms * 16));
 }
@@ -144,6 +164,13 @@ extern "C" int m1_decision_fusion(m1_ctx* ctx, const float* prior, const float* 
                                   float* out, void* stream) {
   M1_CHECK(strategy >= 0 && strategy <= 2, "m1_decision_fusion: unknown strategy %d", strategy);
   fusion_kernel<<<nb(ctx, rows), TB, 0, (cudaStream_t)stream>>>(prior, follow, strategy, rows, out);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_philox_normal(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, float* out, int64_t n,
+                                void* stream) {
+  philox_normal_kernel<<<nb(ctx, (n + 3) / 4), TB, 0, (cudaStream_t)stream>>>(seed, stream_id, out, n);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

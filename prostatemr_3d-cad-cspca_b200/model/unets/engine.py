@@ -1,0 +1,388 @@
+"""Execution engine underneath the M1 model: device activations, a reverse tape, and one method
+per layer family of the reference that launches the corresponding libm1b200 kernels (forward) and
+records the kernels of its backward.
+
+Host logic only: shapes, buffer lifetimes, which kernel to launch with which pointers. In TRACE
+mode (no GPU needed) the same code path only propagates shapes and declares parameters - that is
+how M1.__init__ discovers the parameter inventory, mirroring Keras' build-on-first-call."""
+import numpy as np
+import torch
+
+from ... import _lib, ops
+from ..._lib import BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, F32
+
+LRELU = 0.1
+IN_EPS = 1e-3
+
+
+class Act:
+    """An NDHWC activation: shape, device tensor (None while tracing) and its gradient."""
+    __slots__ = ("shape", "t", "g", "dtype", "needs_grad")
+
+    def __init__(self, shape, dtype, t=None, needs_grad=True):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.t = t
+        self.g = None
+        self.needs_grad = needs_grad
+
+    @property
+    def grid(self):
+        return self.shape[1:4]
+
+    @property
+    def c(self):
+        return self.shape[-1]
+
+
+def _code(dtype):
+    return BF16 if dtype == torch.bfloat16 else F32
+
+
+class InjectedNoise:
+    """Explicit dropout uniforms / latent eps (parity runs): {(pass_name, site): tensor}."""
+
+    def __init__(self, tensors):
+        self.tensors = tensors
+        self._dev = {}
+
+    def _get(self, key, shape, device):
+        if key not in self._dev:
+            if key not in self.tensors:
+                raise KeyError(f"no injected noise for {key}")
+            t = torch.as_tensor(self.tensors[key]).to(device=device, dtype=torch.float32).contiguous()
+            assert tuple(t.shape) == tuple(shape), (key, tuple(t.shape), tuple(shape))
+            self._dev[key] = t
+        return self._dev[key]
+
+    def dropout(self, eng, pass_name, site, shape, rate):
+        return ops.make_dropout(rate, self._get((pass_name, site), shape, eng.device)), \
+            self._dev[(pass_name, site)]
+
+    def normal(self, eng, pass_name, site, shape):
+        return self._get((pass_name, site), shape, eng.device)
+
+
+class PhiloxNoise:
+    """Counter-based on-device noise: the dropout masks are never stored, the backward kernels
+    regenerate them from (seed, stream id, element index)."""
+    SITES = ("drope1", "drope2", "drope3", "drope4", "dropd3", "dropd2", "dropd1", "dropd0",
+             "dropp3", "dropp2", "dropp1", "dropp0", "eps3", "eps2", "eps1", "eps0")
+    PASSES = ("det", "q_sample", "q_mean", "p_z_q", "p_z_qmean", "p_sample")
+
+    def __init__(self, seed=42, rank=0):
+        self.seed = int(seed) + 1000003 * int(rank)
+        self.step = 0
+
+    def _stream(self, pass_name, site):
+        p = self.PASSES.index(pass_name) if pass_name in self.PASSES else len(self.PASSES)
+        return (self.step * 64 + p) * 64 + self.SITES.index(site)
+
+    def dropout(self, eng, pass_name, site, shape, rate):
+        return ops.make_dropout(rate, None, self.seed, self._stream(pass_name, site)), None
+
+    def normal(self, eng, pass_name, site, shape):
+        out = torch.empty(shape, dtype=torch.float32, device=eng.device)
+        ops.philox_normal(eng.ctx, self.seed, self._stream(pass_name, site), out)
+        return out
+
+
+class Engine:
+    def __init__(self, params, precision="bf16", device=None, use_tcgen05=True):
+        assert precision in ("bf16", "fp32")
+        self.params = params
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.use_tc = use_tcgen05 and precision == "bf16"
+        self.tracing = device is None
+        self.device = device
+        self.ctx = None if self.tracing else _lib.Context.get(torch.device(device).index or 0)
+        self.tape = []
+        self.record = True
+        self.noise = None
+        self.packs = {}            # key -> (desc, [kernel names], packed tensor)
+        self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def new(self, shape, dtype=None, zero=False):
+        dtype = dtype or self.act_dtype
+        if self.tracing:
+            return None
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+
+    def input(self, t, needs_grad=False):
+        if self.tracing:
+            return Act(t, self.act_dtype, None, needs_grad)  # t is a shape
+        return Act(t.shape, t.dtype, t, needs_grad)
+
+    def p(self, name, shape, kind):
+        self.params.declare(name, shape, kind)
+        return None if self.tracing else self.params.view(name)
+
+    def pg(self, name):
+        return self.params.grad(name)
+
+    def grad_buffer(self, act, zero=False):
+        """(tensor, accumulate): allocates act.g on first use."""
+        if act.g is None:
+            act.g = (torch.zeros if zero else torch.empty)(act.shape, dtype=act.dtype, device=self.device)
+            return act.g, False
+        return act.g, True
+
+    def begin(self, record=True):
+        self.tape = []
+        self.record = record
+        self.conv_flops = 0
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+    # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
+    def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None):
+        """Conv3D (possibly several layers reading the same input fused along Cout) or
+        Conv3DTranspose over the virtual concatenation of `srcs`.
+        layers: [(param_prefix, cout)]; returns one Act per layer."""
+        k, s = tuple(k), tuple(s)
+        cin = sum(a.c for a in srcs)
+        batch, in_dhw = srcs[0].shape[0], srcs[0].grid
+        for a in srcs:
+            assert a.grid == in_dhw, "concatenated tensors must share the grid"
+        out_dtype = out_dtype or self.act_dtype
+        if transposed:
+            assert len(layers) == 1
+            out_dhw = tuple(in_dhw[i] * s[i] for i in range(3))
+            pad = tuple(ops.same_pads(out_dhw[i], k[i], s[i])[1] for i in range(3))
+            shapes = [k + (layers[0][1], cin)]
+            wstr = [(layers[0][1] * cin, 1, cin)]
+            mode = CONV_TRANSPOSED
+        else:
+            geo = [ops.same_pads(in_dhw[i], k[i], s[i]) for i in range(3)]
+            out_dhw = tuple(g[0] for g in geo)
+            pad = tuple(g[1] for g in geo)
+            shapes = [k + (cin, co) for _, co in layers]
+            wstr = [(cin * co, co, 1) for _, co in layers]
+            mode = CONV_FWD
+        ws = [self.p(n + "/kernel", shp, "kernel") for (n, _), shp in zip(layers, shapes)]
+        bs = [self.p(n + "/bias", (co,), "bias") for n, co in layers]
+        outs = [Act((batch,) + out_dhw + (co,), out_dtype, self.new((batch,) + out_dhw + (co,), out_dtype))
+                for _, co in layers]
+        taps = k[0] * k[1] * k[2]
+        vox = batch * (np.prod(in_dhw) if transposed else np.prod(out_dhw))
+        self.conv_flops += 2 * int(vox) * taps * cin * sum(co for _, co in layers)
+        if self.tracing:
+            return outs
+        src_c = [a.c for a in srcs]
+        out_c = [co for _, co in layers]
+        d = ops.conv_desc(mode, batch, in_dhw, out_dhw, k, s, pad, src_c, out_c, wstr,
+                          act_dtype=_code(srcs[0].dtype), out_dtype=_code(out_dtype),
+                          engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
+        packed = None
+        if self.use_tc and ops.conv3d_tc_supported(d):
+            key = ("fwd",) + tuple(n for n, _ in layers)
+            ent = self.packs.get(key)
+            if ent is None:
+                ent = (d, ws, ops.conv3d_pack_weights(self.ctx, d, ws))
+                self.packs[key] = ent
+            packed = ent[2]
+        ops.conv3d(self.ctx, d, [a.t for a in srcs], ws, bs, [o.t for o in outs], packed)
+        if self.record:
+            self.tape.append(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed,
+                                                    ws, wstr))
+        return outs
+
+    def refresh_packs(self):
+        """Re-derive the bf16 operand packs from the fp32 master weights (after an optimizer step)."""
+        for d, ws, packed in self.packs.values():
+            ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
+
+    def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr):
+        live = [j for j, o in enumerate(outs) if o.g is not None]
+        if not live:
+            return
+        batch = srcs[0].shape[0]
+        cin = sum(a.c for a in srcs)
+        eng = ENGINE_SIMT
+        if not transposed:
+            # ---- wgrad: dW_j[tap, r, n] += gathered(src)[r] * dout_j[n]; BiasAddGrad fused
+            for j in live:
+                co = layers[j][1]
+                d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], [co],
+                                  [wstr[j]], act_dtype=_code(srcs[0].dtype), out_dtype=_code(outs[j].dtype),
+                                  engine=eng)
+                ops.conv3d_wgrad(self.ctx, d, [a.t for a in srcs], [outs[j].g],
+                                 [self.pg(layers[j][0] + "/kernel")], [self.pg(layers[j][0] + "/bias")])
+            # ---- dgrad per gathered tensor: dx_s (+)= sum_j convT(dout_j, W_j[:, off:off+C_s, :])
+            off = 0
+            for a in srcs:
+                if a.needs_grad:
+                    for j in live:
+                        co = layers[j][1]
+                        gbuf, acc = self.grad_buffer(a)
+                        d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c],
+                                          [(cin * co, 1, co)], accumulate=acc, act_dtype=_code(outs[j].dtype),
+                                          out_dtype=_code(a.dtype), engine=eng)
+                        ops.conv3d(self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf])
+                off += a.c
+        else:
+            co = layers[0][1]
+            dy = outs[0].g
+            # ---- wgrad with swapped roles: dWt[tap, co, ci] += dy[i*s + k - pad, co] * x[i, ci]
+            gk = self.pg(layers[0][0] + "/kernel").view(-1)
+            off = 0
+            for a in srcs:
+                d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
+                                  act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=eng)
+                ops.conv3d_wgrad(self.ctx, d, [dy], [a.t], [gk[off:]], None)
+                off += a.c
+            ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
+            # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci]
+            off = 0
+            for a in srcs:
+                if a.needs_grad:
+                    gbuf, acc = self.grad_buffer(a)
+                    d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
+                                      accumulate=acc, act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype),
+                                      engine=eng)
+                    ops.conv3d(self.ctx, d, [dy], [ws[0].view(-1)[off:]], None, [gbuf])
+                off += a.c
+        for o in outs:
+            o.g = None
+
+    # ---- K4 instance norm + activation ---------------------------------------------------------
+    def inorm_act(self, x, name, slope):
+        c = x.c
+        gamma = self.p(name + "/gamma", (c,), "gamma")
+        beta = self.p(name + "/beta", (c,), "beta")
+        y = Act(x.shape, x.dtype, self.new(x.shape, x.dtype))
+        if self.tracing:
+            return y
+        stats = self.new((x.shape[0], c, 2), torch.float32)
+        ops.inorm_stats(self.ctx, x.t, stats, IN_EPS)
+        ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t)
+
+        def bwd():
+            if y.g is None:
+                return
+            gbuf, acc = self.grad_buffer(x)
+            ops.inorm_act_bwd(self.ctx, y.g, x.t, stats, gamma, beta, slope, gbuf, acc,
+                              self.pg(name + "/gamma"), self.pg(name + "/beta"))
+            y.g = None
+        if self.record:
+            self.tape.append(bwd)
+        return y
+
+    # ---- K5 SE tail: norm3/norm4 + squeeze + excite + gate*residual + lrelu + dropout -----------
+    def se_tail(self, raw3, raw4, name, reduction, drop):
+        """drop: None or (pass_name, site, rate)."""
+        c = raw3.c
+        cr = c // reduction
+        g3 = self.p(name + "/norm3/gamma", (c,), "gamma")
+        b3 = self.p(name + "/norm3/beta", (c,), "beta")
+        g4 = self.p(name + "/norm4/gamma", (c,), "gamma")
+        b4 = self.p(name + "/norm4/beta", (c,), "beta")
+        w6 = self.p(name + "/conv6/kernel", (1, 1, 1, c, cr), "se_kernel")
+        b6 = self.p(name + "/conv6/bias", (cr,), "se_bias")
+        w7 = self.p(name + "/conv7/kernel", (1, 1, 1, cr, c), "se_kernel")
+        b7 = self.p(name + "/conv7/bias", (c,), "se_bias")
+        out = Act(raw3.shape, raw3.dtype, self.new(raw3.shape, raw3.dtype))
+        if self.tracing:
+            return out
+        n = raw3.shape[0]
+        f32 = torch.float32
+        st3, st4 = self.new((n, c, 2), f32), self.new((n, c, 2), f32)
+        ops.inorm_stats(self.ctx, raw3.t, st3, IN_EPS)
+        ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
+        pool, hidden, gate = self.new((n, c), f32), self.new((n, cr), f32), self.new((n, c), f32)
+        ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
+        ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
+        if drop is not None and drop[2] > 0.0:
+            dr, keep_alive = self.noise.dropout(self, drop[0], drop[1], raw3.shape, drop[2])
+        else:
+            dr, keep_alive = ops.make_dropout(0.0), None
+        ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t)
+
+        def bwd():
+            if out.g is None:
+                return
+            _ = keep_alive
+            red = self.new((n, c, 5), f32)
+            dgate, dpool = self.new((n, c), f32), self.new((n, c), f32)
+            ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red, dgate)
+            ops.se_excite_bwd(self.ctx, dgate, pool, hidden, gate, w6, w7, dpool,
+                              self.pg(name + "/conv6/kernel"), self.pg(name + "/conv6/bias"),
+                              self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"))
+            assert raw3.g is None and raw4.g is None
+            raw3.g = self.new(raw3.shape, raw3.dtype)
+            raw4.g = self.new(raw4.shape, raw4.dtype)
+            ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red, dpool,
+                                  raw3.g, raw4.g, self.pg(name + "/norm3/gamma"), self.pg(name + "/norm3/beta"),
+                                  self.pg(name + "/norm4/gamma"), self.pg(name + "/norm4/beta"))
+            out.g = None
+        if self.record:
+            self.tape.append(bwd)
+        return out
+
+    # ---- K6 attention gate core ------------------------------------------------------------------
+    def attn_core(self, theta, phi, x, name):
+        f = theta.c
+        wpsi = self.p(name + "/conv3/kernel", (1, 1, 1, f, 1), "kernel")
+        bpsi = self.p(name + "/conv3/bias", (1,), "bias")
+        y = Act(x.shape, x.dtype, self.new(x.shape, x.dtype))
+        if self.tracing:
+            return y
+        psi = self.new((theta.shape[0],) + theta.grid, torch.float32)
+        ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t)
+
+        def bwd():
+            if y.g is None:
+                return
+            assert theta.g is None
+            theta.g = self.new(theta.shape, theta.dtype)
+            dphi = self.new(phi.shape, torch.float32, zero=True)
+            if x.needs_grad:
+                gx, acc = self.grad_buffer(x)
+            else:
+                gx, acc = self.new(x.shape, x.dtype), False
+            ops.attn_bwd(self.ctx, y.g, theta.t, phi.t, wpsi, psi, x.t, gx, acc, theta.g, dphi,
+                         self.pg(name + "/conv3/kernel"), self.pg(name + "/conv3/bias"))
+            if phi.g is None:
+                phi.g = self.new(phi.shape, phi.dtype)
+                ops.cast(self.ctx, dphi, phi.g)
+            else:
+                tmp = self.new(phi.shape, phi.dtype)
+                ops.cast(self.ctx, dphi, tmp)
+                ops.axpy(self.ctx, tmp, 1.0, phi.g)
+            y.g = None
+        if self.record:
+            self.tape.append(bwd)
+        return y
+
+    # ---- K7 latent heads ----------------------------------------------------------------------------
+    def latent(self, ml, mode, eps):
+        """ml: fp32 [.., 2L]; mode 0 sample (eps fp32 tensor), 1 mean."""
+        L = ml.c // 2
+        z = Act(ml.shape[:-1] + (L,), self.act_dtype, self.new(ml.shape[:-1] + (L,)))
+        if self.tracing:
+            return z
+        ops.latent_fwd(self.ctx, ml.t, eps, mode, z.t)
+
+        def bwd():
+            if z.g is None:
+                return
+            gbuf, _ = self.grad_buffer(ml, zero=True)
+            ops.latent_bwd(self.ctx, z.g, ml.t, eps, mode, gbuf)
+            z.g = None
+        if self.record:
+            self.tape.append(bwd)
+        return z
+
+    def kl(self, ml_q, ml_p, kl_out):
+        if self.tracing:
+            return
+        ops.kl_fwd(self.ctx, ml_q.t, ml_p.t, kl_out)
+
+    def kl_seed_grad(self, ml_q, ml_p, scale):
+        gq, _ = self.grad_buffer(ml_q, zero=True)
+        gp, _ = self.grad_buffer(ml_p, zero=True)
+        ops.kl_bwd(self.ctx, ml_q.t, ml_p.t, scale, gq, gp)

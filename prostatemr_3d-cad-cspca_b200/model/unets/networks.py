@@ -1,0 +1,635 @@
+"""Mirror of tf2.5/scripts/model/unets/networks.py: the M1 (Hierarchical Probabilistic) 3D U-Net.
+
+  M1        top-level model, constructor kwargs / compile / fit / get_detect_model   R:networks.py:24-223
+  m1 wiring deterministic and probabilistic branches, 4 live passes, KL, softmax     R:networks.py:232-392
+  M1Core    stem, SE-ResNet encoder, attention gates, nested decoder, latent decoder R:networks.py:402-782
+
+Everything here is host logic: it decides WHICH sm_100a kernels run on WHICH buffers (through
+Engine) - all arithmetic happens in libm1b200.so. Quirks Q1-Q9 of the reference are
+reproduced or shimmed exactly as documented next to each.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from ... import ops
+from .. import initializers, regularizers
+from ..losses import EvidenceLowerBound, Focal
+from ..optimizers import Adam
+from .engine import LRELU, Act, Engine, InjectedNoise, PhiloxNoise
+from .modelio import LoadableModel, store_config_args
+from .network_blocks import GridAttentionBlock3D, SEResNetBottleNeck, StitchingProbDecoder
+from .params import ParamTable
+
+
+# ---------------------------------------------------------------------------------------------
+# M1Core (R:networks.py:402-782)
+# ---------------------------------------------------------------------------------------------
+class M1Core:
+    def __init__(self, net,
+                 num_classes=2, dropout_mode='standard', dropout_rate=0.50,
+                 filters=(32, 64, 128, 256, 512),
+                 strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (1, 2, 2)),
+                 kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
+                 se_reduction=(8, 8, 8, 8, 8),
+                 att_sub_samp=((1, 1, 1), (1, 1, 1), (1, 1, 1), (1, 1, 1)),
+                 dense_skip=False, deep_supervision=False, probabilistic=False,
+                 prob_latent_dims=(1, 1, 1, 1)):
+        self.net = net
+        self.num_classes, self.dropout_mode, self.dropout_rate = num_classes, dropout_mode, dropout_rate
+        self.filters, self.strides, self.kernel_sizes = filters, strides, kernel_sizes
+        self.se_reduction, self.att_sub_samp = se_reduction, att_sub_samp
+        self.dense_skip, self.deep_supervision = dense_skip, deep_supervision
+        self.probabilistic, self.prob_latent_dims = probabilistic, prob_latent_dims
+        # R:networks.py:465-469
+        assert len(self.filters) == 5, "ERROR: Expected Tuple/Array with 5 Values (One Per Resolution)."
+        assert len(self.se_reduction) == 5, "ERROR: Expected Tuple/Array with 5 Values (One Per Resolution)."
+        assert [len(a) for a in self.att_sub_samp] == [3, 3, 3, 3], \
+            "ERROR: Expected 4x3 Tuple/Array (3D Sub-Sampling Factors for 4 Attention Gates)."
+        assert [len(s) for s in self.strides] == [3, 3, 3, 3, 3], \
+            "ERROR: Expected 5x3 Tuple/Array (3D Strides for 5 Resolutions)."
+        assert [len(k) for k in self.kernel_sizes] == [3, 3, 3, 3, 3], \
+            "ERROR: Expected 5x3 Tuple/Array (3D Kernels for 5 Resolutions)."
+        assert dropout_mode in ('standard', 'monte-carlo')
+        F, S, K, R = filters, strides, kernel_sizes, se_reduction
+        n = lambda s: net + '/' + s  # noqa: E731
+        one = (1, 1, 1)
+        self.serse = [None] + [SEResNetBottleNeck(F[i], K[i], S[i], R[i], n('serse%d' % i)) for i in range(1, 5)]
+        self.att = [GridAttentionBlock3D(F[i], att_sub_samp[i], n('att%d' % i)) for i in range(4)]
+        self.sersd = [SEResNetBottleNeck(F[i], K[i], one, R[i], n('sersd%d' % i)) for i in range(4)]
+        Fr, Kr, Rr = F[::-1], K[::-1], R[::-1]
+        # sersp{3-i}: filters F[::-1][i+1], kernel K[::-1][i+1], reduction R[::-1][i+1]  (R:networks.py:554-561)
+        self.sersp = {3 - i: SEResNetBottleNeck(Fr[i + 1], Kr[i + 1], one, Rr[i + 1], n('sersp%d' % (3 - i)))
+                      for i in range(4)}
+        self.shapes = {}
+
+    def __call__(self, eng, inputs, prob_mean=False, prob_z_q=None, pass_name='det', training=True,
+                 stop='full', need_logits=True):
+        """inputs: list of Acts forming the (virtual) input concatenation.
+        stop='latents' is the Keras-pruned partial pass: only what feeds the last latent head."""
+        F, S, K = self.filters, self.strides, self.kernel_sizes
+        net = self.net
+        n = lambda s: net + '/' + s  # noqa: E731
+        L = self.prob_latent_dims
+        prob = self.probabilistic
+        partial = stop == 'latents'
+        last_lat = max([i for i in range(len(L)) if L[i] != 0], default=-1) if prob else -1
+        drop_on = training or self.dropout_mode == 'monte-carlo'
+        rate = self.dropout_rate
+
+        def drop(site, r=rate):
+            return (pass_name, site, r) if (drop_on and r > 0.0) else None
+
+        need = lambda lvl: (not partial) or (3 - lvl) < last_lat  # noqa: E731 - is uconv{lvl}_ needed?
+        out = {}
+        # stem (R:networks.py:574-576)
+        raw, = eng.conv(inputs, [(n('conve0'), F[0])], K[0], S[0])
+        x = eng.inorm_act(raw, n('norme0'), LRELU)
+        # encoder (R:networks.py:579-582); the dropouts are fused into the SE gate kernel
+        conv1 = self.serse[1](eng, [x], drop('drope1'))
+        conv2 = self.serse[2](eng, [conv1], drop('drope2'))
+        conv3 = self.serse[3](eng, [conv2], drop('drope3'))
+        convm = self.serse[4](eng, [conv3], drop('drope4'))
+        enc = [x, conv1, conv2, conv3]
+        # attention gates (R:networks.py:585-588): the gating signal is always convm
+        att = [self.att[i](eng, enc[i], convm) if need(i) else None for i in range(4)]
+
+        dense = self.dense_skip
+        uconv, uconv_ = [None] * 4, [None] * 4
+        ct = lambda name, src, f, k, s: eng.conv([src], [(n(name), f)], k, s, transposed=True)[0]  # noqa: E731
+        if need(3):       # decoder stage 3 (R:networks.py:591-597)
+            deconv3 = ct('convtd3', convm, F[3], K[4], S[4])
+            if dense and need(2):
+                deconv3_up1 = ct('convtd3_up1', deconv3, F[2], K[3], S[3])
+                if need(1):
+                    deconv3_up2 = ct('convtd3_up2', deconv3_up1, F[1], K[2], S[2])
+                    if need(0):
+                        deconv3_up3 = ct('convtd3_up3', deconv3_up2, F[0], K[1], S[1])
+            uconv_[3] = [deconv3, att[3]]
+        if need(2):       # stage 2 (R:networks.py:600-607)
+            uconv[3] = self.sersd[3](eng, uconv_[3], drop('dropd3'))
+            deconv2 = ct('convtd2', uconv[3], F[2], K[3], S[3])
+            if dense:
+                if need(1):
+                    deconv2_up1 = ct('convtd2_up1', deconv2, F[1], K[2], S[2])
+                    if need(0):
+                        deconv2_up2 = ct('convtd2_up2', deconv2_up1, F[0], K[1], S[1])
+                uconv_[2] = [deconv2, deconv3_up1, att[2]]
+            else:
+                uconv_[2] = [deconv2, att[2]]
+        if need(1):       # stage 1 (R:networks.py:610-616)
+            uconv[2] = self.sersd[2](eng, uconv_[2], drop('dropd2'))
+            deconv1 = ct('convtd1', uconv[2], F[1], K[2], S[2])
+            if dense:
+                if need(0):
+                    deconv1_up1 = ct('convtd1_up1', deconv1, F[0], K[1], S[1])
+                uconv_[1] = [deconv1, deconv2_up1, deconv3_up2, att[1]]
+            else:
+                uconv_[1] = [deconv1, att[1]]
+        if need(0):       # stage 0 (R:networks.py:619-624)
+            uconv[1] = self.sersd[1](eng, uconv_[1], drop('dropd1'))
+            deconv0 = ct('convtd0', uconv[1], F[0], K[1], S[1])
+            if dense:
+                uconv_[0] = [deconv0, deconv1_up1, deconv2_up2, deconv3_up3, att[0]]
+            else:
+                uconv_[0] = [deconv0, att[0]]
+        if not partial and need_logits:
+            uconv[0] = self.sersd[0](eng, uconv_[0], drop('dropd0', rate / 2))      # R:networks.py:523
+            out['logits'], = eng.conv([uconv[0]], [(n('logits'), self.num_classes)], (1, 1, 1),
+                                      out_dtype=torch.float32)
+        self.shapes = dict(inputs=[a.shape for a in inputs], x=x.shape, conv1=conv1.shape, conv2=conv2.shape,
+                           conv3=conv3.shape, convm=convm.shape,
+                           att=[None if a is None else a.shape for a in att],
+                           uconv_=[None if u is None else u[0].shape[:-1] + (sum(a.c for a in u),) for u in uconv_],
+                           uconv=[None if u is None else u.shape for u in uconv])
+
+        ds_feats = {}
+        if prob:          # hierarchical latent decoder (R:networks.py:633-734)
+            dists, used = [], []
+            feat = convm
+            Fr, Kr, Sr = F[::-1], K[::-1], S[::-1]
+            for i in range(4):
+                lvl = 3 - i
+                if partial and i > last_lat:
+                    break
+                if L[i] != 0:
+                    ml, = eng.conv([feat], [(n('mu_logsig%d' % lvl), 2 * L[i])], (1, 1, 1), out_dtype=torch.float32)
+                    if prob_z_q is not None:
+                        z = prob_z_q[len(used)]
+                    elif prob_mean:
+                        z = eng.latent(ml, 1, None)
+                    else:
+                        eps = None if eng.tracing else eng.noise.normal(eng, pass_name, 'eps%d' % lvl,
+                                                                        ml.shape[:-1] + (L[i],))
+                        z = eng.latent(ml, 0, eps)
+                    dists.append(ml)
+                    used.append(z)
+                    if partial and i == last_lat:
+                        break
+                    hi_in = [z, feat]
+                else:
+                    hi_in = [feat]
+                up, = eng.conv(hi_in, [(n('dec_hi%d' % lvl), Fr[i + 1])], Kr[i], Sr[i], transposed=True)
+                feat = self.sersp[lvl](eng, [up] + uconv_[lvl], drop('dropp%d' % lvl))
+                ds_feats[lvl] = feat
+            out['prob_distributions'] = dists
+            out['prob_used_latents'] = used
+            if not partial:
+                out['prob_decoder_features'] = feat
+
+        if self.deep_supervision and not partial:
+            # R:networks.py:737-747. 1x1x1 conv and nearest up-sampling commute exactly, so the DS logits
+            # are computed at low resolution and up-sampled inside the loss kernel.
+            srcs = [uconv[1], uconv[2], uconv[3]] if not prob else [ds_feats[1], ds_feats[2], ds_feats[3]]
+            s1, s2, s3 = (np.array(S[i]) for i in (1, 2, 3))
+            ups = [tuple(int(v) for v in s1), tuple(int(v) for v in s1 * s2), tuple(int(v) for v in s1 * s2 * s3)]
+            out['ds_logits'] = []
+            for j, (t, u) in enumerate(zip(srcs, ups)):
+                lg, = eng.conv([t], [(n('dsy%d_logits' % (j + 1)), self.num_classes)], (1, 1, 1),
+                               out_dtype=torch.float32)
+                out['ds_logits'].append((lg, u))
+        return out
+
+    def summary(self):
+        """R:networks.py:761-782 (the shape listing; Q2)."""
+        s = self.shapes
+        rows = [('Input Volume:', s['inputs'][0][:-1] + (sum(i[-1] for i in s['inputs']),)),
+                ('Initial Convolutional Layer (Stage 0):', s['x']),
+                ('Attention Gating: Stage 0:', s['att'][0]), ('Encoder: Stage 1; SE-Residual Block:', s['conv1']),
+                ('Attention Gating: Stage 1:', s['att'][1]), ('Encoder: Stage 2; SE-Residual Block:', s['conv2']),
+                ('Attention Gating: Stage 2:', s['att'][2]), ('Encoder: Stage 3; SE-Residual Block:', s['conv3']),
+                ('Attention Gating: Stage 3:', s['att'][3]), ('Middle: High-Dim Latent Features:', s['convm']),
+                ('Decoder: Stage 3; Nested U-Net Concat.:', s['uconv_'][3]),
+                ('Decoder: Stage 3; Nested U-Net End:', s['uconv'][3]),
+                ('Decoder: Stage 2; Nested U-Net Concat.:', s['uconv_'][2]),
+                ('Decoder: Stage 2; Nested U-Net End:', s['uconv'][2]),
+                ('Decoder: Stage 1; Nested U-Net Concat.:', s['uconv_'][1]),
+                ('Decoder: Stage 1; Nested U-Net End:', s['uconv'][1]),
+                ('Decoder: Stage 0; Nested U-Net Concat.:', s['uconv_'][0]),
+                ('Decoder: Stage 0; Nested U-Net End:', s['uconv'][0])]
+        for label, shp in rows:
+            print((label + '-' * 60)[:60], None if shp is None else (None,) + tuple(shp[1:]))
+
+
+# ---------------------------------------------------------------------------------------------
+# one stage (R:networks.py:232-392) = parameters + engine + the pass wiring
+# ---------------------------------------------------------------------------------------------
+FUSION = {'identity': 0, True: 0, 'noisy-or': 1, 'bayes': 2}
+
+
+class M1(LoadableModel):
+    """
+    [1] Z. Zhou et al. (2019), UNet++. [2] J. Hu et al.(2019), Squeeze-and-Excitation Networks.
+    [3] S. Kohl et al. (2019), Hierarchical Probabilistic U-Net. [4] O. Oktay et al. (2018), Attention U-Net.
+
+    Constructor arguments up to `name` are the reference's (R:networks.py:34-55), same names, order,
+    defaults and assertions. The keyword-only arguments after it are additions of this implementation:
+      precision   'bf16' (tcgen05 tensor-core convolutions, bf16 activations) | 'fp32' (CUDA-core fp32)
+      ds_in_prob  'reference': probabilistic + deep_supervision == no deep supervision (Q3, 2 output channels)
+                  'intended' : wires the dead ds_ops branch (R:networks.py:743-747), 4 heads
+      seed        parameter-initialisation and Philox seed;   device: CUDA device (None: current)
+      build       False -> host-only object (configuration + parameter inventory, no GPU needed)
+    """
+
+    @store_config_args
+    def __init__(self,
+                 input_spatial_dims,
+                 input_channels,
+                 num_classes,
+                 dropout_rate=0.50,
+                 dropout_mode='standard',
+                 filters=(32, 64, 128, 256, 512),
+                 strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (1, 2, 2)),
+                 kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
+                 se_reduction=(8, 8, 8, 8, 8),
+                 att_sub_samp=((1, 1, 1), (1, 1, 1), (1, 1, 1)),
+                 kernel_initializer=initializers.Orthogonal(gain=1.0),
+                 bias_initializer=initializers.TruncatedNormal(mean=0.0, stddev=0.001),
+                 kernel_regularizer=regularizers.l2(1e-4),
+                 bias_regularizer=regularizers.l2(1e-4),
+                 cascaded=False,
+                 dense_skip=False,
+                 deep_supervision=False,
+                 probabilistic=False,
+                 prob_latent_dims=(3, 2, 1),
+                 summary=True,
+                 name='UNET-TYPE-M1',
+                 *, precision='bf16', ds_in_prob='reference', seed=0, device=None, build=None,
+                 use_tcgen05=True, compute_dead_branches=False):
+        ndims = len(input_spatial_dims)
+        assert ndims in [1, 2, 3], 'Variable (ndims) should be  1, 2 or 3. Found: %d.' % ndims
+        assert ndims == 3, 'the sm_100a kernels implement the 3-D model (the only one M1Core can build)'
+        assert ds_in_prob in ('reference', 'intended')
+        if cascaded is not False:
+            raise NotImplementedError("cascaded two-stage M1 (R:networks.py:109-193): use CascadedM1")
+        self.name = name
+        self.input_spatial_dims = tuple(int(d) for d in input_spatial_dims)
+        self.input_channels, self.num_classes = int(input_channels), int(num_classes)
+        self.probabilistic, self.deep_supervision = bool(probabilistic), bool(deep_supervision)
+        self.ds_in_prob, self.precision = ds_in_prob, precision
+        self.compute_dead_branches = compute_dead_branches
+        self.use_tcgen05 = use_tcgen05
+        self.l2_kernel = regularizers.coefficient(kernel_regularizer)
+        self.l2_bias = regularizers.coefficient(bias_regularizer)
+        core_kw = dict(num_classes=num_classes, dropout_mode=dropout_mode, dropout_rate=dropout_rate,
+                       filters=tuple(filters), strides=tuple(tuple(s) for s in strides),
+                       kernel_sizes=tuple(tuple(k) for k in kernel_sizes), se_reduction=tuple(se_reduction),
+                       att_sub_samp=tuple(tuple(a) for a in att_sub_samp), dense_skip=dense_skip)
+        if not probabilistic:
+            # Q1: the reference calls M1Core(...)(inputs=inputs) without prob_mean/prob_z_q (TypeError on
+            # HEAD); the intended semantics prob_mean=False, prob_z_q=None are implemented.
+            self.core = M1Core('m1', deep_supervision=deep_supervision, probabilistic=False, **core_kw)
+            self.heads = 4 if deep_supervision else 1
+        else:
+            # Q3: deep_supervision is NOT forwarded to the prior/posterior cores by the reference
+            ds = bool(deep_supervision) and ds_in_prob == 'intended'
+            kw = dict(core_kw, deep_supervision=ds, probabilistic=True, prob_latent_dims=tuple(prob_latent_dims))
+            self.prior = M1Core('prior', **kw)
+            self.posterior = M1Core('posterior', **dict(kw, deep_supervision=False))
+            self.final_decoder = StitchingProbDecoder(num_classes)
+            self.heads = 4 if ds else 1
+
+        # ---- parameter inventory: a shape-only trace of one training step (Keras builds on first call)
+        self.params = ParamTable()
+        tracer = Engine(self.params, precision, device=None)
+        self._graph(tracer, batch=1, training=True, trace=True)
+        if probabilistic:
+            self._infer_graph(tracer, batch=1, trace=True)
+        self.params.finalize()
+        self.train_flops_per_volume = None
+
+        # ---- references (R:networks.py:93-106)
+        self.references = LoadableModel.ReferenceContainer()
+        self.references.cascaded = cascaded
+        self.references.probabilistic = probabilistic
+        self.references.num_classes = num_classes
+        self.references.m1_model = self
+        if summary:
+            self.summary()
+
+        self.optimizer = None
+        self.focal, self.elbo, self.loss_weights = None, None, [1.0, 1.0]
+        self.world_size, self.rank, self.grad_sync = 1, 0, None
+        self.eng = None
+        self._init_kw = dict(kernel=kernel_initializer, bias=bias_initializer, seed=seed)
+        self.noise = None
+        self.history = None
+        if build is None:
+            build = torch.cuda.is_available()
+        if build:
+            self.build(device)
+
+    # ---- construction ---------------------------------------------------------------------------
+    def build(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("M1.build: no CUDA device - m1b200 has no CPU / PyTorch fallback")
+        if device is None:
+            device = 'cuda:%d' % torch.cuda.current_device()
+        self.device = torch.device(device)
+        self.params.allocate(self.device)
+        kinds = dict(kernel=self._init_kw['kernel'], bias=self._init_kw['bias'],
+                     se_kernel=initializers.GlorotUniform(), se_bias=initializers.Zeros(),
+                     gamma=initializers.Ones(), beta=initializers.Zeros())
+        self.params.initialize(kinds, self._init_kw['seed'])
+        self.eng = Engine(self.params, self.precision, device=self.device, use_tcgen05=self.use_tcgen05)
+        self.noise = PhiloxNoise(seed=42 + self._init_kw['seed'], rank=self.rank)
+        return self
+
+    def summary(self):
+        print('-' * 85)
+        if self.probabilistic:
+            print('Hierarchical Prob. 3D U-Net (Type: M1) - Prior Network')
+            print('-' * 85)
+            self.prior.summary()
+            print('-' * 85)
+            print('Hierarchical Prob. 3D U-Net (Type: M1) - Posterior Network (live layers)')
+        else:
+            print('Deterministic 3D U-Net (Type: M1)')
+            print('-' * 85)
+            self.core.summary()
+        print('-' * 85)
+        print('Parameters: %d (conv %d, SE excite %d, InstanceNorm %d)' % (
+            self.params.num_params(), self.params.num_params(('kernel', 'bias')),
+            self.params.num_params(('se_kernel', 'se_bias')), self.params.num_params(('gamma', 'beta'))))
+        print('-' * 85)
+
+    # ---- graph wiring (R:networks.py:266-390) ------------------------------------------------------
+    def _inputs(self, eng, batch, x, trace):
+        """Model input -> activation tensors. Probabilistic (Q4, R:networks.py:300-301):
+        image = inputs[..., :-(nc-1)], label = inputs[..., -(nc-1)-1:-1] - for nc=2, C=4 the 'label' is
+        image channel 2, NOT channel 3; the slicing is reproduced exactly."""
+        D = self.input_spatial_dims
+        C, nc = self.input_channels, self.num_classes
+        if not self.probabilistic:
+            if trace:
+                return [eng.input((batch,) + D + (C,))], None
+            img = eng.new((batch,) + D + (C,))
+            ops.copy_channels(eng.ctx, x, 0, img, 0, C)
+            return [eng.input(img)], None
+        ci = C - (nc - 1)
+        lab_lo, lab_hi = C - (nc - 1) - 1, C - 1
+        cl = lab_hi - lab_lo
+        if trace:
+            return [eng.input((batch,) + D + (ci,))], [eng.input((batch,) + D + (cl,))]
+        img = eng.new((batch,) + D + (ci,))
+        lab = eng.new((batch,) + D + (cl,))
+        ops.copy_channels(eng.ctx, x, 0, img, 0, ci)
+        ops.copy_channels(eng.ctx, x, lab_lo, lab, 0, cl)
+        return [eng.input(img)], [eng.input(lab)]
+
+    def _graph(self, eng, batch, training, trace=False, x=None):
+        """One training-graph forward. Returns dict(heads=[(logits Act, up)], kl_pairs=[(ml_q, ml_p)])."""
+        img, lab = self._inputs(eng, batch, x, trace)
+        if not self.probabilistic:
+            o = self.core(eng, img, pass_name='det', training=training)
+            heads = [(o['logits'], (1, 1, 1))] + (o.get('ds_logits') or [])
+            return dict(heads=heads, kl_pairs=[])
+        post_in = img + lab
+        q_sample = self.posterior(eng, post_in, False, None, 'q_sample', training, 'latents')
+        q_mean = self.posterior(eng, post_in, True, None, 'q_mean', training, 'latents')
+        p_zq = self.prior(eng, img, False, q_sample['prob_used_latents'], 'p_z_q', training, 'latents')
+        dead = trace or self.compute_dead_branches or self.prior.deep_supervision
+        p_zqm = self.prior(eng, img, False, q_mean['prob_used_latents'], 'p_z_qmean', training, 'full',
+                           need_logits=dead)
+        train_conv = self.final_decoder(eng, p_zqm['prob_decoder_features'])
+        heads = [(train_conv, (1, 1, 1))] + (p_zqm.get('ds_logits') or [])
+        return dict(heads=heads,
+                    kl_pairs=list(zip(q_sample['prob_distributions'], p_zq['prob_distributions'])))
+
+    def _infer_graph(self, eng, batch, trace=False, x=None, pass_name='p_sample'):
+        """get_detect_model() graph (R:networks.py:196-206, :350,:355)."""
+        img, _ = self._inputs(eng, batch, x, trace)
+        if not self.probabilistic:
+            o = self.core(eng, img, pass_name='det', training=False)
+            return o['logits']
+        p_s = self.prior(eng, img, False, None, pass_name, False, 'full', need_logits=False)
+        return self.final_decoder(eng, p_s['prob_decoder_features'])
+
+    # ---- Keras-style API ---------------------------------------------------------------------------
+    def compile(self, optimizer=None, loss=None, loss_weights=None, **_):
+        """unet_model.compile(optimizer, loss=[Focal.loss, ELBO.loss], loss_weights=[1, 10])
+        (train_model.py:231, README.md:60-61). `loss` entries are the bound .loss methods (or the objects)."""
+        self.optimizer = optimizer if optimizer is not None else Adam(1e-3, amsgrad=True)
+        if not getattr(self.optimizer, 'amsgrad', True):
+            raise NotImplementedError("only Adam(amsgrad=True) (train_model.py:120) has a fused kernel")
+        losses = loss if isinstance(loss, (list, tuple)) else [loss]
+        objs = [getattr(ls, '__self__', ls) for ls in losses if ls is not None]
+        self.focal = next((o for o in objs if isinstance(o, Focal)), Focal())
+        self.elbo = next((o for o in objs if isinstance(o, EvidenceLowerBound)), EvidenceLowerBound())
+        if len(self.focal.alpha) != self.num_classes:      # train_model.py:148-149
+            raise Exception("Number of Class Weights Declared in Loss Function != Number of Classes in "
+                            "Labels/Loss Objective")
+        lw = list(loss_weights) if loss_weights is not None else [1.0] * max(1, len(losses))
+        self.loss_weights = [float(lw[0]), float(lw[1]) if len(lw) > 1 else 1.0]
+        return self
+
+    def set_noise(self, tensors=None, seed=None):
+        """noise injection for parity runs: {(pass_name, site): tensor}; None -> Philox."""
+        if tensors is not None:
+            self.noise = InjectedNoise(tensors)
+        else:
+            self.noise = PhiloxNoise(seed if seed is not None else 42, self.rank)
+
+    def _to_device(self, a, dtype=torch.float32):
+        if isinstance(a, dict):
+            a = a.get('image', a.get('detection'))
+        t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
+        return t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def train_step(self, x, y_true, apply_update=True):
+        """Forward of the 4-pass graph, focal + KL losses, full backward, (all-reduce), Adam-AMSGrad.
+        x: (B,D,H,W,C) fp32, y_true: one-hot (B,D,H,W,nc). Returns dict of device scalars."""
+        if self.eng is None:
+            raise RuntimeError("M1.train_step: model not built on a GPU (m1b200 has no CPU fallback)")
+        if self.optimizer is None:
+            self.compile()
+        eng = self.eng
+        x = self._to_device(x)
+        y = self._to_device(y_true)
+        B = x.shape[0]
+        eng.noise = self.noise
+        eng.begin(record=True)
+        self.params.g.zero_()
+        g = self._graph(eng, B, training=True, x=x)
+        if self.train_flops_per_volume is None:
+            self.train_flops_per_volume = 3 * eng.conv_flops // B
+        nc = self.num_classes
+        heads = g['heads']
+        det = torch.empty((B,) + self.input_spatial_dims + (nc * len(heads),), dtype=torch.float32,
+                          device=self.device)
+        scal = torch.zeros(4, dtype=torch.float32, device=self.device)   # focal, kl, l2, unused
+        inv_r = 1.0 / self.world_size
+        w_f, w_kl = self.loss_weights
+        for hi, (lg, up) in enumerate(heads):
+            gbuf, _ = eng.grad_buffer(lg, zero=True)
+            ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
+                              1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
+        for ml_q, ml_p in g['kl_pairs']:
+            eng.kl(ml_q, ml_p, scal[1:2])
+            eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
+        eng.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.params.g)
+        if apply_update:
+            self._apply_update(scal[2:3], inv_r)
+        if isinstance(self.noise, PhiloxNoise):
+            self.noise.step += 1
+        return dict(detection=det, focal=scal[0:1], kl=scal[1:2], l2=scal[2:3])
+
+    def _apply_update(self, l2_out, gscale=1.0):
+        opt, P = self.optimizer, self.params
+        lr_t = opt.lr_t()
+        for grp, l2 in (('kernel', self.l2_kernel), ('bias', self.l2_bias), ('plain', 0.0)):
+            a, b = P.group_range[grp]
+            if b > a:
+                # L2 term of every rank is scaled 1/R like the data term (MirroredStrategy semantics)
+                ops.adam_amsgrad(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b], lr_t,
+                                 opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0, l2_out if l2 > 0 else None)
+        opt.iterations += 1
+        self.eng.refresh_packs()
+
+    def total_loss(self, r):
+        """loss value Keras would log: w_f * focal + w_kl * beta * KL + sum(L2)."""
+        w_f, w_kl = self.loss_weights
+        return w_f * r['focal'] + w_kl * self.elbo.beta * r['kl'] + r['l2']
+
+    def fit(self, x=None, y=None, epochs=1, steps_per_epoch=None, initial_epoch=0, verbose=2, callbacks=None,
+            **_):
+        """unet_model.fit(x=dataset, epochs, steps_per_epoch, initial_epoch, verbose, callbacks)
+        (train_model.py:253-259). `x` is an iterable of (inputs, targets) with inputs {'image': ...} and
+        targets {'detection': one-hot, 'KL': ...} (train_model.py:153-164), or arrays x, y."""
+        history = {'loss': [], 'detection_loss': [], 'KL_loss': []}
+        if y is not None:
+            data = [(x, y)]
+            steps_per_epoch = steps_per_epoch or 1
+        else:
+            data = x
+        it = iter(data)
+        for cb in callbacks or []:
+            getattr(cb, 'on_train_begin', lambda logs=None: None)()
+        for epoch in range(initial_epoch, epochs):
+            t0 = time.time()
+            acc = torch.zeros(3, dtype=torch.float64)
+            steps = 0
+            while steps_per_epoch is None or steps < steps_per_epoch:
+                try:
+                    inputs, targets = next(it)
+                except StopIteration:
+                    if steps_per_epoch is None:
+                        break
+                    it = iter(data)
+                    inputs, targets = next(it)
+                r = self.train_step(inputs, targets)
+                acc += torch.stack([self.total_loss(r)[0], self.loss_weights[0] * r['focal'][0],
+                                    r['kl'][0] * self.elbo.beta]).double().cpu()
+                steps += 1
+            logs = {k: float(v / max(steps, 1)) for k, v in zip(history, acc)}
+            for k, v in logs.items():
+                history[k].append(v)
+            if verbose:
+                print('Epoch %d/%d - %.1fs - loss: %.4f - detection_loss: %.4f - KL_loss: %.4f' % (
+                    epoch + 1, epochs, time.time() - t0, logs['loss'], logs['detection_loss'], logs['KL_loss']))
+            for cb in callbacks or []:
+                getattr(cb, 'on_epoch_end', lambda e, logs=None: None)(epoch, logs)
+            it = iter(data) if steps_per_epoch is None else it
+        self.history = history
+        return history
+
+    def __call__(self, x, training=False):
+        return self.predict_train_graph(x) if training else self.get_detect_model()(x)
+
+    def predict_train_graph(self, x, y_true=None):
+        """outputs of the training model: [detection (softmax of train_conv [+DS heads]), KL]."""
+        eng = self.eng
+        x = self._to_device(x)
+        B = x.shape[0]
+        eng.noise = self.noise
+        eng.begin(record=False)
+        g = self._graph(eng, B, training=True, x=x)
+        nc = self.num_classes
+        det = torch.empty((B,) + self.input_spatial_dims + (nc * len(g['heads']),), dtype=torch.float32,
+                          device=self.device)
+        kl = torch.zeros(1, dtype=torch.float32, device=self.device)
+        for hi, (lg, up) in enumerate(g['heads']):
+            ops.softmax_focal(eng.ctx, lg.t, None, None, 0.0, up, det, nc * hi, 0.0, None, None, 0.0)
+        for ml_q, ml_p in g['kl_pairs']:
+            eng.kl(ml_q, ml_p, kl)
+        return [det, kl]
+
+    def get_detect_model(self):
+        """R:networks.py:196-206: model reconfigured to predict segment probabilities only."""
+        return DetectModel(self)
+
+    # ---- weights / optimizer state -------------------------------------------------------------------
+    def get_weights(self):
+        return self.params.state_dict()
+
+    def set_weights(self, weights, strict=True):
+        self.params.load_state_dict(weights, strict)
+        if self.eng is not None:
+            self.eng.refresh_packs()
+
+    def gradients(self):
+        return {n: self.params.grad(n) for n in self.params.specs}
+
+    def get_optimizer_state(self):
+        P = self.params
+        return dict(m=P.m.cpu().numpy(), v=P.v.cpu().numpy(), vhat=P.vhat.cpu().numpy(),
+                    iterations=np.array([self.optimizer.iterations if self.optimizer else 0]))
+
+    def set_optimizer_state(self, st):
+        P = self.params
+        for k in ('m', 'v', 'vhat'):
+            getattr(P, k).copy_(torch.from_numpy(np.asarray(st[k])))
+        if self.optimizer is None:
+            self.compile()
+        self.optimizer.iterations = int(np.asarray(st['iterations'])[0])
+
+
+class DetectModel:
+    """tf.keras.Model(inputs, softmax(infer_conv)) of R:networks.py:205-206: one prior pass with
+    z ~ P at every level (probabilistic) or the deterministic pass, first num_classes channels."""
+
+    def __init__(self, model):
+        self.model = model
+        self._pass = 0
+
+    def __call__(self, x):
+        return self.predict(x)
+
+    def predict(self, x, pass_name='p_sample'):
+        m = self.model
+        if m.eng is None:
+            raise RuntimeError("model not built on a GPU (m1b200 has no CPU fallback)")
+        eng = m.eng
+        x = m._to_device(x)
+        B = x.shape[0]
+        eng.noise = m.noise
+        eng.begin(record=False)
+        lg = m._infer_graph(eng, B, x=x, pass_name=pass_name)
+        nc = m.num_classes
+        out = torch.empty((B,) + m.input_spatial_dims + (nc,), dtype=torch.float32, device=m.device)
+        ops.softmax_focal(eng.ctx, lg.t, None, None, 0.0, (1, 1, 1), out, 0, 0.0, None, None, 0.0)
+        if isinstance(m.noise, PhiloxNoise):
+            m.noise.step += 1
+        return out
+
+    def predict_mc(self, x, passes=20):
+        """Monte-Carlo dropout ensemble (BASELINE config 4): mean softmax of `passes` stochastic
+        prior passes with fresh Philox streams (the loop itself is not in the reference: the flag
+        UNET_PROBA_ITER of train_model.py:71 is unused there)."""
+        m = self.model
+        mean = None
+        for _ in range(passes):
+            p = self.predict(x)
+            if mean is None:
+                mean = torch.zeros_like(p)
+            ops.axpy(m.eng.ctx, p, 1.0 / passes, mean)
+        return mean
+
+
+def m1(*args, **kwargs):
+    """R:networks.py:232 - the mid-level wrapper is folded into M1 (one stage = one M1 object)."""
+    raise NotImplementedError("use M1(...): the functional m1() wiring lives in M1._graph")

@@ -201,11 +201,11 @@ def kl_bwd(ctx, ml_q, ml_p, scale, dml_q, dml_p):
 
 # ---- K8 softmax + focal ----------------------------------------------------------------------
 def softmax_focal(ctx, logits, y_true, alpha, gamma, up, prob, head_off, head_weight, loss_out, dlogits,
-                  grad_scale):
+                  grad_scale, from_probs=False):
     nc = logits.shape[-1]
     al = (C.c_float * nc)(*[float(a) for a in alpha]) if alpha is not None else None
     check(lib().m1_softmax_focal(
-        ctx.handle, ptr(logits), F32, ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
+        ctx.handle, ptr(logits), 2 if from_probs else F32, ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
         C.cast(al, C.c_void_p) if al is not None else None, gamma, logits.shape[0], _grid(logits),
         (C.c_int32 * 3)(*up), nc, ptr(prob), prob.shape[-1] if prob is not None else 0, head_off, head_weight,
         ptr(loss_out), ptr(dlogits), grad_scale, current_stream()))
@@ -235,3 +235,13 @@ def axpy(ctx, x, a, y):
 def decision_fusion(ctx, prior, follow, strategy, out):
     check(lib().m1_decision_fusion(ctx.handle, ptr(prior), ptr(follow), strategy, follow.numel(), ptr(out),
                                    current_stream()))
+
+
+def bias_grad(ctx, dout, dbias):
+    rows = dout.numel() // dout.shape[-1]
+    check(lib().m1_bias_grad(ctx.handle, ptr(dout), dtype_code(dout), rows, dout.shape[-1], ptr(dbias),
+                             current_stream()))
+
+
+def philox_normal(ctx, seed, stream_id, out):
+    check(lib().m1_philox_normal(ctx.handle, seed, stream_id, ptr(out), out.numel(), current_stream()))

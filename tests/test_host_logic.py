@@ -1,0 +1,135 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol of include/m1b200.h,
+the M1 constructor API / config capture, and the traced parameter inventory against the oracle's."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+import m1b200
+from m1b200 import _lib
+from m1b200.model import losses, optimizers, unets
+from oracle import m1_oracle as O
+
+README = dict(filters=(32, 64, 128, 256, 512),
+              strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (2, 2, 2)),
+              kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
+              se_reduction=(8, 8, 8, 8, 8), att_sub_samp=((1, 1, 1),) * 4)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "libm1b200.so not built (run __graft_entry__.build())"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    sigs = _lib.parse_header()
+    assert len(sigs) >= 30
+    for name in sigs:
+        assert hasattr(h, name), name
+    h.m1_version.restype = ctypes.c_int
+    assert h.m1_version() >= 100
+    # no compute without a GPU: creating a context must fail loudly, not fall back
+    if not torch.cuda.is_available():
+        lib = _lib.lib()
+        hnd = ctypes.c_void_p()
+        assert lib.m1_ctx_create(0, ctypes.byref(hnd)) != 0
+        assert b"no CPU fallback" in lib.m1_last_error()
+
+
+def test_no_cpu_fallback_in_model():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = unets.networks.M1((4, 16, 16), 3, 2, summary=False, **README)
+    with pytest.raises(RuntimeError):
+        m.train_step(torch.zeros(1, 4, 16, 16, 3), torch.zeros(1, 4, 16, 16, 2))
+    with pytest.raises(RuntimeError):
+        m.get_detect_model()(torch.zeros(1, 4, 16, 16, 3))
+
+
+def test_constructor_defaults_and_assertions():
+    # Q7: the class default att_sub_samp has 3 entries, M1Core asserts 4 -> AssertionError
+    with pytest.raises(AssertionError):
+        unets.networks.M1((4, 16, 16), 3, 2, summary=False)
+    with pytest.raises(AssertionError):
+        unets.networks.M1((4, 16, 16), 3, 2, summary=False, filters=(8, 16, 32, 64), att_sub_samp=((1, 1, 1),) * 4)
+    m = unets.networks.M1((4, 16, 16), 3, 2, summary=False, att_sub_samp=((1, 1, 1),) * 4)
+    cfg = m.get_config()
+    assert cfg['dropout_rate'] == 0.5 and cfg['dropout_mode'] == 'standard'
+    assert cfg['strides'][-1] == (1, 2, 2)                       # Q9: class default last stride
+    assert cfg['prob_latent_dims'] == (3, 2, 1) and cfg['name'] == 'UNET-TYPE-M1'
+    m2 = unets.networks.M1.from_config(cfg)
+    assert m2.params.num_params() == m.params.num_params()
+
+
+def test_param_inventory_matches_oracle_deterministic():
+    m = unets.networks.M1((4, 32, 32), 3, 2, summary=False, **README)
+    cfg = O.default_config(**{k: README[k] for k in ('filters', 'strides', 'kernel_sizes')})
+    ps = O.ParamStore(dtype=torch.float32)
+    O.m1_deterministic(ps, cfg, torch.zeros((1, 4, 32, 32, 3)), O.Noise(0, torch.float32), training=False)
+    ours = {n: sp.shape for n, sp in m.params.specs.items()}
+    theirs = {n: tuple(t.shape) for n, t in ps.p.items()}
+    assert ours == theirs
+    assert m.params.num_params(('kernel', 'bias', 'se_kernel', 'se_bias')) == 17517642
+    kinds = {n: sp.kind for n, sp in m.params.specs.items()}
+    assert kinds == dict(ps.kind)
+
+
+@pytest.mark.parametrize("ds_mode", ['reference', 'intended'])
+def test_param_inventory_matches_oracle_probabilistic(ds_mode):
+    m = unets.networks.M1((4, 32, 32), 4, 2, summary=False, dense_skip=True, deep_supervision=True,
+                          probabilistic=True, prob_latent_dims=(3, 2, 1, 0), dropout_mode='monte-carlo',
+                          ds_in_prob=ds_mode, **README)
+    cfg = O.default_config(dense_skip=True, deep_supervision=True, probabilistic=True,
+                           prob_latent_dims=(3, 2, 1, 0), dropout_mode='monte-carlo',
+                           **{k: README[k] for k in ('filters', 'strides', 'kernel_sizes')})
+    ps = O.ParamStore(dtype=torch.float32)
+    x, _ = O.synthetic_batch(1, (4, 32, 32))
+    O.m1_probabilistic(ps, cfg, x, O.Noise(0, torch.float32), ds_in_prob=ds_mode, with_infer=True)
+    ours = {n: sp.shape for n, sp in m.params.specs.items()}
+    theirs = {n: tuple(t.shape) for n, t in ps.p.items()}
+    assert set(ours) == set(theirs), (sorted(set(ours) ^ set(theirs))[:10])
+    assert ours == theirs
+    # ~64.0 M trainable parameters in the training graph
+    total = m.params.num_params()
+    assert 63_900_000 < total < 64_100_000, total
+    # flat layout: groups are contiguous, every parameter 64-float aligned
+    P = m.params
+    for sp in P.specs.values():
+        assert sp.offset % 64 == 0
+    (k0, k1), (b0, b1), (p0, p1) = (P.group_range[g] for g in ('kernel', 'bias', 'plain'))
+    assert k0 == 0 and k1 == b0 and b1 == p0 and p1 == P.total
+
+
+def test_compile_reads_reference_loss_objects():
+    m = unets.networks.M1((4, 16, 16), 4, 2, summary=False, probabilistic=True, prob_latent_dims=(3, 2, 1, 0),
+                          **README)
+    sched = optimizers.CosineDecayRestarts(1e-3, 100, t_mul=2.0, m_mul=1.0, alpha=1e-3)
+    m.compile(optimizer=optimizers.Adam(learning_rate=sched, amsgrad=True),
+              loss=[losses.Focal(alpha=[0.75, 0.25], gamma=2.0).loss, losses.EvidenceLowerBound().loss],
+              loss_weights=[1.0, 10.0])
+    assert m.focal.alpha == [0.75, 0.25] and m.loss_weights == [1.0, 10.0] and m.elbo.beta == 1.0
+    for step in (0, 1, 50, 99, 100, 150, 299, 300, 1234):
+        assert abs(sched(step) - O.cosine_decay_restarts(step, 1e-3, 100, 2.0, 1.0, 1e-3)) < 1e-15
+    with pytest.raises(Exception):
+        m.compile(loss=losses.Focal(alpha=[1.0, 1.0, 1.0]).loss)
+
+
+def test_store_config_args_semantics():
+    class Toy(unets.modelio.LoadableModel):
+        @unets.modelio.store_config_args
+        def __init__(self, a, b=2, *, c=3):
+            pass
+
+    assert Toy(1).get_config() == {'a': 1, 'b': 2, 'c': 3}
+    assert Toy(1, 5, c=7).get_config() == {'a': 1, 'b': 5, 'c': 7}
+
+    class Bare(unets.modelio.LoadableModel):
+        pass
+
+    with pytest.raises(RuntimeError):
+        Bare().get_config()
+
+
+def test_dlpack_pointer_export_rejects_cpu_memory():
+    t = torch.zeros(4)
+    with pytest.raises(_lib.M1Error):
+        _lib.ptr(t)
+    assert _lib.dlpack_device_ptr(t, expect_cuda=False) == t.data_ptr()

@@ -1,0 +1,184 @@
+"""Whole-model parity: M1 on the B200 (through the C-ABI) against the CPU oracle on identical
+weights, inputs and injected dropout / latent noise.
+
+Tolerances are the north star's: per-voxel softmax within 1e-4 abs (fp32 mode) / 2e-2 (bf16),
+KL and focal loss within 1e-3 relative, gradients by cosine similarity (>= 0.999 fp32, >= 0.98 bf16
+over the concatenated parameter gradient; per-tensor bounds stated below)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import m1_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+STRIDES = ((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (2, 2, 2))
+KERNELS = ((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3))
+TINY = dict(filters=(8, 16, 24, 32, 48), se_reduction=(4, 4, 4, 4, 4))
+MID = dict(filters=(32, 64, 128, 192, 256), se_reduction=(8, 8, 8, 8, 8))   # channel counts the tcgen05 engine takes
+
+
+def _build(arch, dims, batch, precision, probabilistic, dense, ds, ds_in_prob='reference', mode='monte-carlo',
+           seed=0):
+    from m1b200.model import losses, optimizers, unets
+    cin = 4 if probabilistic else 3
+    kw = dict(strides=STRIDES, kernel_sizes=KERNELS, att_sub_samp=((1, 1, 1),) * 4, dropout_rate=0.5,
+              dropout_mode=mode, dense_skip=dense, deep_supervision=ds, probabilistic=probabilistic,
+              prob_latent_dims=(3, 2, 1, 0), **arch)
+    model = unets.networks.M1(dims, cin, 2, summary=False, precision=precision, ds_in_prob=ds_in_prob, seed=seed,
+                              **kw)
+    model.compile(optimizer=optimizers.Adam(1e-3, amsgrad=True),
+                  loss=[losses.Focal(alpha=[0.75, 0.25], gamma=2.0).loss, losses.EvidenceLowerBound().loss],
+                  loss_weights=[1.0, 10.0])
+    cfg = O.default_config(num_classes=2, dropout_rate=0.5, dropout_mode=mode, strides=STRIDES,
+                           kernel_sizes=KERNELS, dense_skip=dense, deep_supervision=ds,
+                           probabilistic=probabilistic, prob_latent_dims=(3, 2, 1, 0),
+                           filters=arch['filters'], se_reduction=arch['se_reduction'])
+    x, y = O.synthetic_batch(batch, dims, probabilistic=probabilistic, seed=11)
+    return model, cfg, x, y
+
+
+def _oracle_step(cfg, x, y, ds_in_prob, dtype=torch.float64, seed=5, round_bf16=False):
+    ps = O.ParamStore(dtype=dtype, seed=3, requires_grad=True)
+    noise = O.Noise(seed, dtype)
+    if round_bf16:
+        x = x.bfloat16().float()
+    r = O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0,
+                     ds_in_prob=ds_in_prob)
+    data_loss = r['detection_loss'] + (10.0 * r['KL_loss'] if cfg['probabilistic'] else 0.0)
+    data_loss.backward()
+    return ps, noise, r
+
+
+def _compare(model, ps, noise, r, x, y, tol_sm, tol_loss, cos_min, per_tensor_cos):
+    model.set_weights({n: t.detach().float().numpy() for n, t in ps.p.items()})
+    model.set_noise(noise.t)
+    out = model.train_step(x, y, apply_update=False)
+    torch.cuda.synchronize()
+    det = out['detection'].double().cpu()
+    ref = r['detection'].detach().double()
+    assert det.shape == ref.shape
+    err = (det - ref).abs().max().item()
+    assert err < tol_sm, f'softmax max abs err {err:.3e}'
+    fl, fl_ref = out['focal'].item(), r['detection_loss'].item()
+    assert abs(fl - fl_ref) <= tol_loss * abs(fl_ref), (fl, fl_ref)
+    if 'KL' in r:
+        kl, kl_ref = out['kl'].item(), r['KL'].item()
+        assert abs(kl - kl_ref) <= tol_loss * abs(kl_ref), (kl, kl_ref)
+    grads = model.gradients()
+    a_all, b_all = [], []
+    worst = (1.0, None)
+    for n, t in ps.p.items():
+        g_ref = t.grad if t.grad is not None else torch.zeros_like(t)
+        g = grads[n].double().cpu()
+        assert torch.isfinite(g).all(), n
+        a_all.append(g.flatten())
+        b_all.append(g_ref.double().flatten())
+        na, nb = g.norm().item(), g_ref.norm().item()
+        if nb > 1e-9 * max(1.0, t.numel() ** 0.5) and na > 0:
+            cs = (g.flatten() @ g_ref.double().flatten()).item() / (na * nb)
+            if cs < worst[0]:
+                worst = (cs, n)
+    a, b = torch.cat(a_all), torch.cat(b_all)
+    cos = (a @ b).item() / (a.norm().item() * b.norm().item())
+    rel = (a - b).norm().item() / b.norm().item()
+    print(f'grad cosine {cos:.6f} rel-l2 {rel:.3e} worst tensor {worst}')
+    assert cos >= cos_min, (cos, rel)
+    assert worst[0] >= per_tensor_cos, worst
+    return cos
+
+
+@pytest.mark.parametrize("dense,ds,ds_mode", [(True, True, 'reference'), (False, False, 'reference'),
+                                              (True, True, 'intended')])
+def test_probabilistic_train_step_fp32(ctx, dense, ds, ds_mode):
+    model, cfg, x, y = _build(TINY, (4, 16, 16), 2, 'fp32', True, dense, ds, ds_mode)
+    ps, noise, r = _oracle_step(cfg, x, y, ds_mode)
+    assert r['detection'].shape[-1] == (8 if (ds and ds_mode == 'intended') else 2)     # Q3
+    _compare(model, ps, noise, r, x, y, tol_sm=1e-4, tol_loss=1e-3, cos_min=0.9999, per_tensor_cos=0.999)
+
+
+@pytest.mark.parametrize("dense,ds", [(True, True), (False, False)])
+def test_deterministic_train_step_fp32(ctx, dense, ds):
+    model, cfg, x, y = _build(TINY, (4, 16, 16), 2, 'fp32', False, dense, ds, mode='standard')
+    ps, noise, r = _oracle_step(cfg, x, y, 'reference')
+    assert r['detection'].shape[-1] == (8 if ds else 2)
+    _compare(model, ps, noise, r, x, y, tol_sm=1e-4, tol_loss=1e-3, cos_min=0.9999, per_tensor_cos=0.999)
+
+
+def test_probabilistic_train_step_bf16_tcgen05(ctx):
+    """bf16 activations, tcgen05 tensor-core convolutions wherever the shape allows."""
+    model, cfg, x, y = _build(MID, (4, 32, 32), 2, 'bf16', True, True, True)
+    ps, noise, r = _oracle_step(cfg, x, y, 'reference', dtype=torch.float32, round_bf16=True)
+    before = ctx.launch_count()
+    _compare(model, ps, noise, r, x, y, tol_sm=2e-2, tol_loss=5e-2, cos_min=0.98, per_tensor_cos=0.80)
+    assert ctx.launch_count() > before
+    assert len(model.eng.packs) > 0, "no convolution took the tcgen05 engine"
+
+
+def test_adam_update_and_second_step(ctx):
+    """Two full train steps (Adam-AMSGrad + L2) track the oracle's parameters."""
+    model, cfg, x, y = _build(TINY, (4, 16, 16), 2, 'fp32', True, True, False)
+    dtype = torch.float64
+    ps = O.ParamStore(dtype=dtype, seed=3, requires_grad=True)
+    noise = O.Noise(9, dtype)
+    O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), noise)          # materialise parameters
+    model.set_weights({n: t.detach().float().numpy() for n, t in ps.p.items()})
+    state = {n: [torch.zeros_like(t), torch.zeros_like(t), torch.zeros_like(t)] for n, t in ps.p.items()}
+    for step in (1, 2):
+        noise = O.Noise(100 + step, dtype)
+        for t in ps.p.values():
+            t.grad = None
+        r = O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0)
+        r['loss'].backward()
+        model.set_noise(noise.t)
+        out = model.train_step(x, y)
+        torch.cuda.synchronize()
+        total = model.total_loss(out).item()
+        assert abs(total - r['loss'].item()) < 1e-3 * abs(r['loss'].item()), (total, r['loss'].item())
+        with torch.no_grad():
+            for n, t in ps.p.items():
+                m, v, vh = state[n]
+                w, m, v, vh = O.adam_amsgrad_step(t.detach(), t.grad, m, v, vh, step, 1e-3)
+                state[n] = [m, v, vh]
+                t.copy_(w)
+        w_ours = model.get_weights()
+        worst = max((torch.from_numpy(w_ours[n]).double() - t.detach()).abs().max().item() for n, t in ps.p.items())
+        # Adam moves every weight by ~lr per step; agreement well below one step size
+        assert worst < 2e-4, worst
+
+
+def test_inference_and_mc_ensemble(ctx):
+    model, cfg, x, y = _build(TINY, (4, 16, 16), 2, 'fp32', True, True, True)
+    ps = O.ParamStore(dtype=torch.float64, seed=3)
+    noise = O.Noise(21)
+    ref = O.m1_infer(ps, cfg, x.double(), noise)
+    model.set_weights({n: t.detach().float().numpy() for n, t in ps.p.items()}, strict=False)
+    model.set_noise(noise.t)
+    det = model.get_detect_model()
+    p = det(x)
+    torch.cuda.synchronize()
+    assert (p.double().cpu() - ref).abs().max().item() < 1e-4
+    model.set_noise(None, seed=7)                       # Philox: stochastic passes differ, mean is a softmax
+    p1, p2 = det(x), det(x)
+    assert not torch.equal(p1, p2)
+    mean = det.predict_mc(x, passes=4)
+    torch.cuda.synchronize()
+    assert (mean.sum(-1) - 1).abs().max().item() < 1e-5
+
+
+def test_fit_and_save_load_roundtrip(ctx, tmp_path):
+    model, cfg, x, y = _build(TINY, (4, 16, 16), 2, 'fp32', True, True, False)
+    data = [({'image': x}, {'detection': y, 'KL': torch.zeros_like(y)})]
+    hist = model.fit(x=data, epochs=3, steps_per_epoch=2, verbose=0)
+    assert len(hist['loss']) == 3 and all(math.isfinite(v) for v in hist['loss'])
+    assert hist['loss'][-1] < hist['loss'][0]           # it trains
+    path = str(tmp_path / 'ckpt.npz')
+    model.save(path)
+    from m1b200.model import unets
+    m2 = unets.networks.M1.load(path)
+    w1, w2 = model.get_weights(), m2.get_weights()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
+    assert m2.optimizer.iterations == model.optimizer.iterations == 6
+    assert np.array_equal(m2.get_optimizer_state()['vhat'], model.get_optimizer_state()['vhat'])
