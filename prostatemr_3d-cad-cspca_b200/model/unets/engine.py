@@ -100,6 +100,7 @@ class Engine:
         self.record = True
         self.noise = None
         self.packs = {}            # key -> (desc, [kernel names], packed tensor)
+        self.prof = None           # bench.py: list of (category, flops, start_event, end_event)
         self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -128,14 +129,33 @@ class Engine:
             return act.g, False
         return act.g, True
 
+    def _timed(self, cat, flops, fn):
+        if self.prof is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.prof.append((cat, flops, a, b))
+
     def begin(self, record=True):
         self.tape = []
         self.record = record
         self.conv_flops = 0
+        self.param_uses = {}
 
-    def backward(self):
-        for fn in reversed(self.tape):
+    def _rec(self, fn, names):
+        """record a backward closure and the parameters whose gradients it contributes to"""
+        self.tape.append((fn, names))
+        for n in names:
+            self.param_uses[n] = self.param_uses.get(n, 0) + 1
+
+    def backward(self, on_param_done=None):
+        for fn, names in reversed(self.tape):
             fn()
+            if on_param_done is not None:
+                for n in names:
+                    on_param_done(n)
         self.tape = []
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
@@ -185,10 +205,12 @@ class Engine:
                 ent = (d, ws, ops.conv3d_pack_weights(self.ctx, d, ws))
                 self.packs[key] = ent
             packed = ent[2]
-        ops.conv3d(self.ctx, d, [a.t for a in srcs], ws, bs, [o.t for o in outs], packed)
+        fl = 2 * int(vox) * taps * cin * sum(co for _, co in layers)
+        self._timed("conv_fwd_tcgen05" if packed is not None else "conv_fwd_simt", fl,
+                    lambda: ops.conv3d(self.ctx, d, [a.t for a in srcs], ws, bs, [o.t for o in outs], packed))
         if self.record:
-            self.tape.append(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed,
-                                                    ws, wstr))
+            self._rec(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr),
+                      [n + sfx for n, _ in layers for sfx in ("/kernel", "/bias")])
         return outs
 
     def refresh_packs(self):
@@ -210,8 +232,10 @@ class Engine:
                 d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], [co],
                                   [wstr[j]], act_dtype=_code(srcs[0].dtype), out_dtype=_code(outs[j].dtype),
                                   engine=eng)
-                ops.conv3d_wgrad(self.ctx, d, [a.t for a in srcs], [outs[j].g],
-                                 [self.pg(layers[j][0] + "/kernel")], [self.pg(layers[j][0] + "/bias")])
+                fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * cin * co
+                self._timed("conv_wgrad_simt", fl, lambda: ops.conv3d_wgrad(
+                    self.ctx, d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
+                    [self.pg(layers[j][0] + "/bias")]))
             # ---- dgrad per gathered tensor: dx_s (+)= sum_j convT(dout_j, W_j[:, off:off+C_s, :])
             off = 0
             for a in srcs:
@@ -222,7 +246,9 @@ class Engine:
                         d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c],
                                           [(cin * co, 1, co)], accumulate=acc, act_dtype=_code(outs[j].dtype),
                                           out_dtype=_code(a.dtype), engine=eng)
-                        ops.conv3d(self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf])
+                        fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * a.c * co
+                        self._timed("conv_dgrad_simt", fl, lambda: ops.conv3d(
+                            self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf]))
                 off += a.c
         else:
             co = layers[0][1]
@@ -233,7 +259,9 @@ class Engine:
             for a in srcs:
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
                                   act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=eng)
-                ops.conv3d_wgrad(self.ctx, d, [dy], [a.t], [gk[off:]], None)
+                fl = 2 * batch * int(np.prod(in_dhw)) * int(np.prod(k)) * a.c * co
+                self._timed("conv_wgrad_simt", fl,
+                            lambda: ops.conv3d_wgrad(self.ctx, d, [dy], [a.t], [gk[off:]], None))
                 off += a.c
             ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
             # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci]
@@ -244,7 +272,9 @@ class Engine:
                     d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
                                       accumulate=acc, act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype),
                                       engine=eng)
-                    ops.conv3d(self.ctx, d, [dy], [ws[0].view(-1)[off:]], None, [gbuf])
+                    fl = 2 * batch * int(np.prod(in_dhw)) * int(np.prod(k)) * a.c * co
+                    self._timed("conv_dgrad_simt", fl,
+                                lambda: ops.conv3d(self.ctx, d, [dy], [ws[0].view(-1)[off:]], None, [gbuf]))
                 off += a.c
         for o in outs:
             o.g = None
@@ -269,7 +299,7 @@ class Engine:
                               self.pg(name + "/gamma"), self.pg(name + "/beta"))
             y.g = None
         if self.record:
-            self.tape.append(bwd)
+            self._rec(bwd, [name + "/gamma", name + "/beta"])
         return y
 
     # ---- K5 SE tail: norm3/norm4 + squeeze + excite + gate*residual + lrelu + dropout -----------
@@ -320,7 +350,8 @@ class Engine:
                                   self.pg(name + "/norm4/gamma"), self.pg(name + "/norm4/beta"))
             out.g = None
         if self.record:
-            self.tape.append(bwd)
+            self._rec(bwd, [name + sfx for sfx in ("/norm3/gamma", "/norm3/beta", "/norm4/gamma", "/norm4/beta",
+                                                   "/conv6/kernel", "/conv6/bias", "/conv7/kernel", "/conv7/bias")])
         return out
 
     # ---- K6 attention gate core ------------------------------------------------------------------
@@ -355,7 +386,7 @@ class Engine:
                 ops.axpy(self.ctx, tmp, 1.0, phi.g)
             y.g = None
         if self.record:
-            self.tape.append(bwd)
+            self._rec(bwd, [name + "/conv3/kernel", name + "/conv3/bias"])
         return y
 
     # ---- K7 latent heads ----------------------------------------------------------------------------
@@ -374,7 +405,7 @@ class Engine:
             ops.latent_bwd(self.ctx, z.g, ml.t, eps, mode, gbuf)
             z.g = None
         if self.record:
-            self.tape.append(bwd)
+            self._rec(bwd, [])
         return z
 
     def kl(self, ml_q, ml_p, kl_out):

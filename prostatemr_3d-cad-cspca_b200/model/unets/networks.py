@@ -425,6 +425,19 @@ class M1(LoadableModel):
         self.loss_weights = [float(lw[0]), float(lw[1]) if len(lw) > 1 else 1.0]
         return self
 
+    def distribute(self, bucket_bytes=32 << 20, group=None):
+        """Data-parallel training over the initialised torch.distributed group (one process per GPU):
+        the MirroredStrategy scope of train_model.py:167-170. Replicas must start from identical
+        weights (same `seed`); each draws its own Philox sub-stream."""
+        import torch.distributed as dist
+        from ..distribute import BucketedGradSync
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.grad_sync = BucketedGradSync(self.params, bucket_bytes, group)
+        if isinstance(self.noise, PhiloxNoise):
+            self.noise = PhiloxNoise(seed=42 + self._init_kw['seed'], rank=self.rank)
+        return self
+
     def set_noise(self, tensors=None, seed=None):
         """noise injection for parity runs: {(pass_name, site): tensor}; None -> Philox."""
         if tensors is not None:
@@ -469,9 +482,12 @@ class M1(LoadableModel):
         for ml_q, ml_p in g['kl_pairs']:
             eng.kl(ml_q, ml_p, scal[1:2])
             eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
-        eng.backward()
         if self.grad_sync is not None:
-            self.grad_sync(self.params.g)
+            self.grad_sync.begin(self.params.g, eng.param_uses)
+            eng.backward(self.grad_sync.param_done)
+            self.grad_sync.finish()
+        else:
+            eng.backward()
         if apply_update:
             self._apply_update(scal[2:3], inv_r)
         if isinstance(self.noise, PhiloxNoise):
