@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define M1_MAX_SRC 8
-#define M1_MAX_OUT 2
+#define M1_MAX_OUT 8
 
 typedef enum { M1_F32 = 0, M1_BF16 = 1 } m1_dtype;
 
@@ -40,8 +40,9 @@ typedef enum { M1_ENGINE_AUTO = 0, M1_ENGINE_SIMT = 1, M1_ENGINE_TCGEN05 = 2 } m
 
 /* One convolution-shaped launch.  "in" is the tensor that is gathered from (possibly a virtual
  * channel-concatenation of several tensors, R:networks.py:596,604,613,621,653,677,701,725),
- * "out" the tensor that is produced (possibly split over two tensors along channels: the fused
- * conv1||conv4 pair of an SE block, R:network_blocks.py:37,43).
+ * "out" the tensor that is produced (possibly split over several tensors along channels: the fused
+ * conv1||conv4 pair of an SE block, R:network_blocks.py:37,43, or - in a data-gradient launch - the
+ * gradients of the concatenated tensors).
  * TF "SAME" padding (R:networks.py:259 'padding':'same'): pad[] is pad_before of the FORWARD
  * convolution this launch belongs to (for M1_CONV_TRANSPOSED it is the forward conv's pad). */
 typedef struct {
@@ -58,7 +59,7 @@ typedef struct {
    * r = reduced (gathered) channel over the concatenation, n = produced channel of output j
    * (one weight tensor per output). */
   int64_t w_stride_tap[M1_MAX_OUT], w_stride_red[M1_MAX_OUT], w_stride_out[M1_MAX_OUT];
-  int32_t accumulate;                 /* 1: out += result (gradient accumulation) */
+  int32_t accumulate;                 /* bit j set: outs[j] += result (gradient accumulation) */
   int32_t act_dtype;                  /* m1_dtype of the gathered tensors */
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
@@ -96,7 +97,8 @@ int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* cons
 /* ---- K3: weight gradient (Conv3DBackpropFilterV2 of autodiff) + BiasAddGrad ----------------
  * dW_j[tap, r, n] += sum_{batch,o} gathered(o,tap)[r] * dout_j[o, n]   (same strides as d->w_*)
  * dbias_j[n]     += sum dout_j[.., n]  (if dbias[j] != NULL).  Always accumulates (shared
- * weights receive gradients from several passes, R:networks.py:348-352). */
+ * weights receive gradients from several passes, R:networks.py:348-352).  d->engine AUTO takes the
+ * tcgen05 engine for stride-1 bf16 launches with 16-aligned channel counts, else the CUDA cores. */
 int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                     const void* const* douts, float* const* dw, float* const* dbias, void* stream);
 

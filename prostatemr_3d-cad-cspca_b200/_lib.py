@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libm1b200.so")
 
 M1_MAX_SRC = 8
-M1_MAX_OUT = 2
+M1_MAX_OUT = 8
 F32, BF16 = 0, 1
 CONV_FWD, CONV_TRANSPOSED = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2

@@ -13,7 +13,7 @@ pids=()
 for src in "$here"/*.cu; do
   obj="$here/_obj/$(basename "${src%.cu}").o"
   objs+=("$obj")
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$here/../../include/m1b200.h" -nt "$obj" ]]; then
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$here/common.cuh" -nt "$obj" || "$here/tc_common.cuh" -nt "$obj" || "$here/../../include/m1b200.h" -nt "$obj" ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" &
     pids+=($!)
   fi

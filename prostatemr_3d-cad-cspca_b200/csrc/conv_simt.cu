@@ -32,10 +32,19 @@ struct SimtParams {
   const float* w[M1_MAX_OUT];
   const float* bias[M1_MAX_OUT];
   int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
-  int accumulate;
+  int accumulate;   // bitmask over outputs
   int n_total;
+  int out_start[M1_MAX_OUT + 1];  // prefix sums of out_c
   int64_t out_vox;  // batch * Do*Ho*Wo
 };
+
+// produced tensor that owns global column n (n is rewritten to the column inside it)
+__device__ __forceinline__ int out_of(const SimtParams& p, int& n) {
+  int j = 0;
+  while (j + 1 < p.nout && n >= p.out_start[j + 1]) ++j;
+  n -= p.out_start[j];
+  return j;
+}
 
 // input voxel index (within the batch-flattened gathered grid) for output voxel (n,d,h,w) and tap
 // (a,b,c); -1 when the tap falls into the SAME padding / between the stride phases
@@ -125,8 +134,7 @@ __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ S
           int n = n0 + nn;
           float x = 0.f;
           if (ch < C && n < p.n_total) {
-            int j = 0;
-            if (p.nout > 1 && n >= p.out_c[0]) { n -= p.out_c[0]; j = 1; }
+            const int j = out_of(p, n);
             x = p.w[j][tap * p.st[j] + (int64_t)(r_base + ch) * p.sr[j] + (int64_t)n * p.so[j]];
           }
           Ws[kk][nn] = x;
@@ -161,12 +169,11 @@ __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ S
     for (int jj = 0; jj < 8; ++jj) {
       int n = n0 + tx * 8 + jj;
       if (n >= p.n_total) continue;
-      int j = 0;
-      if (p.nout > 1 && n >= p.out_c[0]) { n -= p.out_c[0]; j = 1; }
+      const int j = out_of(p, n);
       float v = acc[i][jj];
       if (p.bias[j]) v += p.bias[j][n];
       TO* dst = reinterpret_cast<TO*>(p.out[j]) + m * p.out_c[j] + n;
-      if (p.accumulate) v += ld_f<TO>(dst);
+      if ((p.accumulate >> j) & 1) v += ld_f<TO>(dst);
       st_f<TO>(dst, v);
     }
   }
@@ -314,10 +321,12 @@ int fill_params(const m1_conv_desc* d, SimtParams* p) {
   p->n_total = 0;
   for (int s = 0; s < d->nsrc; ++s) p->src_c[s] = d->src_c[s];
   for (int j = 0; j < d->nout; ++j) {
+    p->out_start[j] = p->n_total;
     p->out_c[j] = d->out_c[j];
     p->st[j] = d->w_stride_tap[j]; p->sr[j] = d->w_stride_red[j]; p->so[j] = d->w_stride_out[j];
     p->n_total += d->out_c[j];
   }
+  p->out_start[d->nout] = p->n_total;
   p->accumulate = d->accumulate;
   p->out_vox = (int64_t)d->batch * p->Do * p->Ho * p->Wo;
   return 0;
@@ -362,7 +371,15 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
     q.dw = dw[j];
     q.st = d->w_stride_tap[j]; q.sr = d->w_stride_red[j]; q.so = d->w_stride_out[j];
     int r_base = 0;
-    for (int s = 0; s < d->nsrc; ++s) {
+    const bool use_tc = d->engine != M1_ENGINE_SIMT && m1_conv3d_wgrad_tc_supported(d, j);
+    if (d->engine == M1_ENGINE_TCGEN05 && !use_tc) {
+      m1_set_error("m1_conv3d_wgrad: launch not supported by the tcgen05 engine");
+      return 1;
+    }
+    if (use_tc) {
+      if (m1_conv3d_wgrad_tc(ctx, d, j, srcs, douts[j], dw[j], st)) return 1;
+    }
+    for (int s = 0; s < d->nsrc && !use_tc; ++s) {
       q.src_index = s;
       q.r_base = r_base;
       const int C = d->src_c[s];

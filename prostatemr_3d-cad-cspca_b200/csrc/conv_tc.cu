@@ -17,10 +17,10 @@
 // 8-row swizzle atoms), so one tcgen05.mma per 16 channels consumes them with no data movement
 // by threads.  One CTA = one M tile x one N tile; several CTAs are co-resident per SM so that the
 // epilogue of one overlaps the main loop of another.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace {
+using namespace tc;
 
 constexpr int kThreads = 128;
 
@@ -48,74 +48,11 @@ struct TcParams {
   int nout;
   void* out[M1_MAX_OUT];
   int out_c[M1_MAX_OUT];
+  int out_start[M1_MAX_OUT + 1];
   const float* bias[M1_MAX_OUT];
   int out_bf16;
-  int accumulate;
+  int accumulate;              // bitmask over outputs
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-}
 
 __global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -249,7 +186,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       int gc = n0 + j;
       if (!valid || gc >= p.n_total) continue;
       int o = 0;
-      if (p.nout > 1 && gc >= p.out_c[0]) { gc -= p.out_c[0]; o = 1; }
+      while (o + 1 < p.nout && gc >= p.out_start[o + 1]) ++o;
+      gc -= p.out_start[o];
+      const bool accum = (p.accumulate >> o) & 1;
       float f[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
@@ -262,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int64_t off = vox * p.out_c[o] + gc;
       if (p.out_bf16) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[o]) + off;
-        if (p.accumulate) {
+        if (accum) {
           uint4 old = *reinterpret_cast<const uint4*>(dst);
           const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
@@ -278,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         *reinterpret_cast<uint4*>(dst) = pk;
       } else {
         float* dst = reinterpret_cast<float*>(p.out[o]) + off;
-        if (p.accumulate) {
+        if (accum) {
           const float4 o0 = *reinterpret_cast<const float4*>(dst);
           const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
           f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
@@ -298,28 +237,31 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-// fp32 master weights -> bf16 [tap][n_total][k_total]
-__global__ void pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
-                                    int n0c, int n_real, int n_total, int k_total, int taps, int64_t st0,
-                                    int64_t sr0, int64_t so0, int64_t st1, int64_t sr1,
-                                    int64_t so1, __nv_bfloat16* __restrict__ out) {
+// fp32 master weights -> bf16 [tap][n_total][k_total]; one weight tensor per produced tensor
+struct PackArgs {
+  const float* w[M1_MAX_OUT];
+  int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
+  int out_start[M1_MAX_OUT + 1];
+  int nout;
+};
+__global__ void pack_weights_kernel(PackArgs a, int n_real, int n_total, int k_total, int taps,
+                                    __nv_bfloat16* __restrict__ out) {
   const int64_t total = (int64_t)taps * n_total * k_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i % k_total);
-    const int n = (int)((i / k_total) % n_total);
+    int n = (int)((i / k_total) % n_total);
     const int tap = (int)(i / ((int64_t)k_total * n_total));
     float v = 0.f;
-    if (n < n0c) v = w0[tap * st0 + r * sr0 + n * so0];
-    else if (n < n_real) v = w1[tap * st1 + r * sr1 + (n - n0c) * so1];
+    if (n < n_real) {
+      int j = 0;
+      while (j + 1 < a.nout && n >= a.out_start[j + 1]) ++j;
+      n -= a.out_start[j];
+      v = a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
+    }
     out[i] = __float2bfloat16_rn(v);
   }
 }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Plan {
   int ck, n_real, n_total, k_total, n_tile, n_tiles;   // n_total = n_real padded to 16
@@ -424,11 +366,19 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
   const int64_t total = (int64_t)taps * pl.n_total * pl.k_total;
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 8);
-  const int j1 = d->nout > 1 ? 1 : 0;
-  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      w[0], w[j1], d->out_c[0], pl.n_real, pl.n_total, pl.k_total, taps, d->w_stride_tap[0],
-      d->w_stride_red[0], d->w_stride_out[0], d->w_stride_tap[j1], d->w_stride_red[j1],
-      d->w_stride_out[j1], reinterpret_cast<__nv_bfloat16*>(w_packed));
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nout = d->nout;
+  int acc = 0;
+  for (int j = 0; j < d->nout; ++j) {
+    a.w[j] = w[j];
+    a.st[j] = d->w_stride_tap[j]; a.sr[j] = d->w_stride_red[j]; a.so[j] = d->w_stride_out[j];
+    a.out_start[j] = acc;
+    acc += d->out_c[j];
+  }
+  a.out_start[d->nout] = acc;
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pl.n_real, pl.n_total, pl.k_total, taps,
+                                                              reinterpret_cast<__nv_bfloat16*>(w_packed));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -505,6 +455,11 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   const uint32_t layout = pl.ck == 64 ? 2u : pl.ck == 32 ? 4u : 6u;
   p.desc_hi = sbo | (1u << 14) | (layout << 29);
   p.nout = d->nout;
+  {
+    int acc = 0;
+    for (int j = 0; j < d->nout; ++j) { p.out_start[j] = acc; acc += d->out_c[j]; }
+    p.out_start[d->nout] = acc;
+  }
   for (int j = 0; j < d->nout; ++j) {
     p.out[j] = outs[j];
     p.out_c[j] = d->out_c[j];

@@ -1,0 +1,349 @@
+// conv_wgrad_tc.cu — K3: weight gradient of a stride-1 3-D convolution on the tcgen05 tensor cores.
+//
+// Replaces Conv3DBackpropFilterV2 (autodiff of tf.keras.layers.Conv3D, R:network_blocks.py:37-46).
+//
+//   dW[tap][r][n] = sum over output voxels o of  X[o + tap - pad][r] * dY[o][n]
+//
+// GEMM view per tap:   D[M = 128 reduced channels r, N = produced channels] += A[M, K] * B[K, N]
+// with K = output voxels.  Both operands are "MN-major" for the tensor core: their contraction index
+// (the voxel) is the slow one in memory, channels are contiguous - exactly how NDHWC tensors lie in
+// HBM, so again TMA boxes feed the MMA with no data movement by threads:
+//   A block  = 5-D TMA box (ck channels, bw, bh, bd, 1) of one gathered tensor, corner shifted by the
+//              tap (zero fill == SAME padding); 128/ck such blocks (possibly from DIFFERENT tensors of
+//              the virtual concatenation) form the M = 128 rows, LBO = block bytes
+//   B block  = 5-D TMA box (cb channels, bw, bh, bd, 1) of dY, n_tile/cb blocks form N
+//   K step   = 16 voxels = 16 rows of every block (2 swizzle groups of 8 rows, SBO = 8 rows)
+// A CTA owns one (tap group, M tile, N tile) and a slab of voxel bricks (split-K); the taps of a
+// group differ only in kw and share the B blocks (one accumulator per tap in TMEM); partial dW tiles
+// are added to the fp32 gradient with atomics (shared weights accumulate over passes anyway).
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace {
+using namespace tc;
+
+constexpr int kThreads = 128;
+constexpr int kMaxBlocks = 64;   // 16-channel blocks over the concatenation handled per launch (<= 1024 ch)
+
+struct WgParams {
+  CUtensorMap tmA[M1_MAX_SRC];
+  CUtensorMap tmB;
+  int nsrc;
+  uint8_t blk_src[kMaxBlocks];   // M block -> gathered tensor
+  uint16_t blk_c0[kMaxBlocks];   // M block -> first channel inside that tensor
+  uint16_t blk_goff[kMaxBlocks]; // M block -> first channel over the virtual concatenation
+  int nblocks;                   // total M blocks (ck channels each)
+  int blocks_per_tile;           // 128 / ck
+  int cin_total;
+  int kd, kh, kw, pd, ph, pw;
+  int tpg;                       // taps per group (1 or kw)
+  int bd, bh, bw, td, th, tw;    // brick, bricks per dim
+  int batch;
+  int kv;                        // voxels per brick (multiple of 16)
+  int ck, cb;                    // channels per A / B block
+  int n_tile, n_blocks;          // N per CTA, B blocks per CTA
+  int co;                        // produced channels (real)
+  int stages;
+  uint32_t a_tap_bytes, b_off, stage_bytes;
+  uint32_t a_blk_bytes, b_blk_bytes;
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  uint32_t a_desc_hi, b_desc_hi;
+  uint32_t a_lbo, b_lbo;         // >> 4
+  int splits;
+  int64_t bricks_total;
+  float* dw;
+  int64_t st, sr, so;
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_base;
+  const uint32_t bar_empty = smem_base + 8u * 16u;
+  const uint32_t bar_accum = smem_base + 8u * 32u;
+  const uint32_t tmem_slot = smem_base + 8u * 33u;
+  const uint32_t tiles = smem_base + 1024u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work decomposition: blockIdx.x = ((group * m_tiles + m_tile) * n_tiles + n_tile), blockIdx.y = split
+  const int m_tiles = (p.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  const int n_tiles = (p.co + p.n_tile - 1) / p.n_tile;
+  int t = blockIdx.x;
+  const int nt = t % n_tiles; t /= n_tiles;
+  const int mt = t % m_tiles; t /= m_tiles;
+  const int group = t;
+  const int groups_per_row = p.kw / p.tpg;
+  const int kw0 = (group % groups_per_row) * p.tpg;
+  const int kh_i = (group / groups_per_row) % p.kh;
+  const int kd_i = group / (groups_per_row * p.kh);
+  const int blk0 = mt * p.blocks_per_tile;
+  const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
+  const int n0 = nt * p.n_tile;
+  const int64_t per = (p.bricks_total + p.splits - 1) / p.splits;
+  const int64_t b_begin = (int64_t)blockIdx.y * per;
+  const int64_t b_end = min(b_begin + per, p.bricks_total);
+  const int iters = (int)max((int64_t)0, b_end - b_begin);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + 8u * 33u);
+
+  if (iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer: one stage = one voxel brick =====
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < iters; ++it) {
+          int64_t b = b_begin + it;
+          const int tw_i = (int)(b % p.tw); b /= p.tw;
+          const int th_i = (int)(b % p.th); b /= p.th;
+          const int td_i = (int)(b % p.td); b /= p.td;
+          const int n_img = (int)b;
+          const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8u * stage;
+          mbar_expect_tx(full, (uint32_t)(p.tpg * nblk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes);
+          const uint32_t sbase = tiles + stage * p.stage_bytes;
+          for (int tp = 0; tp < p.tpg; ++tp)
+            for (int j = 0; j < nblk; ++j) {
+              const int blk = blk0 + j;
+              tma_load_5d(sbase + tp * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]], full,
+                          (int)p.blk_c0[blk], w0 + kw0 + tp - p.pw, h0 + kh_i - p.ph, d0 + kd_i - p.pd, n_img);
+            }
+          for (int j = 0; j < p.n_blocks; ++j)
+            tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB, full, n0 + j * p.cb, w0, h0, d0, n_img);
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        uint32_t stage = 0, phase = 0;
+        const uint64_t a_hi = (uint64_t)p.a_desc_hi << 32, b_hi = (uint64_t)p.b_desc_hi << 32;
+        const uint32_t a_kstep = (16u * p.ck * 2u) >> 4, b_kstep = (16u * p.cb * 2u) >> 4;
+        const int k16s = p.kv / 16;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(bar_full + 8u * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sbase = tiles + stage * p.stage_bytes;
+          const uint64_t b_lo = (uint64_t)(((sbase + p.b_off) >> 4) & 0x3FFFu) | ((uint64_t)p.b_lbo << 16);
+          for (int tp = 0; tp < p.tpg; ++tp) {
+            const uint64_t a_lo =
+                (uint64_t)(((sbase + tp * p.a_tap_bytes) >> 4) & 0x3FFFu) | ((uint64_t)p.a_lbo << 16);
+            for (int k = 0; k < k16s; ++k)
+              umma_bf16(tmem_base + (uint32_t)(tp * p.n_tile), a_hi | (a_lo + (uint64_t)k * a_kstep),
+                        b_hi | (b_lo + (uint64_t)k * b_kstep), p.idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8u * stage);
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+
+    // ===== epilogue: TMEM -> registers -> fp32 atomics into dW =====
+    mbar_wait(bar_accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = threadIdx.x;                       // row of the M tile == TMEM lane
+    const int rblk = blk0 + r / p.ck;
+    const bool row_ok = (r / p.ck) < nblk;
+    const int rglob = row_ok ? (int)p.blk_goff[rblk] + r % p.ck : 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int tp = 0; tp < p.tpg; ++tp) {
+      const int tap = (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
+      float* dst_row = p.dw + tap * p.st + (int64_t)rglob * p.sr;
+      for (int j = 0; j < p.n_tile; j += 8) {
+        uint32_t v[8];
+        tmem_ld8(lane_addr + (uint32_t)(tp * p.n_tile + j), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + j + i;
+          if (n < p.co) atomicAdd(dst_row + (int64_t)n * p.so, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+struct WgPlan {
+  int ck, cb, n_tile, n_blocks, tpg, kv, bd, bh, bw, td, th, tw, stages, nblocks, cin_total;
+  uint32_t a_blk_bytes, b_blk_bytes, a_tap_bytes, b_off, stage_bytes, smem_bytes, tmem_cols;
+};
+
+bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
+  if (d->mode != M1_CONV_FWD) return false;
+  if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
+  for (int i = 0; i < 3; ++i)
+    if (d->stride[i] != 1 || d->in_dhw[i] != d->out_dhw[i]) return false;
+  if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC) return false;
+  int ck = 64, cin = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    if (d->src_c[s] % 16) return false;
+    while (d->src_c[s] % ck) ck >>= 1;
+    cin += d->src_c[s];
+  }
+  if (cin / ck > kMaxBlocks) {
+    // fall back to coarser blocks only if every tensor allows it; otherwise refuse
+    return false;
+  }
+  const int co = d->out_c[j];
+  if (co % 16) return false;
+  int cb = 64;
+  while (co % cb) cb >>= 1;
+  int n_tile = co;
+  if (n_tile > 256) {
+    n_tile = 256;
+    while (co % n_tile || n_tile % cb) n_tile -= cb;
+  }
+  int tpg = (d->kernel[2] * n_tile <= 512) ? d->kernel[2] : 1;
+  // brick: voxels multiple of 16, <= kv_max, best volume coverage
+  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
+  auto pick = [&](int kv_max, int* obd, int* obh, int* obw) {
+    double best = -1;
+    for (int bd = 1; bd <= kv_max && bd <= D; ++bd)
+      for (int bh = 1; bd * bh <= kv_max && bh <= H; ++bh)
+        for (int bw = 1; bd * bh * bw <= kv_max && bw <= W; ++bw) {
+          const int kv = bd * bh * bw;
+          if (kv % 16) continue;
+          const int64_t tiles = (int64_t)((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
+          const double eff = (double)D * H * W / ((double)kv * tiles);
+          const double score = eff + 1e-3 * kv / kv_max + 1e-6 * bw;
+          if (score > best) { best = score; *obd = bd; *obh = bh; *obw = bw; }
+        }
+    return best > 0;
+  };
+  for (int kv_max = 128; kv_max >= 16; kv_max >>= 1) {
+    int bd, bh, bw;
+    if (!pick(kv_max, &bd, &bh, &bw)) continue;
+    const int kv = bd * bh * bw;
+    for (int tp = tpg; tp >= 1; tp = (tp == 1 ? 0 : 1)) {
+      const uint32_t a_blk = (uint32_t)kv * ck * 2u, b_blk = (uint32_t)kv * cb * 2u;
+      const uint32_t a_tap = (128u / ck) * a_blk;
+      const uint32_t b_off = (uint32_t)tp * a_tap;
+      const uint32_t stage = (b_off + (uint32_t)(n_tile / cb) * b_blk + 1023u) & ~1023u;
+      int stages = (int)((227u * 1024u - 2048u) / stage);
+      if (stages > 8) stages = 8;
+      if (stages < 2) continue;
+      pl->ck = ck; pl->cb = cb; pl->n_tile = n_tile; pl->n_blocks = n_tile / cb; pl->tpg = tp; pl->kv = kv;
+      pl->bd = bd; pl->bh = bh; pl->bw = bw;
+      pl->td = (D + bd - 1) / bd; pl->th = (H + bh - 1) / bh; pl->tw = (W + bw - 1) / bw;
+      pl->stages = stages; pl->nblocks = cin / ck; pl->cin_total = cin;
+      pl->a_blk_bytes = a_blk; pl->b_blk_bytes = b_blk; pl->a_tap_bytes = a_tap; pl->b_off = b_off;
+      pl->stage_bytes = stage; pl->smem_bytes = 2048u + (uint32_t)stages * stage;
+      uint32_t cols = 32;
+      while ((int)cols < tp * n_tile) cols <<= 1;
+      pl->tmem_cols = cols;
+      return true;
+    }
+  }
+  return false;
+}
+
+}  // namespace
+
+int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j) {
+  WgPlan pl;
+  return make_wg_plan(d, j, &pl) ? 1 : 0;
+}
+
+int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* const* srcs, const void* dout,
+                       float* dw, cudaStream_t st) {
+  WgPlan pl;
+  M1_CHECK(make_wg_plan(d, j, &pl), "m1_conv3d_wgrad: launch not supported by the tcgen05 engine");
+  M1_CHECK(ctx->encode_tiled != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  static_assert(sizeof(WgParams) < 4000, "kernel parameter block too large");
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
+  int blk = 0, goff = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d_wgrad: gathered tensor %d not 16-byte aligned", s);
+    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], W, H, D, d->batch, pl.ck, pl.bw, pl.bh, pl.bd);
+    M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad A %d) failed: %d", s, r);
+    for (int c0 = 0; c0 < d->src_c[s]; c0 += pl.ck) {
+      p.blk_src[blk] = (uint8_t)s;
+      p.blk_c0[blk] = (uint16_t)c0;
+      p.blk_goff[blk] = (uint16_t)(goff + c0);
+      ++blk;
+    }
+    goff += d->src_c[s];
+  }
+  {
+    int r = encode_ndhwc(encode, &p.tmB, dout, d->out_c[j], W, H, D, d->batch, pl.cb, pl.bw, pl.bh, pl.bd);
+    M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad B) failed: %d", r);
+  }
+  p.nsrc = d->nsrc;
+  p.nblocks = pl.nblocks;
+  p.blocks_per_tile = 128 / pl.ck;
+  p.cin_total = pl.cin_total;
+  p.kd = d->kernel[0]; p.kh = d->kernel[1]; p.kw = d->kernel[2];
+  p.pd = d->pad[0]; p.ph = d->pad[1]; p.pw = d->pad[2];
+  p.tpg = pl.tpg;
+  p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw; p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
+  p.batch = d->batch;
+  p.kv = pl.kv;
+  p.ck = pl.ck; p.cb = pl.cb;
+  p.n_tile = pl.n_tile; p.n_blocks = pl.n_blocks;
+  p.co = d->out_c[j];
+  p.stages = pl.stages;
+  p.a_tap_bytes = pl.a_tap_bytes; p.b_off = pl.b_off; p.stage_bytes = pl.stage_bytes;
+  p.a_blk_bytes = pl.a_blk_bytes; p.b_blk_bytes = pl.b_blk_bytes;
+  p.tmem_cols = pl.tmem_cols;
+  // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(pl.n_tile >> 3) << 17) |
+            ((128u >> 4) << 24);
+  // MN-major descriptors: SBO = 8 voxel rows of a block, LBO = one block (next channel block)
+  p.a_desc_hi = ((8u * pl.ck * 2u) >> 4) | (1u << 14) | (layout_for(pl.ck) << 29);
+  p.b_desc_hi = ((8u * pl.cb * 2u) >> 4) | (1u << 14) | (layout_for(pl.cb) << 29);
+  p.a_lbo = pl.a_blk_bytes >> 4;
+  p.b_lbo = pl.b_blk_bytes >> 4;
+  M1_CHECK(p.a_lbo < (1u << 14) && p.b_lbo < (1u << 14), "wgrad: block too large for the descriptor LBO field");
+  p.bricks_total = (int64_t)d->batch * pl.td * pl.th * pl.tw;
+  const int m_tiles = (pl.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  const int n_tiles = (p.co + pl.n_tile - 1) / pl.n_tile;
+  const int groups = p.kd * p.kh * (p.kw / pl.tpg);
+  const int64_t base_ctas = (int64_t)groups * m_tiles * n_tiles;
+  int64_t splits = std::max<int64_t>(1, ((int64_t)ctx->num_sms * 2 + base_ctas - 1) / base_ctas);
+  splits = std::min<int64_t>(splits, std::max<int64_t>(1, p.bricks_total / 4));
+  p.splits = (int)splits;
+  p.dw = dw;
+  p.st = d->w_stride_tap[j]; p.sr = d->w_stride_red[j]; p.so = d->w_stride_out[j];
+
+  static int smem_set = 0;
+  if (!smem_set) {
+    M1_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 1;
+  }
+  dim3 grid((unsigned)base_ctas, (unsigned)splits);
+  wgrad_tc_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}

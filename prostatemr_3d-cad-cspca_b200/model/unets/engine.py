@@ -236,20 +236,44 @@ class Engine:
                 self._timed("conv_wgrad_simt", fl, lambda: ops.conv3d_wgrad(
                     self.ctx, d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
                     [self.pg(layers[j][0] + "/bias")]))
-            # ---- dgrad per gathered tensor: dx_s (+)= sum_j convT(dout_j, W_j[:, off:off+C_s, :])
-            off = 0
-            for a in srcs:
-                if a.needs_grad:
-                    for j in live:
-                        co = layers[j][1]
-                        gbuf, acc = self.grad_buffer(a)
-                        d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c],
-                                          [(cin * co, 1, co)], accumulate=acc, act_dtype=_code(outs[j].dtype),
-                                          out_dtype=_code(a.dtype), engine=eng)
-                        fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * a.c * co
-                        self._timed("conv_dgrad_simt", fl, lambda: ops.conv3d(
-                            self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf]))
-                off += a.c
+            # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j) - ONE launch per layer j whose
+            # produced channels are split over the gradients of the concatenated tensors
+            need = [a for a in srcs if a.needs_grad]
+            if need and len(need) == len(srcs):
+                offs = np.cumsum([0] + [a.c for a in srcs])[:-1]
+                for j in live:
+                    co = layers[j][1]
+                    bufs, accs = zip(*[self.grad_buffer(a) for a in srcs])
+                    wv = [ws[j].view(-1)[int(off) * co:] for off in offs]
+                    d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c for a in srcs],
+                                      [(cin * co, 1, co)] * len(srcs), accumulate=list(accs),
+                                      act_dtype=_code(outs[j].dtype), out_dtype=_code(srcs[0].dtype),
+                                      engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
+                    packed = None
+                    if self.use_tc and ops.conv3d_tc_supported(d):
+                        key = ("dgrad", layers[j][0])
+                        ent = self.packs.get(key)
+                        if ent is None:
+                            ent = (d, wv, ops.conv3d_pack_weights(self.ctx, d, wv))
+                            self.packs[key] = ent
+                        packed = ent[2]
+                    fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * cin * co
+                    self._timed("conv_dgrad_tcgen05" if packed is not None else "conv_dgrad_simt", fl,
+                                lambda: ops.conv3d(self.ctx, d, [outs[j].g], wv, None, list(bufs), packed))
+            elif need:
+                off = 0
+                for a in srcs:
+                    if a.needs_grad:
+                        for j in live:
+                            co = layers[j][1]
+                            gbuf, acc = self.grad_buffer(a)
+                            d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c],
+                                              [(cin * co, 1, co)], accumulate=acc, act_dtype=_code(outs[j].dtype),
+                                              out_dtype=_code(a.dtype), engine=eng)
+                            fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * a.c * co
+                            self._timed("conv_dgrad_simt", fl, lambda: ops.conv3d(
+                                self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf]))
+                    off += a.c
         else:
             co = layers[0][1]
             dy = outs[0].g

@@ -38,7 +38,10 @@ def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w
     for j, c in enumerate(out_c):
         d.out_c[j] = c
         d.w_stride_tap[j], d.w_stride_red[j], d.w_stride_out[j] = w_strides[j]
-    d.accumulate = 1 if accumulate else 0
+    if isinstance(accumulate, (list, tuple)):          # per-output flags -> bitmask
+        d.accumulate = sum(1 << j for j, a in enumerate(accumulate) if a)
+    else:
+        d.accumulate = ((1 << len(out_c)) - 1) if accumulate else 0
     d.act_dtype = act_dtype
     d.out_dtype = act_dtype if out_dtype is None else out_dtype
     d.engine = engine

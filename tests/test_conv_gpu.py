@@ -170,3 +170,71 @@ def test_conv_wgrad_dgrad_simt(ctx, k, s):
         torch.cuda.synchronize()
         assert (dx.cpu().double() - x.grad).abs().max().item() < 1e-3
         off += c
+
+
+@pytest.mark.parametrize("dhw,cins,cout,k", [((4, 16, 16), [64, 32], 64, (3, 3, 3)),
+                                             ((6, 20, 20), [128, 128, 64], 32, (1, 3, 3)),
+                                             ((4, 16, 16), [32, 32, 32, 32, 32], 32, (1, 3, 3))])
+def test_conv_dgrad_tcgen05_multi_output(ctx, dhw, cins, cout, k):
+    """Data gradient of a stride-1 conv over a virtual concatenation: ONE tcgen05 launch whose produced
+    channels are split over the gradients of the concatenated tensors (one pre-loaded: accumulate bit)."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(8)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g, dtype=torch.float64, requires_grad=True) for c in cins]
+    w = (torch.randn((*k, cin, cout), generator=g) / (cin * 9) ** 0.5).bfloat16().double()
+    y = O.conv3d_same(torch.cat(xs, -1), w, None, (1, 1, 1))
+    dy = torch.randn(y.shape, generator=g).bfloat16().double()
+    y.backward(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    prior = torch.randn(xs[0].shape, generator=g).bfloat16()          # pre-existing gradient of tensor 0
+    bufs = [prior.clone().to(dev)] + [torch.full(x.shape, float('nan'), device=dev, dtype=torch.bfloat16)
+                                      for x in xs[1:]]
+    wd = w.float().to(dev).contiguous()
+    offs = [sum(cins[:i]) for i in range(len(cins))]
+    wv = [wd.view(-1)[o * cout:] for o in offs]
+    d = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, dhw, k, (1, 1, 1), pad, [cout], cins,
+                      [(cin * cout, 1, cout)] * len(cins), accumulate=[True] + [False] * (len(cins) - 1),
+                      act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    assert ops.conv3d_tc_supported(d)
+    packed = ops.conv3d_pack_weights(ctx, d, wv)
+    ops.conv3d(ctx, d, [dy.to(dev, torch.bfloat16).contiguous()], wv, None, bufs, packed)
+    torch.cuda.synchronize()
+    for i, (x, b) in enumerate(zip(xs, bufs)):
+        ref = x.grad + (prior.double() if i == 0 else 0)
+        err = (b.double().cpu() - ref).abs().max().item()
+        assert err < 3e-2 * max(1.0, ref.abs().max().item()), (i, err)
+
+
+@pytest.mark.parametrize("dhw,cins,cout,k", [((4, 16, 16), [64], 64, (3, 3, 3)),
+                                             ((4, 16, 16), [64, 32], 32, (1, 3, 3)),
+                                             ((6, 20, 20), [128, 128, 64], 128, (3, 3, 3)),
+                                             ((4, 16, 32), [32, 32, 32, 32, 32], 32, (1, 3, 3)),
+                                             ((5, 10, 10), [256], 512, (3, 3, 3)),
+                                             ((4, 16, 16), [16, 48], 16, (3, 3, 3)),
+                                             ((2, 8, 16), [64], 160, (1, 1, 1))])
+def test_conv_wgrad_tcgen05(ctx, dhw, cins, cout, k):
+    """Weight gradient on the tensor cores (MN-major operands straight from NDHWC) vs autograd."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(9)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g).bfloat16().double() for c in cins]
+    w = torch.zeros((*k, cin, cout), dtype=torch.float64, requires_grad=True)
+    y = O.conv3d_same(torch.cat(xs, -1), w, None, (1, 1, 1))
+    dy = torch.randn(y.shape, generator=g).bfloat16().double()
+    y.backward(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, dhw, k, (1, 1, 1), pad, cins, [cout], [(cin * cout, cout, 1)],
+                      act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    dw = torch.full(w.shape, 0.5, device=dev)                       # accumulates onto existing content
+    db = torch.zeros(cout, device=dev)
+    ops.conv3d_wgrad(ctx, d, [x.to(dev, torch.bfloat16).contiguous() for x in xs],
+                     [dy.to(dev, torch.bfloat16).contiguous()], [dw], [db])
+    torch.cuda.synchronize()
+    ref = w.grad + 0.5
+    scale = max(1.0, ref.abs().max().item())
+    err = (dw.double().cpu() - ref).abs().max().item() / scale
+    assert err < 2e-3, err
+    assert (db.double().cpu() - dy.sum(dim=(0, 1, 2, 3))).abs().max().item() < 1e-2 * scale

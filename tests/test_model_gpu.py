@@ -193,8 +193,16 @@ def test_adam_update_and_second_step(ctx):
                 state[n] = [m, v, vh]
                 t.copy_(w)
         w_ours = model.get_weights()
-        worst = max((torch.from_numpy(w_ours[n]).double() - t.detach()).abs().max().item() for n, t in ps.p.items())
-        # Adam moves every weight by ~lr per step; agreement well below one step size
+        # Adam moves every weight by ~lr * sign(g) on the first steps, so entries whose true gradient is
+        # (analytically) zero - e.g. conv biases in front of an InstanceNorm - move by +-lr on rounding noise
+        # in ANY implementation; compare the well-conditioned entries (|g| > 1e-3 max|g| of the tensor).
+        worst = 0.0
+        for n, t in ps.p.items():
+            if t.grad is None or t.grad.abs().max() == 0:
+                continue
+            mask = t.grad.abs() > 1e-3 * t.grad.abs().max()
+            dw = (torch.from_numpy(w_ours[n]).double() - t.detach()).abs()
+            worst = max(worst, dw[mask].max().item())
         assert worst < 2e-4, worst
 
 

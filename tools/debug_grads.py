@@ -36,6 +36,9 @@ print('...')
 tot_d = sum(r[4] ** 2 for r in rows) ** 0.5
 tot_r = sum(r[3] ** 2 for r in rows) ** 0.5
 print('total rel', tot_d / tot_r)
+import torch as _t
+A = _t.cat([grads[n].double().cpu().flatten() for n in ps.p]); Bv = _t.cat([(t.grad if t.grad is not None else _t.zeros_like(t)).double().flatten() for t in ps.p.values()])
+print('GLOBAL COS', (A @ Bv).item() / (A.norm().item() * Bv.norm().item()))
 rows.sort(key=lambda r: -r[4])
 print('largest abs diffs:')
 for cos, n, na, nb, d in rows[:15]:
