@@ -102,6 +102,8 @@ int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* cons
 int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                     const void* const* douts, float* const* dw, float* const* dbias, void* stream);
 
+/* 1 if the tcgen05 engine takes the weight gradient of output 0 of this launch */
+int m1_conv3d_wgrad_tc_supported0(const m1_conv_desc* d);
 /* BiasAddGrad on its own: dbias[n] += sum_rows dout[row][n] (Conv3DTranspose layers, whose
  * weight gradient runs with the operand roles swapped) */
 int m1_bias_grad(m1_ctx* ctx, const void* dout, int dtype, int64_t rows, int C, float* dbias,

@@ -1,9 +1,17 @@
-// conv_tc.cu — K1/K2: stride-1 3-D convolution (and the data gradient of one) as an implicit
-// GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged
-// by TMA (cp.async.bulk.tensor) straight from the NDHWC activation tensors.
+// conv_tc.cu — K1/K2: 3-D convolution, transposed convolution and their data gradients as an
+// implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA (cp.async.bulk.tensor) straight from the NDHWC activation tensors.
 //
 // Replaces tf.keras.layers.Conv3D at R:network_blocks.py:37-46 (conv1||conv4, conv2, conv3 of
-// every SEResNetBottleNeck), R:networks.py:472 and the Conv3DBackpropInputV2 of their autodiff.
+// every SEResNetBottleNeck), R:networks.py:472, tf.keras.layers.Conv3DTranspose at
+// R:networks.py:496-553 and the Conv3DBackpropInputV2 of their autodiff.
+//
+// Two gather forms cover all four cases (m1_conv_mode):
+//   FWD         in = o*s + k - pad : the A box of a tap is loaded with TMA element strides s
+//               (every s-th voxel), its corner at o0*s + k - pad
+//   TRANSPOSED  in = (o + pad - k)/s : decomposed into the s_d*s_h*s_w output PHASES o = s*j + phi;
+//               inside a phase it is a stride-1 gather in = j + (phi + pad - k)/s over the taps with
+//               k == phi + pad (mod s); the tile is a brick of j, written back with stride s
 //
 // GEMM view   D[M = 128 output voxels, N = produced channels] += A[M, K] * B[N, K]^T
 //   M tile  = a (bd x bh x bw) brick of output voxels of ONE volume (<= 128 voxels)
@@ -30,12 +38,17 @@ struct TcParams {
   int nsrc;
   int src_chunks[M1_MAX_SRC];  // channels / ck of each gathered tensor
   int src_koff[M1_MAX_SRC];    // first K index of the tensor inside a weight-pack row
-  int kd, kh, kw;              // taps
-  int od, oh, ow;              // gather offset of tap 0 (per dim)
-  int sgn;                     // +1: in = o + off0 + k ; -1: in = o + off0 - k
-  int bd, bh, bw;              // brick
+  // tap table: entries [phase_tap0[ph], phase_tap0[ph+1]) belong to output phase ph
+  int nphase;
+  uint8_t phase_tap0[9];
+  int8_t phase_d[8], phase_h[8], phase_w[8];   // phi per dim
+  uint8_t tap_w[32];                           // weight tap of the entry
+  int8_t tap_od[32], tap_oh[32], tap_ow[32];   // gather offset of the entry (voxels of the gathered grid)
+  int istr_d, istr_h, istr_w;  // gathered-grid step per tile voxel (FWD stride; 1 for phases)
+  int ostr_d, ostr_h, ostr_w;  // produced-grid step per tile voxel (phase stride; 1 for FWD)
+  int bd, bh, bw;              // brick (in tile voxels)
   int td, th, tw;              // bricks per dim
-  int Do, Ho, Wo;
+  int Do, Ho, Wo;              // produced grid
   int n_tile;
   int n_total;                 // real produced channels (the weight pack is zero-padded to 16)
   int ck;
@@ -76,6 +89,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const int n_img = t;
   const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
   const int n0 = blockIdx.y * p.n_tile;
+  const int ph = blockIdx.z;
+  const int tap_begin = p.phase_tap0[ph], tap_end = p.phase_tap0[ph + 1];
 
   // ---- one-time setup -------------------------------------------------------------------
   if (warp == 0) {
@@ -100,15 +115,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
   int total_chunks = 0;
   for (int s = 0; s < p.nsrc; ++s) total_chunks += p.src_chunks[s];
-  const int taps = p.kd * p.kh * p.kw;
-  const int ksteps = taps * total_chunks;
+  const int ksteps = (tap_end - tap_begin) * total_chunks;
   const int nstage_iters = (ksteps + p.group - 1) / p.group;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      int tap = 0, src = 0, chunk = 0;
-      int kd_i = 0, kh_i = 0, kw_i = 0;
+      int tap = tap_begin, src = 0, chunk = 0;
+      const int a_d0 = d0 * p.istr_d, a_h0 = h0 * p.istr_h, a_w0 = w0 * p.istr_w;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < nstage_iters; ++it) {
         const int g = min(p.group, ksteps - it * p.group);
@@ -118,20 +132,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         for (int j = 0; j < g; ++j) {
           const uint32_t slot = tiles + (stage * p.group + j) * p.slot_bytes;
           const int c_in = chunk * p.ck;
-          tma_load_5d(slot, &p.tmA[src], full, c_in, w0 + p.ow + p.sgn * kw_i,
-                      h0 + p.oh + p.sgn * kh_i, d0 + p.od + p.sgn * kd_i, n_img);
-          tma_load_3d(slot + p.a_alloc, &p.tmB, full, p.src_koff[src] + c_in, n0, tap);
+          tma_load_5d(slot, &p.tmA[src], full, c_in, a_w0 + p.tap_ow[tap], a_h0 + p.tap_oh[tap],
+                      a_d0 + p.tap_od[tap], n_img);
+          tma_load_3d(slot + p.a_alloc, &p.tmB, full, p.src_koff[src] + c_in, n0, (int)p.tap_w[tap]);
           // advance (chunk, src, tap)
           if (++chunk == p.src_chunks[src]) {
             chunk = 0;
-            if (++src == p.nsrc) {
-              src = 0;
-              ++tap;
-              if (++kw_i == p.kw) {
-                kw_i = 0;
-                if (++kh_i == p.kh) { kh_i = 0; ++kd_i; }
-              }
-            }
+            if (++src == p.nsrc) { src = 0; ++tap; }
           }
         }
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -168,6 +175,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
 
   // ===== epilogue: TMEM -> registers -> (+bias) -> global, all four warps =====
+  // (a phase without taps - kernel smaller than the stride - produces bias only: nothing was issued,
+  //  the MMA warp still commits bar_accum and the accumulator is treated as zero)
   mbar_wait(bar_accum, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
@@ -175,7 +184,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const int lw = r % p.bw;
     const int lh = (r / p.bw) % p.bh;
     const int ld = r / (p.bw * p.bh);
-    const int d = d0 + ld, h = h0 + lh, w = w0 + lw;
+    const int d = (d0 + ld) * p.ostr_d + p.phase_d[ph], h = (h0 + lh) * p.ostr_h + p.phase_h[ph],
+              w = (w0 + lw) * p.ostr_w + p.phase_w[ph];
     const bool valid = (ld < p.bd) && d < p.Do && h < p.Ho && w < p.Wo;
     const int64_t vox = (((int64_t)n_img * p.Do + d) * p.Ho + h) * p.Wo + w;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -183,6 +193,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       uint32_t v[8];
       tmem_ld8(lane_addr + (uint32_t)j, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (ksteps == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0u;
+      }
       int gc = n0 + j;
       if (!valid || gc >= p.n_total) continue;
       int o = 0;
@@ -265,6 +279,9 @@ __global__ void pack_weights_kernel(PackArgs a, int n_real, int n_total, int k_t
 
 struct Plan {
   int ck, n_real, n_total, k_total, n_tile, n_tiles;   // n_total = n_real padded to 16
+  int md, mh, mw;                                      // tile grid (produced grid, or one phase of it)
+  int sd, sh, sw;                                      // strides
+  int nphase;
   int bd, bh, bw, td, th, tw;
   int group, stages;
   uint32_t a_alloc, b_alloc, slot_bytes, smem_bytes, tmem_cols;
@@ -272,11 +289,14 @@ struct Plan {
 
 bool make_plan(const m1_conv_desc* d, Plan* pl) {
   if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
-  for (int i = 0; i < 3; ++i) {
-    if (d->stride[i] != 1) return false;
-    if (d->in_dhw[i] != d->out_dhw[i]) return false;
-  }
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
+  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  if (taps > 32) return false;
+  int nphase = 1;
+  for (int i = 0; i < 3; ++i) {
+    if (d->stride[i] < 1 || d->stride[i] > 2) return false;
+    if (d->mode == M1_CONV_TRANSPOSED) nphase *= d->stride[i];
+  }
   int ck = 64, k_total = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     const int c = d->src_c[s];
@@ -296,8 +316,15 @@ bool make_plan(const m1_conv_desc* d, Plan* pl) {
   for (int c = 256; c >= 16; c -= 16)
     if (n_total % c == 0) { n_tile = c; break; }
   if (!n_tile) return false;
+  // tile grid: the produced grid (FWD) or one output phase of it (TRANSPOSED)
+  int M[3];
+  for (int i = 0; i < 3; ++i)
+    M[i] = d->mode == M1_CONV_TRANSPOSED ? (d->out_dhw[i] + d->stride[i] - 1) / d->stride[i] : d->out_dhw[i];
+  const int D = M[0], H = M[1], W = M[2];
+  // TMA box extent over the gathered grid: brick * element stride <= 256 per dimension
+  const int is_d = d->mode == M1_CONV_FWD ? d->stride[0] : 1, is_h = d->mode == M1_CONV_FWD ? d->stride[1] : 1,
+            is_w = d->mode == M1_CONV_FWD ? d->stride[2] : 1;
   // brick: maximise useful voxels / 128 over all (bd,bh,bw) with bd*bh*bw <= 128
-  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
   double best = -1;
   int bbd = 1, bbh = 1, bbw = 1;
   for (int bd = 1; bd <= 128 && bd <= D; ++bd)
@@ -305,14 +332,19 @@ bool make_plan(const m1_conv_desc* d, Plan* pl) {
       int bw = 128 / (bd * bh);
       if (bw > W) bw = W;
       if (bw < 1) continue;
+      if (bd * is_d > 256 || bh * is_h > 256 || bw * is_w > 256) continue;
       const int64_t tiles = (int64_t)((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
       const double eff = (double)D * H * W / (128.0 * tiles);
       // prefer wide bricks (longer contiguous runs) on ties
       const double score = eff + 1e-6 * bw;
       if (score > best) { best = score; bbd = bd; bbh = bh; bbw = bw; }
     }
+  if (best < 0) return false;
   pl->ck = ck; pl->n_real = n_real; pl->n_total = n_total; pl->k_total = k_total; pl->n_tile = n_tile;
   pl->n_tiles = n_total / n_tile;
+  pl->md = D; pl->mh = H; pl->mw = W;
+  pl->sd = d->stride[0]; pl->sh = d->stride[1]; pl->sw = d->stride[2];
+  pl->nphase = nphase;
   pl->bd = bbd; pl->bh = bbh; pl->bw = bbw;
   pl->td = (D + bbd - 1) / bbd; pl->th = (H + bbh - 1) / bbh; pl->tw = (W + bbw - 1) / bbw;
   pl->a_alloc = 128u * ck * 2u;
@@ -323,21 +355,20 @@ bool make_plan(const m1_conv_desc* d, Plan* pl) {
   pl->tmem_cols = cols;
   // k-steps per stage: aim at >= 64 channels of work per barrier round trip
   pl->group = 64 / ck;
-  const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
-  const int ksteps = taps * (k_total / ck);
+  const int ksteps = ((taps + nphase - 1) / nphase) * (k_total / ck);   // typical k-steps of one CTA
   // co-residency target: as many CTAs/SM as TMEM allows (<=4), smem split accordingly
   int ctas = 512 / (int)cols;
   if (ctas > 4) ctas = 4;
   const uint32_t budget = (227u * 1024u) / ctas - 2048u;
   int stages = (int)(budget / (pl->slot_bytes * pl->group));
   if (stages > 12) stages = 12;
-  const int iters = (ksteps + pl->group - 1) / pl->group;
+  const int iters = std::max(1, (ksteps + pl->group - 1) / pl->group);
   if (stages > iters) stages = iters;
   if (stages < 2) {
     // not enough room at this co-residency: fall back to 1 CTA/SM
     stages = (int)((227u * 1024u - 2048u) / (pl->slot_bytes * pl->group));
     if (stages > 12) stages = 12;
-    if (stages > iters) stages = iters;
+    if (stages > iters) stages = std::max(iters, 1);
     if (stages < 1) return false;
   }
   pl->stages = stages;
@@ -395,18 +426,20 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   static_assert(sizeof(TcParams) < 4000, "kernel parameter block too large");
   TcParams p;
   memset(&p, 0, sizeof(p));
-  const CUtensorMapSwizzle swz = pl.ck == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : pl.ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                               : CU_TENSOR_MAP_SWIZZLE_32B;
-  const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
+  const CUtensorMapSwizzle swz = swizzle_for(pl.ck);
+  const bool fwd = d->mode == M1_CONV_FWD;
+  const int is[3] = {fwd ? pl.sd : 1, fwd ? pl.sh : 1, fwd ? pl.sw : 1};   // gathered-grid step per tile voxel
+  const int os[3] = {fwd ? 1 : pl.sd, fwd ? 1 : pl.sh, fwd ? 1 : pl.sw};   // produced-grid step per tile voxel
+  const int Di = d->in_dhw[0], Hi = d->in_dhw[1], Wi = d->in_dhw[2];
   int koff = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     const cuuint64_t C = (cuuint64_t)d->src_c[s];
-    cuuint64_t dims[5] = {C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)d->batch};
-    cuuint64_t strides[4] = {C * 2, C * 2 * W, C * 2 * W * H, C * 2 * W * H * D};
-    cuuint32_t box[5] = {(cuuint32_t)pl.ck, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh,
-                         (cuuint32_t)pl.bd, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint64_t dims[5] = {C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {C * 2, C * 2 * Wi, C * 2 * Wi * Hi, C * 2 * Wi * Hi * Di};
+    // strided gather: box extent b*s with element stride s loads b voxels (every s-th)
+    cuuint32_t box[5] = {(cuuint32_t)pl.ck, (cuuint32_t)(pl.bw * is[2]), (cuuint32_t)(pl.bh * is[1]),
+                         (cuuint32_t)(pl.bd * is[0]), 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)is[2], (cuuint32_t)is[1], (cuuint32_t)is[0], 1};
     M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d: gathered tensor %d not 16-byte aligned", s);
     CUresult r = encode(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]),
                         dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -428,15 +461,49 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
     M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
   p.nsrc = d->nsrc;
-  p.kd = d->kernel[0]; p.kh = d->kernel[1]; p.kw = d->kernel[2];
-  if (d->mode == M1_CONV_FWD) {
-    p.sgn = 1; p.od = -d->pad[0]; p.oh = -d->pad[1]; p.ow = -d->pad[2];
-  } else {
-    p.sgn = -1; p.od = d->pad[0]; p.oh = d->pad[1]; p.ow = d->pad[2];
+  // ---- tap table (and output phases of a transposed gather)
+  {
+    const int K[3] = {d->kernel[0], d->kernel[1], d->kernel[2]};
+    const int S[3] = {pl.sd, pl.sh, pl.sw};
+    const int P[3] = {d->pad[0], d->pad[1], d->pad[2]};
+    int n = 0, ph = 0;
+    const int pd_n = fwd ? 1 : S[0], ph_n = fwd ? 1 : S[1], pw_n = fwd ? 1 : S[2];
+    for (int fd = 0; fd < pd_n; ++fd)
+      for (int fh = 0; fh < ph_n; ++fh)
+        for (int fw = 0; fw < pw_n; ++fw) {
+          p.phase_tap0[ph] = (uint8_t)n;
+          p.phase_d[ph] = (int8_t)fd; p.phase_h[ph] = (int8_t)fh; p.phase_w[ph] = (int8_t)fw;
+          const int F[3] = {fd, fh, fw};
+          for (int a = 0; a < K[0]; ++a)
+            for (int b = 0; b < K[1]; ++b)
+              for (int c = 0; c < K[2]; ++c) {
+                const int kk[3] = {a, b, c};
+                int off[3];
+                bool ok = true;
+                for (int i = 0; i < 3; ++i) {
+                  if (fwd) {
+                    off[i] = kk[i] - P[i];
+                  } else {
+                    const int num = F[i] + P[i] - kk[i];
+                    if (((num % S[i]) + S[i]) % S[i] != 0) { ok = false; break; }
+                    off[i] = num / S[i];     // exact
+                  }
+                }
+                if (!ok) continue;
+                p.tap_w[n] = (uint8_t)((a * K[1] + b) * K[2] + c);
+                p.tap_od[n] = (int8_t)off[0]; p.tap_oh[n] = (int8_t)off[1]; p.tap_ow[n] = (int8_t)off[2];
+                ++n;
+              }
+          ++ph;
+        }
+    p.phase_tap0[ph] = (uint8_t)n;
+    p.nphase = ph;
   }
+  p.istr_d = is[0]; p.istr_h = is[1]; p.istr_w = is[2];
+  p.ostr_d = os[0]; p.ostr_h = os[1]; p.ostr_w = os[2];
   p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw;
   p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
-  p.Do = D; p.Ho = H; p.Wo = W;
+  p.Do = d->out_dhw[0]; p.Ho = d->out_dhw[1]; p.Wo = d->out_dhw[2];
   p.n_tile = pl.n_tile;
   p.n_total = pl.n_real;
   p.ck = pl.ck;
@@ -475,7 +542,7 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                                  227 * 1024));
     smem_set = 227 * 1024;
   }
-  dim3 grid((unsigned)(d->batch * pl.td * pl.th * pl.tw), (unsigned)pl.n_tiles);
+  dim3 grid((unsigned)(d->batch * pl.td * pl.th * pl.tw), (unsigned)pl.n_tiles, (unsigned)pl.nphase);
   conv_tc_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
   M1_LAUNCH_CHECK(ctx);
   return 0;

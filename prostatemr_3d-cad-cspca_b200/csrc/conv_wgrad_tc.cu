@@ -36,6 +36,7 @@ struct WgParams {
   int blocks_per_tile;           // 128 / ck
   int cin_total;
   int kd, kh, kw, pd, ph, pw;
+  int sd, sh, sw;                // FWD stride: A boxes are loaded with TMA element strides
   int tpg;                       // taps per group (1 or kw)
   int bd, bh, bw, td, th, tw;    // brick, bricks per dim
   int batch;
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
             for (int j = 0; j < nblk; ++j) {
               const int blk = blk0 + j;
               tma_load_5d(sbase + tp * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]], full,
-                          (int)p.blk_c0[blk], w0 + kw0 + tp - p.pw, h0 + kh_i - p.ph, d0 + kd_i - p.pd, n_img);
+                          (int)p.blk_c0[blk], w0 * p.sw + kw0 + tp - p.pw, h0 * p.sh + kh_i - p.ph,
+                          d0 * p.sd + kd_i - p.pd, n_img);
             }
           for (int j = 0; j < p.n_blocks; ++j)
             tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB, full, n0 + j * p.cb, w0, h0, d0, n_img);
@@ -201,7 +203,7 @@ bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
   if (d->mode != M1_CONV_FWD) return false;
   if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
   for (int i = 0; i < 3; ++i)
-    if (d->stride[i] != 1 || d->in_dhw[i] != d->out_dhw[i]) return false;
+    if (d->stride[i] < 1 || d->stride[i] > 2) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC) return false;
   int ck = 64, cin = 0;
   for (int s = 0; s < d->nsrc; ++s) {
@@ -232,6 +234,7 @@ bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
         for (int bw = 1; bd * bh * bw <= kv_max && bw <= W; ++bw) {
           const int kv = bd * bh * bw;
           if (kv % 16) continue;
+          if (bd * d->stride[0] > 256 || bh * d->stride[1] > 256 || bw * d->stride[2] > 256) continue;
           const int64_t tiles = (int64_t)((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
           const double eff = (double)D * H * W / ((double)kv * tiles);
           const double score = eff + 1e-3 * kv / kv_max + 1e-6 * bw;
@@ -273,6 +276,8 @@ int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j) {
   return make_wg_plan(d, j, &pl) ? 1 : 0;
 }
 
+extern "C" int m1_conv3d_wgrad_tc_supported0(const m1_conv_desc* d) { return m1_conv3d_wgrad_tc_supported(d, 0); }
+
 int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* const* srcs, const void* dout,
                        float* dw, cudaStream_t st) {
   WgPlan pl;
@@ -286,7 +291,8 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* co
   int blk = 0, goff = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d_wgrad: gathered tensor %d not 16-byte aligned", s);
-    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], W, H, D, d->batch, pl.ck, pl.bw, pl.bh, pl.bd);
+    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], d->in_dhw[2], d->in_dhw[1], d->in_dhw[0],
+                         d->batch, pl.ck, pl.bw, pl.bh, pl.bd, d->stride[2], d->stride[1], d->stride[0]);
     M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad A %d) failed: %d", s, r);
     for (int c0 = 0; c0 < d->src_c[s]; c0 += pl.ck) {
       p.blk_src[blk] = (uint8_t)s;
@@ -306,6 +312,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* co
   p.cin_total = pl.cin_total;
   p.kd = d->kernel[0]; p.kh = d->kernel[1]; p.kw = d->kernel[2];
   p.pd = d->pad[0]; p.ph = d->pad[1]; p.pw = d->pad[2];
+  p.sd = d->stride[0]; p.sh = d->stride[1]; p.sw = d->stride[2];
   p.tpg = pl.tpg;
   p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw; p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
   p.batch = d->batch;

@@ -81,14 +81,15 @@ inline CUtensorMapSwizzle swizzle_for(int ck) {
 // UMMA shared-memory descriptor layout_type field for rows of ck bf16 elements
 inline uint32_t layout_for(int ck) { return ck == 64 ? 2u : ck == 32 ? 4u : 6u; }
 
-// 5-D map over an NDHWC bf16 tensor with box (ck, bw, bh, bd, 1)
+// 5-D map over an NDHWC bf16 tensor: a box of (ck channels, bw, bh, bd voxels, 1 volume) where voxels
+// are taken every (sw, sh, sd)-th position (TMA element strides; box extent = count * stride)
 inline int encode_ndhwc(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int C, int W, int H, int D, int N,
-                        int ck, int bw, int bh, int bd) {
+                        int ck, int bw, int bh, int bd, int sw = 1, int sh = 1, int sd = 1) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t c2 = (cuuint64_t)C * 2;
   cuuint64_t strides[4] = {c2, c2 * W, c2 * W * H, c2 * W * H * D};
-  cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh), (cuuint32_t)(bd * sd), 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
   return (int)encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ck), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

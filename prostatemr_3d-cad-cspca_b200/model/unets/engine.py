@@ -159,6 +159,48 @@ class Engine:
         self.tape = []
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
+    def _gather(self, cat, mode, batch, in_dhw, out_dhw, k, s, pad, src_t, src_c, ws, wstr, bias, out_t, out_c,
+                acc, key):
+        """One convolution-shaped launch family: outs[j] (+)= gather(concat(src)) * ws[j] (+ bias[j]).
+        The tcgen05 engine takes it when every gathered tensor has a multiple of 16 channels; a
+        concatenation that mixes such tensors with odd ones (the 1-3 channel latents, R:networks.py:653)
+        is split into runs - tensor-core launch for the aligned run, CUDA cores for the rest."""
+        taps = int(np.prod(k))
+        vox = batch * int(np.prod(in_dhw if mode == CONV_TRANSPOSED else out_dhw))
+        act_code, out_code = _code(src_t[0].dtype), _code(out_t[0].dtype)
+        runs = [(0, len(src_t))]
+        if self.use_tc and act_code == BF16 and out_code == BF16:
+            ok = [c % 16 == 0 for c in src_c]
+            if any(ok) and not all(ok):
+                runs, i = [], 0
+                while i < len(ok):
+                    j = i
+                    while j < len(ok) and ok[j] == ok[i]:
+                        j += 1
+                    runs.append((i, j))
+                    i = j
+        offs = np.cumsum([0] + list(src_c))
+        first = True
+        for (i0, i1) in runs:
+            sub_w = [w.view(-1)[int(offs[i0]) * st[1]:] for w, st in zip(ws, wstr)]
+            a_flags = list(acc) if first else [True] * len(out_t)
+            d = ops.conv_desc(mode, batch, in_dhw, out_dhw, k, s, pad, list(src_c[i0:i1]), list(out_c), list(wstr),
+                              accumulate=a_flags, act_dtype=act_code, out_dtype=out_code,
+                              engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
+            packed = None
+            if self.use_tc and ops.conv3d_tc_supported(d):
+                pk = key + (i0,)
+                ent = self.packs.get(pk)
+                if ent is None:
+                    ent = (d, sub_w, ops.conv3d_pack_weights(self.ctx, d, sub_w))
+                    self.packs[pk] = ent
+                packed = ent[2]
+            fl = 2 * vox * taps * int(sum(src_c[i0:i1])) * int(sum(out_c))
+            b = bias if first else None
+            self._timed(cat + ("_tcgen05" if packed is not None else "_simt"), fl,
+                        lambda: ops.conv3d(self.ctx, d, list(src_t[i0:i1]), sub_w, b, list(out_t), packed))
+            first = False
+
     def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None):
         """Conv3D (possibly several layers reading the same input fused along Cout) or
         Conv3DTranspose over the virtual concatenation of `srcs`.
@@ -192,22 +234,9 @@ class Engine:
         self.conv_flops += 2 * int(vox) * taps * cin * sum(co for _, co in layers)
         if self.tracing:
             return outs
-        src_c = [a.c for a in srcs]
-        out_c = [co for _, co in layers]
-        d = ops.conv_desc(mode, batch, in_dhw, out_dhw, k, s, pad, src_c, out_c, wstr,
-                          act_dtype=_code(srcs[0].dtype), out_dtype=_code(out_dtype),
-                          engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
-        packed = None
-        if self.use_tc and ops.conv3d_tc_supported(d):
-            key = ("fwd",) + tuple(n for n, _ in layers)
-            ent = self.packs.get(key)
-            if ent is None:
-                ent = (d, ws, ops.conv3d_pack_weights(self.ctx, d, ws))
-                self.packs[key] = ent
-            packed = ent[2]
-        fl = 2 * int(vox) * taps * cin * sum(co for _, co in layers)
-        self._timed("conv_fwd_tcgen05" if packed is not None else "conv_fwd_simt", fl,
-                    lambda: ops.conv3d(self.ctx, d, [a.t for a in srcs], ws, bs, [o.t for o in outs], packed))
+        self._gather("conv_fwd", mode, batch, in_dhw, out_dhw, k, s, pad, [a.t for a in srcs], [a.c for a in srcs],
+                     ws, wstr, bs, [o.t for o in outs], [co for _, co in layers], [False] * len(layers),
+                     ("fwd",) + tuple(n for n, _ in layers))
         if self.record:
             self._rec(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr),
                       [n + sfx for n, _ in layers for sfx in ("/kernel", "/bias")])
@@ -218,62 +247,41 @@ class Engine:
         for d, ws, packed in self.packs.values():
             ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
 
+    def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl):
+        on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)
+        self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl,
+                    lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs))
+
     def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr):
         live = [j for j, o in enumerate(outs) if o.g is not None]
         if not live:
             return
         batch = srcs[0].shape[0]
         cin = sum(a.c for a in srcs)
-        eng = ENGINE_SIMT
+        auto = ENGINE_AUTO if self.use_tc else ENGINE_SIMT
+        taps = int(np.prod(k))
+        need = [a for a in srcs if a.needs_grad]
+        assert not need or len(need) == len(srcs), "mixed needs_grad inside one concatenation"
         if not transposed:
             # ---- wgrad: dW_j[tap, r, n] += gathered(src)[r] * dout_j[n]; BiasAddGrad fused
             for j in live:
                 co = layers[j][1]
                 d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], [co],
                                   [wstr[j]], act_dtype=_code(srcs[0].dtype), out_dtype=_code(outs[j].dtype),
-                                  engine=eng)
-                fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * cin * co
-                self._timed("conv_wgrad_simt", fl, lambda: ops.conv3d_wgrad(
-                    self.ctx, d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
-                    [self.pg(layers[j][0] + "/bias")]))
-            # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j) - ONE launch per layer j whose
+                                  engine=auto)
+                self._wgrad(d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
+                            [self.pg(layers[j][0] + "/bias")], 2 * batch * int(np.prod(out_dhw)) * taps * cin * co)
+            # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j): ONE launch per layer j whose
             # produced channels are split over the gradients of the concatenated tensors
-            need = [a for a in srcs if a.needs_grad]
-            if need and len(need) == len(srcs):
+            if need:
                 offs = np.cumsum([0] + [a.c for a in srcs])[:-1]
                 for j in live:
                     co = layers[j][1]
                     bufs, accs = zip(*[self.grad_buffer(a) for a in srcs])
                     wv = [ws[j].view(-1)[int(off) * co:] for off in offs]
-                    d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c for a in srcs],
-                                      [(cin * co, 1, co)] * len(srcs), accumulate=list(accs),
-                                      act_dtype=_code(outs[j].dtype), out_dtype=_code(srcs[0].dtype),
-                                      engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
-                    packed = None
-                    if self.use_tc and ops.conv3d_tc_supported(d):
-                        key = ("dgrad", layers[j][0])
-                        ent = self.packs.get(key)
-                        if ent is None:
-                            ent = (d, wv, ops.conv3d_pack_weights(self.ctx, d, wv))
-                            self.packs[key] = ent
-                        packed = ent[2]
-                    fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * cin * co
-                    self._timed("conv_dgrad_tcgen05" if packed is not None else "conv_dgrad_simt", fl,
-                                lambda: ops.conv3d(self.ctx, d, [outs[j].g], wv, None, list(bufs), packed))
-            elif need:
-                off = 0
-                for a in srcs:
-                    if a.needs_grad:
-                        for j in live:
-                            co = layers[j][1]
-                            gbuf, acc = self.grad_buffer(a)
-                            d = ops.conv_desc(CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c],
-                                              [(cin * co, 1, co)], accumulate=acc, act_dtype=_code(outs[j].dtype),
-                                              out_dtype=_code(a.dtype), engine=eng)
-                            fl = 2 * batch * int(np.prod(out_dhw)) * int(np.prod(k)) * a.c * co
-                            self._timed("conv_dgrad_simt", fl, lambda: ops.conv3d(
-                                self.ctx, d, [outs[j].g], [ws[j].view(-1)[off * co:]], None, [gbuf]))
-                    off += a.c
+                    self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [outs[j].g], [co],
+                                 wv, [(cin * co, 1, co)] * len(srcs), None, list(bufs), [a.c for a in srcs],
+                                 list(accs), ("dgrad", layers[j][0]))
         else:
             co = layers[0][1]
             dy = outs[0].g
@@ -282,24 +290,20 @@ class Engine:
             off = 0
             for a in srcs:
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
-                                  act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=eng)
-                fl = 2 * batch * int(np.prod(in_dhw)) * int(np.prod(k)) * a.c * co
-                self._timed("conv_wgrad_simt", fl,
-                            lambda: ops.conv3d_wgrad(self.ctx, d, [dy], [a.t], [gk[off:]], None))
+                                  act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=auto)
+                self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co)
                 off += a.c
             ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
-            # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci]
-            off = 0
-            for a in srcs:
-                if a.needs_grad:
+            # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci] (strided FWD gather);
+            # tensors with odd channel counts (latents) go to the CUDA cores, aligned ones to tcgen05
+            if need:
+                off = 0
+                for idx, a in enumerate(srcs):
                     gbuf, acc = self.grad_buffer(a)
-                    d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
-                                      accumulate=acc, act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype),
-                                      engine=eng)
-                    fl = 2 * batch * int(np.prod(in_dhw)) * int(np.prod(k)) * a.c * co
-                    self._timed("conv_dgrad_simt", fl,
-                                lambda: ops.conv3d(self.ctx, d, [dy], [ws[0].view(-1)[off:]], None, [gbuf]))
-                off += a.c
+                    self._gather("conv_dgrad", CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [dy], [co],
+                                 [ws[0].view(-1)[off:]], [(co * cin, cin, 1)], None, [gbuf], [a.c], [acc],
+                                 ("dgradT", layers[0][0], idx))
+                    off += a.c
         for o in outs:
             o.g = None
 

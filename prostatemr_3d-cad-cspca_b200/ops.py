@@ -61,6 +61,10 @@ def conv3d_tc_supported(d):
     return bool(lib().m1_conv3d_tc_supported(C.byref(d)))
 
 
+def conv3d_wgrad_tc_supported(d):
+    return bool(lib().m1_conv3d_wgrad_tc_supported0(C.byref(d)))
+
+
 def conv3d_pack_weights(ctx, d, ws):
     nbytes = lib().m1_conv3d_packed_bytes(C.byref(d))
     if nbytes == 0:

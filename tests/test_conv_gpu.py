@@ -238,3 +238,91 @@ def test_conv_wgrad_tcgen05(ctx, dhw, cins, cout, k):
     err = (dw.double().cpu() - ref).abs().max().item() / scale
     assert err < 2e-3, err
     assert (db.double().cpu() - dy.sum(dim=(0, 1, 2, 3))).abs().max().item() < 1e-2 * scale
+
+
+STRIDED_TC = [((4, 16, 16), [64], [16, 64], (1, 3, 3), (1, 2, 2)),
+              ((8, 16, 16), [64, 32], [32, 128], (3, 3, 3), (2, 2, 2)),
+              ((6, 20, 12), [128], [64], (3, 3, 3), (1, 2, 2)),
+              ((5, 9, 11), [32], [32], (3, 3, 3), (2, 2, 2))]       # odd sizes: SAME pads (1,1)
+
+
+@pytest.mark.parametrize("dhw,cins,couts,k,s", STRIDED_TC)
+def test_conv_fwd_strided_tcgen05(ctx, dhw, cins, couts, k, s):
+    """Strided convolution: the A boxes are loaded with TMA element strides."""
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k, seed=5)
+    got = _run_fwd(ctx, xs, ws, bs, k, s, torch.bfloat16, _lib.ENGINE_TCGEN05)
+    ref = _ref_fwd(xs, ws, bs, s, torch.bfloat16)
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape and torch.isfinite(g).all()
+        assert (g - r).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("dhw,k,s,cin,cout", [((3, 8, 8), (3, 3, 3), (2, 2, 2), 64, 32),
+                                              ((4, 8, 8), (3, 3, 3), (1, 2, 2), 128, 64),
+                                              ((4, 10, 6), (1, 3, 3), (1, 2, 2), 64, 32),
+                                              ((3, 5, 7), (3, 3, 3), (2, 2, 2), 32, 48)])
+def test_conv_transpose_tcgen05(ctx, dhw, k, s, cin, cout):
+    """Conv3DTranspose forward on the tensor cores: one launch, one output phase per blockIdx.z."""
+    from m1b200 import _lib
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((2, *dhw, cin), generator=g).bfloat16().float()
+    w = (torch.randn((*k, cout, cin), generator=g) / (cin * 4) ** 0.5).bfloat16().float()
+    b = torch.randn((cout,), generator=g) * 0.1
+    from m1b200 import ops
+    dev = 'cuda'
+    out_dhw = [dhw[i] * s[i] for i in range(3)]
+    pad = [ops.same_pads(out_dhw[i], k[i], s[i])[1] for i in range(3)]
+    d = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, out_dhw, k, s, pad, [cin], [cout], [(cout * cin, 1, cin)],
+                      act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    assert ops.conv3d_tc_supported(d)
+    wd, bd = w.to(dev).contiguous(), b.to(dev).contiguous()
+    packed = ops.conv3d_pack_weights(ctx, d, [wd])
+    out = torch.full((2, *out_dhw, cout), float('nan'), device=dev, dtype=torch.bfloat16)
+    ops.conv3d(ctx, d, [x.to(dev, torch.bfloat16).contiguous()], [wd], [bd], [out], packed)
+    torch.cuda.synchronize()
+    ref = O.conv3d_transpose_same(x.double(), w.double(), b.double(), s).float()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all(), "unwritten output voxels"
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dhw,cins,cout,k,s", [((4, 16, 16), [64], 64, (1, 3, 3), (1, 2, 2)),
+                                               ((8, 16, 16), [64, 64], 32, (3, 3, 3), (2, 2, 2)),
+                                               ((5, 9, 11), [32], 32, (3, 3, 3), (2, 2, 2))])
+def test_conv_strided_wgrad_dgrad_tcgen05(ctx, dhw, cins, cout, k, s):
+    """Backward of a STRIDED convolution on the tensor cores: wgrad (element-strided A boxes) and the
+    phase-decomposed data gradient, against autograd of the oracle."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(10)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g).bfloat16().double().requires_grad_() for c in cins]
+    w = (torch.randn((*k, cin, cout), generator=g) / (cin * 9) ** 0.5).bfloat16().double().requires_grad_()
+    y = O.conv3d_same(torch.cat(xs, -1), w, None, s)
+    dy = torch.randn(y.shape, generator=g).bfloat16().double()
+    y.backward(dy)
+    dev = 'cuda'
+    out_dhw = list(y.shape[1:4])
+    pad = [ops.same_pads(dhw[i], k[i], s[i])[1] for i in range(3)]
+    dyd = dy.to(dev, torch.bfloat16).contiguous()
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, out_dhw, k, s, pad, cins, [cout], [(cin * cout, cout, 1)],
+                      act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    dw = torch.zeros(w.shape, device=dev)
+    ops.conv3d_wgrad(ctx, d, [x.detach().to(dev, torch.bfloat16).contiguous() for x in xs], [dyd], [dw], None)
+    torch.cuda.synchronize()
+    scale = max(1.0, w.grad.abs().max().item())
+    assert (dw.double().cpu() - w.grad).abs().max().item() < 2e-3 * scale
+    wd = w.detach().float().to(dev).contiguous()
+    offs = [sum(cins[:i]) for i in range(len(cins))]
+    wv = [wd.view(-1)[o * cout:] for o in offs]
+    dd = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, out_dhw, dhw, k, s, pad, [cout], cins,
+                       [(cin * cout, 1, cout)] * len(cins), act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    assert ops.conv3d_tc_supported(dd)
+    packed = ops.conv3d_pack_weights(ctx, dd, wv)
+    bufs = [torch.full(x.shape, float('nan'), device=dev, dtype=torch.bfloat16) for x in xs]
+    ops.conv3d(ctx, dd, [dyd], wv, None, bufs, packed)
+    torch.cuda.synchronize()
+    for x, bfr in zip(xs, bufs):
+        got = bfr.double().cpu()
+        assert torch.isfinite(got).all()
+        assert (got - x.grad).abs().max().item() < 3e-2 * max(1.0, x.grad.abs().max().item())
