@@ -279,7 +279,12 @@ def run_ours(args):
 
     # ---- roofline of the dominant conv kernel family (CUDA-event durations inside the timed region)
     cats = {}
-    for cat, fl, a, b in prof:
+    if os.environ.get("M1_DUMP_PROF"):
+        rows = sorted(((a.elapsed_time(b), cat, fl, str(lbl)) for cat, fl, a, b, lbl in prof), reverse=True)
+        with open(os.environ["M1_DUMP_PROF"], "w") as fh:
+            for t_ms, cat, fl, lbl in rows:
+                fh.write("%9.3f ms  %-20s %8.2f TFLOP/s  %s\n" % (t_ms, cat, fl / 1e9 / max(t_ms, 1e-6), lbl))
+    for cat, fl, a, b, _ in prof:
         c = cats.setdefault(cat, [0.0, 0.0, 0])
         c[0] += fl; c[1] += a.elapsed_time(b); c[2] += 1
     peaks = {}

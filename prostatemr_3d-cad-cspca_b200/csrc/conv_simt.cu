@@ -179,6 +179,79 @@ __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ S
   }
 }
 
+// ---- few-channel convolution ------------------------------------------------------------------
+// Launches with <= 16 gathered or <= 16 produced channels (stem 3-4 -> 32, the f/4 = 8 bottleneck at
+// full resolution, 1-3 channel latents, 2-6 channel heads and their data gradients) waste most of the
+// 64x64x16 tiles above. Here a thread owns ONE produced voxel x 8 produced channels; the weight
+// slice [tap][r][32 channels] of the block's channel tile sits in shared memory, gathered rows are
+// read straight from global/L1 - exactly the needed FMAs, coalesced 16-byte stores.
+constexpr int TN = 32;   // produced channels per block
+constexpr int TV = 32;   // voxels per block (x 4 channel groups of 8 = 128 threads)
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(128) conv_thin_kernel(const __grid_constant__ SimtParams p, int k_total) {
+  extern __shared__ float wsm[];   // [tap][r][TN]
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * TN;
+  const int taps = p.kd * p.kh * p.kw;
+  for (int e = tid; e < taps * k_total * TN; e += 128) {
+    const int nn = e % TN;
+    const int r = (e / TN) % k_total;
+    const int tap = e / (TN * k_total);
+    int n = n0 + nn;
+    float x = 0.f;
+    if (n < p.n_total) {
+      const int j = out_of(p, n);
+      x = p.w[j][tap * p.st[j] + (int64_t)r * p.sr[j] + (int64_t)n * p.so[j]];
+    }
+    wsm[e] = x;
+  }
+  __syncthreads();
+  const int g = tid >> 5;                       // channel group of 8 inside the tile
+  const int64_t m = (int64_t)blockIdx.x * TV + (tid & 31);
+  if (m >= p.out_vox) return;
+  int64_t t = m;
+  const int w = (int)(t % p.Wo); t /= p.Wo;
+  const int h = (int)(t % p.Ho); t /= p.Ho;
+  const int d = (int)(t % p.Do); t /= p.Do;
+  const int n_img = (int)t;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+    const int64_t iv = gather_index(p, n_img, d, h, w, a, b, c);
+    if (iv < 0) continue;
+    int r_base = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      const int C = p.src_c[s];
+      const T* row = reinterpret_cast<const T*>(p.src[s]) + iv * C;
+      const float* wrow = wsm + ((size_t)tap * k_total + r_base) * TN + g * 8;
+      for (int ci = 0; ci < C; ++ci) {
+        const float x = ld_f<T>(row + ci);
+        const float4 w0 = *reinterpret_cast<const float4*>(wrow + (size_t)ci * TN);
+        const float4 w1 = *reinterpret_cast<const float4*>(wrow + (size_t)ci * TN + 4);
+        acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+        acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+        acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+        acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+      }
+      r_base += C;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int n = n0 + g * 8 + i;
+    if (n >= p.n_total) continue;
+    const int j = out_of(p, n);
+    float v = acc[i];
+    if (p.bias[j]) v += p.bias[j][n];
+    TO* dst = reinterpret_cast<TO*>(p.out[j]) + m * p.out_c[j] + n;
+    if ((p.accumulate >> j) & 1) v += ld_f<TO>(dst);
+    st_f<TO>(dst, v);
+  }
+}
+
 // ---- weight gradient ----------------------------------------------------------------------
 // dW[tap, r, n] += sum_o G(o, tap)[r] * dY[o, n];  block = (64 r x 64 n) tile of one tap over a
 // slab of output voxels, fp32 atomics into dW.
@@ -279,6 +352,91 @@ __global__ void __launch_bounds__(TH) wgrad_simt_kernel(const __grid_constant__ 
   }
 }
 
+// ---- weight gradient, few-channel layers ------------------------------------------------------
+// Layers such as the stem (3-4 -> 32), the f/4 = 8 bottlenecks at full resolution, the 1-3 channel
+// latents and the 2-6 channel heads have R*N <= 4096 outputs per tap but millions of voxels: the
+// 64x64-tile kernel above would spend >90 % of its FMAs on zero padding. Here a block owns one tap
+// and a voxel slab, stages VCH voxels of both operands in shared memory and every thread keeps
+// ceil(R*N / blockDim) accumulators in registers - exactly the needed MACs.
+// Thread = (4 reduced rows x 8 produced channels) micro-tile x one voxel lane: per staged voxel it
+// reads 4 + 8 values from shared memory for 32 FMAs; the voxel lanes of a block split the slab.
+constexpr int SW_RB = 4, SW_NB = 8;
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant__ WgradParams q, int vch) {
+  const SimtParams& p = q.g;
+  extern __shared__ float sm[];
+  const int R = p.src_c[q.src_index], N = q.Cn;
+  const int Rp = (R + SW_RB - 1) / SW_RB * SW_RB, Np = (N + SW_NB - 1) / SW_NB * SW_NB;
+  float* xs = sm;                      // [vch][Rp]
+  float* ys = sm + (size_t)vch * Rp;   // [vch][Np]
+  __shared__ int64_t vin[64];
+  const T* src = reinterpret_cast<const T*>(p.src[q.src_index]);
+  const TO* dy = reinterpret_cast<const TO*>(q.dout);
+  const int tap = blockIdx.y;
+  const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+  const int64_t v_begin = (int64_t)blockIdx.x * q.vox_per_block;
+  const int64_t v_end = min(v_begin + q.vox_per_block, p.out_vox);
+  const int mt = (Rp / SW_RB) * (Np / SW_NB);      // micro-tiles
+  const int lanes = blockDim.x / mt;               // voxel lanes (>= 1 by construction)
+  const int my_mt = threadIdx.x % mt, my_lane = threadIdx.x / mt;
+  const int r0 = (my_mt / (Np / SW_NB)) * SW_RB, n0 = (my_mt % (Np / SW_NB)) * SW_NB;
+  float acc[SW_RB][SW_NB];
+#pragma unroll
+  for (int i = 0; i < SW_RB; ++i)
+#pragma unroll
+    for (int j = 0; j < SW_NB; ++j) acc[i][j] = 0.f;
+
+  for (int64_t v0 = v_begin; v0 < v_end; v0 += vch) {
+    __syncthreads();
+    if (threadIdx.x < vch) {
+      int64_t m = v0 + threadIdx.x;
+      int64_t iv = -1;
+      if (m < v_end) {
+        int w = (int)(m % p.Wo); m /= p.Wo;
+        int h = (int)(m % p.Ho); m /= p.Ho;
+        int d = (int)(m % p.Do); m /= p.Do;
+        iv = gather_index(p, (int)m, d, h, w, a, b, c);
+      }
+      vin[threadIdx.x] = iv;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < vch * Rp; e += blockDim.x) {
+      const int vv = e / Rp, rr = e % Rp;
+      const int64_t iv = vin[vv];
+      xs[e] = (iv >= 0 && rr < R) ? ld_f<T>(src + iv * R + rr) : 0.f;
+    }
+    for (int e = threadIdx.x; e < vch * Np; e += blockDim.x) {
+      const int vv = e / Np, nn = e % Np;
+      ys[e] = (vin[vv] >= 0 && nn < N) ? ld_f<TO>(dy + (v0 + vv) * N + nn) : 0.f;
+    }
+    __syncthreads();
+    if (my_lane < lanes) {
+      for (int vv = my_lane; vv < vch; vv += lanes) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + vv * Rp + r0);
+        const float4 y0 = *reinterpret_cast<const float4*>(ys + vv * Np + n0);
+        const float4 y1 = *reinterpret_cast<const float4*>(ys + vv * Np + n0 + 4);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+        for (int i = 0; i < SW_RB; ++i)
+#pragma unroll
+          for (int j = 0; j < SW_NB; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+      }
+    }
+  }
+  if (my_lane < lanes) {
+#pragma unroll
+    for (int i = 0; i < SW_RB; ++i)
+#pragma unroll
+      for (int j = 0; j < SW_NB; ++j) {
+        const int rr = r0 + i, nn = n0 + j;
+        if (rr < R && nn < N && acc[i][j] != 0.f)
+          atomicAdd(q.dw + tap * q.st + (int64_t)(q.r_base + rr) * q.sr + (int64_t)nn * q.so, acc[i][j]);
+      }
+  }
+}
+
 // column sums: dbias[n] += sum_rows x[row][n]
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t rows, int C, int64_t rows_per_block,
@@ -345,8 +503,21 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
     p.w[j] = w[j];
     p.bias[j] = bias ? bias[j] : nullptr;
   }
-  dim3 grid((unsigned)cdiv64(p.out_vox, BM), (unsigned)((p.n_total + BN - 1) / BN));
   const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
+  int k_total = 0;
+  for (int s = 0; s < d->nsrc; ++s) k_total += d->src_c[s];
+  const int taps = p.kd * p.kh * p.kw;
+  const size_t thin_smem = (size_t)taps * k_total * TN * sizeof(float);
+  if ((k_total <= 16 || p.n_total <= 16) && thin_smem <= 48 * 1024) {
+    dim3 tgrid((unsigned)cdiv64(p.out_vox, TV), (unsigned)((p.n_total + TN - 1) / TN));
+    if (ib && ob) conv_thin_kernel<__nv_bfloat16, __nv_bfloat16><<<tgrid, 128, thin_smem, st>>>(p, k_total);
+    else if (ib) conv_thin_kernel<__nv_bfloat16, float><<<tgrid, 128, thin_smem, st>>>(p, k_total);
+    else if (ob) conv_thin_kernel<float, __nv_bfloat16><<<tgrid, 128, thin_smem, st>>>(p, k_total);
+    else conv_thin_kernel<float, float><<<tgrid, 128, thin_smem, st>>>(p, k_total);
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  dim3 grid((unsigned)cdiv64(p.out_vox, BM), (unsigned)((p.n_total + BN - 1) / BN));
   if (ib && ob) conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
   else if (ib) conv_simt_kernel<__nv_bfloat16, float><<<grid, TH, 0, st>>>(p);
   else if (ob) conv_simt_kernel<float, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
@@ -383,6 +554,30 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       q.src_index = s;
       q.r_base = r_base;
       const int C = d->src_c[s];
+      {
+        // few-channel layer: exact-work kernel (micro-tiles of 4 x 8 outputs, <= 256 per block)
+        const int Rp = (C + SW_RB - 1) / SW_RB * SW_RB, Np = (q.Cn + SW_NB - 1) / SW_NB * SW_NB;
+        const int mt = (Rp / SW_RB) * (Np / SW_NB);
+        if (mt <= 256 && (C < 48 || q.Cn < 48)) {
+          int vch = 40960 / ((Rp + Np) * 4);
+          vch = std::min(64, vch & ~7);
+          if (vch >= 8) {
+            int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, taps));
+            int64_t vpb = std::max<int64_t>(cdiv64(cdiv64(out_vox, want), vch) * vch, (int64_t)vch * 4);
+            q.vox_per_block = vpb;
+            dim3 grid((unsigned)cdiv64(out_vox, vpb), (unsigned)taps);
+            const size_t smem = (size_t)vch * (Rp + Np) * sizeof(float);
+            const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
+            if (ib && ob) wgrad_small_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>(q, vch);
+            else if (ib) wgrad_small_kernel<__nv_bfloat16, float><<<grid, 256, smem, st>>>(q, vch);
+            else if (ob) wgrad_small_kernel<float, __nv_bfloat16><<<grid, 256, smem, st>>>(q, vch);
+            else wgrad_small_kernel<float, float><<<grid, 256, smem, st>>>(q, vch);
+            M1_LAUNCH_CHECK(ctx);
+            r_base += C;
+            continue;
+          }
+        }
+      }
       const int tiles = ((C + BM - 1) / BM) * ((q.Cn + BN - 1) / BN);
       // split the voxel reduction so that the launch has ~8 blocks per SM
       int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, tiles * taps));

@@ -129,14 +129,14 @@ class Engine:
             return act.g, False
         return act.g, True
 
-    def _timed(self, cat, flops, fn):
+    def _timed(self, cat, flops, fn, label=None):
         if self.prof is None:
             return fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
         b.record()
-        self.prof.append((cat, flops, a, b))
+        self.prof.append((cat, flops, a, b, label))
 
     def begin(self, record=True):
         self.tape = []
@@ -198,7 +198,8 @@ class Engine:
             fl = 2 * vox * taps * int(sum(src_c[i0:i1])) * int(sum(out_c))
             b = bias if first else None
             self._timed(cat + ("_tcgen05" if packed is not None else "_simt"), fl,
-                        lambda: ops.conv3d(self.ctx, d, list(src_t[i0:i1]), sub_w, b, list(out_t), packed))
+                        lambda: ops.conv3d(self.ctx, d, list(src_t[i0:i1]), sub_w, b, list(out_t), packed),
+                        label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)))
             first = False
 
     def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None):
@@ -247,10 +248,12 @@ class Engine:
         for d, ws, packed in self.packs.values():
             ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
 
-    def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl):
+    def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl, label=None):
         on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)
         self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl,
-                    lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs))
+                    lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
+                    label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
+                           tuple(srcs_t[0].shape[1:4])))
 
     def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr):
         live = [j for j, o in enumerate(outs) if o.g is not None]
@@ -270,7 +273,8 @@ class Engine:
                                   [wstr[j]], act_dtype=_code(srcs[0].dtype), out_dtype=_code(outs[j].dtype),
                                   engine=auto)
                 self._wgrad(d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
-                            [self.pg(layers[j][0] + "/bias")], 2 * batch * int(np.prod(out_dhw)) * taps * cin * co)
+                            [self.pg(layers[j][0] + "/bias")], 2 * batch * int(np.prod(out_dhw)) * taps * cin * co,
+                            layers[j][0])
             # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j): ONE launch per layer j whose
             # produced channels are split over the gradients of the concatenated tensors
             if need:
@@ -291,7 +295,8 @@ class Engine:
             for a in srcs:
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
                                   act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=auto)
-                self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co)
+                self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
+                            layers[0][0] + "(T)")
                 off += a.c
             ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
             # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci] (strided FWD gather);
