@@ -17,14 +17,17 @@ IN_EPS = 1e-3
 
 class Act:
     """An NDHWC activation: shape, device tensor (None while tracing) and its gradient."""
-    __slots__ = ("shape", "t", "g", "dtype", "needs_grad")
+    __slots__ = ("shape", "t", "g", "dtype", "needs_grad", "lc")
 
-    def __init__(self, shape, dtype, t=None, needs_grad=True):
+    def __init__(self, shape, dtype, t=None, needs_grad=True, lc=None):
         self.shape = tuple(int(s) for s in shape)
         self.dtype = dtype
         self.t = t
         self.g = None
         self.needs_grad = needs_grad
+        # logical (reference) channel count; shape[-1] is the physical one, zero-padded to the tensor-core
+        # granularity for the few-channel tensors (f/4 = 8 bottlenecks, 3-4 channel inputs, 1-3 channel latents)
+        self.lc = int(lc) if lc is not None else self.shape[-1]
 
     @property
     def grid(self):
@@ -110,13 +113,17 @@ class Engine:
             return None
         return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
 
-    def input(self, t, needs_grad=False):
+    def input(self, t, needs_grad=False, lc=None):
         if self.tracing:
-            return Act(t, self.act_dtype, None, needs_grad)  # t is a shape
-        return Act(t.shape, t.dtype, t, needs_grad)
+            return Act(t, self.act_dtype, None, needs_grad, lc)  # t is a shape
+        return Act(t.shape, t.dtype, t, needs_grad, lc)
 
-    def p(self, name, shape, kind):
-        self.params.declare(name, shape, kind)
+    def padc(self, c):
+        """physical channel count of a few-channel activation: multiples of 16 feed the tensor cores"""
+        return -(-c // 16) * 16 if self.use_tc else c
+
+    def p(self, name, shape, kind, pshape=None, index=None):
+        self.params.declare(name, shape, kind, pshape, index)
         return None if self.tracing else self.params.view(name)
 
     def pg(self, name):
@@ -202,12 +209,20 @@ class Engine:
                         label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)))
             first = False
 
-    def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None):
+    def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None, pad_out=None):
         """Conv3D (possibly several layers reading the same input fused along Cout) or
         Conv3DTranspose over the virtual concatenation of `srcs`.
-        layers: [(param_prefix, cout)]; returns one Act per layer."""
+        layers: [(param_prefix, cout)]; returns one Act per layer. pad_out[j]: zero-pad layer j's output
+        channels to the tensor-core granularity (the parameters keep their reference shape logically)."""
         k, s = tuple(k), tuple(s)
+        pad_out = pad_out or [False] * len(layers)
+        lcin = sum(a.lc for a in srcs)
+        lco = [co for _, co in layers]
+        layers = [(n, self.padc(co) if po else co) for (n, co), po in zip(layers, pad_out)]
         cin = sum(a.c for a in srcs)
+        # logical -> physical position of every gathered channel over the virtual concatenation
+        cin_index = np.concatenate([off + np.arange(a.lc) for off, a in
+                                    zip(np.cumsum([0] + [a.c for a in srcs])[:-1], srcs)])
         batch, in_dhw = srcs[0].shape[0], srcs[0].grid
         for a in srcs:
             assert a.grid == in_dhw, "concatenated tensors must share the grid"
@@ -217,6 +232,8 @@ class Engine:
             out_dhw = tuple(in_dhw[i] * s[i] for i in range(3))
             pad = tuple(ops.same_pads(out_dhw[i], k[i], s[i])[1] for i in range(3))
             shapes = [k + (layers[0][1], cin)]
+            lshapes = [k + (lco[0], lcin)]
+            index = [{3: np.arange(lco[0]), 4: cin_index}]
             wstr = [(layers[0][1] * cin, 1, cin)]
             mode = CONV_TRANSPOSED
         else:
@@ -224,15 +241,18 @@ class Engine:
             out_dhw = tuple(g[0] for g in geo)
             pad = tuple(g[1] for g in geo)
             shapes = [k + (cin, co) for _, co in layers]
+            lshapes = [k + (lcin, c) for c in lco]
+            index = [{3: cin_index, 4: np.arange(c)} for c in lco]
             wstr = [(cin * co, co, 1) for _, co in layers]
             mode = CONV_FWD
-        ws = [self.p(n + "/kernel", shp, "kernel") for (n, _), shp in zip(layers, shapes)]
-        bs = [self.p(n + "/bias", (co,), "bias") for n, co in layers]
-        outs = [Act((batch,) + out_dhw + (co,), out_dtype, self.new((batch,) + out_dhw + (co,), out_dtype))
-                for _, co in layers]
+        ws = [self.p(n + "/kernel", lshp, "kernel", shp, ix)
+              for (n, _), shp, lshp, ix in zip(layers, shapes, lshapes, index)]
+        bs = [self.p(n + "/bias", (c,), "bias", (co,), {0: np.arange(c)}) for (n, co), c in zip(layers, lco)]
+        outs = [Act((batch,) + out_dhw + (co,), out_dtype, self.new((batch,) + out_dhw + (co,), out_dtype), lc=c)
+                for (_, co), c in zip(layers, lco)]
         taps = k[0] * k[1] * k[2]
         vox = batch * (np.prod(in_dhw) if transposed else np.prod(out_dhw))
-        self.conv_flops += 2 * int(vox) * taps * cin * sum(co for _, co in layers)
+        self.conv_flops += 2 * int(vox) * taps * lcin * sum(lco)      # algorithmic (reference) FLOPs
         if self.tracing:
             return outs
         self._gather("conv_fwd", mode, batch, in_dhw, out_dhw, k, s, pad, [a.t for a in srcs], [a.c for a in srcs],
@@ -315,9 +335,10 @@ class Engine:
     # ---- K4 instance norm + activation ---------------------------------------------------------
     def inorm_act(self, x, name, slope):
         c = x.c
-        gamma = self.p(name + "/gamma", (c,), "gamma")
-        beta = self.p(name + "/beta", (c,), "beta")
-        y = Act(x.shape, x.dtype, self.new(x.shape, x.dtype))
+        ix = {0: np.arange(x.lc)}
+        gamma = self.p(name + "/gamma", (x.lc,), "gamma", (c,), ix)     # padded channels: gamma = beta = 0
+        beta = self.p(name + "/beta", (x.lc,), "beta", (c,), ix)
+        y = Act(x.shape, x.dtype, self.new(x.shape, x.dtype), lc=x.lc)
         if self.tracing:
             return y
         stats = self.new((x.shape[0], c, 2), torch.float32)
@@ -426,7 +447,8 @@ class Engine:
     def latent(self, ml, mode, eps):
         """ml: fp32 [.., 2L]; mode 0 sample (eps fp32 tensor), 1 mean."""
         L = ml.c // 2
-        z = Act(ml.shape[:-1] + (L,), self.act_dtype, self.new(ml.shape[:-1] + (L,)))
+        zc = self.padc(L)
+        z = Act(ml.shape[:-1] + (zc,), self.act_dtype, self.new(ml.shape[:-1] + (zc,)), lc=L)
         if self.tracing:
             return z
         ops.latent_fwd(self.ctx, ml.t, eps, mode, z.t)

@@ -20,14 +20,16 @@ class SEResNetBottleNeck:
 
     def __call__(self, eng, srcs, drop=None):
         f, n = self.filters, self.name
-        cin = sum(a.c for a in srcs)
+        cin = sum(a.lc for a in srcs)
         if cin == f:
             # R:network_blocks.py:63 - identity residual; never reached by M1 (every block changes the
             # channel count) and it would need the concatenation materialised.
             raise NotImplementedError("SEResNetBottleNeck with an identity residual (Cin == filters)")
-        raw1, raw4 = eng.conv(srcs, [(n + "/conv1", f // 4), (n + "/conv4", f)], self.kernel_size, self.strides)
+        # the f/4 bottleneck tensors are zero-padded to 16 channels when f/4 is not a multiple of 16 (f = 32)
+        raw1, raw4 = eng.conv(srcs, [(n + "/conv1", f // 4), (n + "/conv4", f)], self.kernel_size, self.strides,
+                              pad_out=[True, False])
         a = eng.inorm_act(raw1, n + "/norm1", LRELU)
-        raw2, = eng.conv([a], [(n + "/conv2", f // 4)], (3, 3, 3))
+        raw2, = eng.conv([a], [(n + "/conv2", f // 4)], (3, 3, 3), pad_out=[True])
         b = eng.inorm_act(raw2, n + "/norm2", LRELU)
         raw3, = eng.conv([b], [(n + "/conv3", f)], (1, 1, 1))
         return eng.se_tail(raw3, raw4, n, self.reduction, drop)

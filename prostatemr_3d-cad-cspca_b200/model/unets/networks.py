@@ -142,7 +142,7 @@ class M1Core:
         self.shapes = dict(inputs=[a.shape for a in inputs], x=x.shape, conv1=conv1.shape, conv2=conv2.shape,
                            conv3=conv3.shape, convm=convm.shape,
                            att=[None if a is None else a.shape for a in att],
-                           uconv_=[None if u is None else u[0].shape[:-1] + (sum(a.c for a in u),) for u in uconv_],
+                           uconv_=[None if u is None else u[0].shape[:-1] + (sum(a.lc for a in u),) for u in uconv_],
                            uconv=[None if u is None else u.shape for u in uconv])
 
         ds_feats = {}
@@ -293,7 +293,7 @@ class M1(LoadableModel):
 
         # ---- parameter inventory: a shape-only trace of one training step (Keras builds on first call)
         self.params = ParamTable()
-        tracer = Engine(self.params, precision, device=None)
+        tracer = Engine(self.params, precision, device=None, use_tcgen05=use_tcgen05)
         self._graph(tracer, batch=1, training=True, trace=True)
         if probabilistic:
             self._infer_graph(tracer, batch=1, trace=True)
@@ -362,22 +362,26 @@ class M1(LoadableModel):
         image channel 2, NOT channel 3; the slicing is reproduced exactly."""
         D = self.input_spatial_dims
         C, nc = self.input_channels, self.num_classes
-        if not self.probabilistic:
+
+        def padded(lc, copies):
+            """(B,D,H,W,pad16(lc)) activation, zero beyond the real channels (tensor-core granularity)"""
+            pc = eng.padc(lc)
             if trace:
-                return [eng.input((batch,) + D + (C,))], None
-            img = eng.new((batch,) + D + (C,))
-            ops.copy_channels(eng.ctx, x, 0, img, 0, C)
-            return [eng.input(img)], None
+                return eng.input((batch,) + D + (pc,), lc=lc)
+            t = eng.new((batch,) + D + (pc,), zero=pc != lc)
+            for src_off, dst_off, n in copies:
+                ops.copy_channels(eng.ctx, x, src_off, t, dst_off, n)
+            return eng.input(t, lc=lc)
+
+        if not self.probabilistic:
+            return [padded(C, [(0, 0, C)])], None
         ci = C - (nc - 1)
         lab_lo, lab_hi = C - (nc - 1) - 1, C - 1
         cl = lab_hi - lab_lo
-        if trace:
-            return [eng.input((batch,) + D + (ci,))], [eng.input((batch,) + D + (cl,))]
-        img = eng.new((batch,) + D + (ci,))
-        lab = eng.new((batch,) + D + (cl,))
-        ops.copy_channels(eng.ctx, x, 0, img, 0, ci)
-        ops.copy_channels(eng.ctx, x, lab_lo, lab, 0, cl)
-        return [eng.input(img)], [eng.input(lab)]
+        img = padded(ci, [(0, 0, ci)])
+        # posterior input = concat([image, label]) as ONE tensor (R:networks.py:348)
+        post = padded(ci + cl, [(0, 0, ci), (lab_lo, ci, cl)])
+        return [img], [post]
 
     def _graph(self, eng, batch, training, trace=False, x=None):
         """One training-graph forward. Returns dict(heads=[(logits Act, up)], kl_pairs=[(ml_q, ml_p)])."""
@@ -386,7 +390,7 @@ class M1(LoadableModel):
             o = self.core(eng, img, pass_name='det', training=training)
             heads = [(o['logits'], (1, 1, 1))] + (o.get('ds_logits') or [])
             return dict(heads=heads, kl_pairs=[])
-        post_in = img + lab
+        post_in = lab                 # [image || label] already concatenated by _inputs
         q_sample = self.posterior(eng, post_in, False, None, 'q_sample', training, 'latents')
         q_mean = self.posterior(eng, post_in, True, None, 'q_mean', training, 'latents')
         p_zq = self.prior(eng, img, False, q_sample['prob_used_latents'], 'p_z_q', training, 'latents')
@@ -588,7 +592,8 @@ class M1(LoadableModel):
             self.eng.refresh_packs()
 
     def gradients(self):
-        return {n: self.params.grad(n) for n in self.params.specs}
+        """reference-shaped gradients of the last train_step (host tensors)"""
+        return self.params.grad_dict()
 
     def get_optimizer_state(self):
         P = self.params

@@ -20,12 +20,34 @@ KIND_GROUP = {"kernel": "kernel", "bias": "bias", "se_kernel": "plain", "se_bias
 
 
 class ParamSpec:
-    __slots__ = ("name", "shape", "kind", "offset", "size")
+    """shape = the reference (Keras) shape; pshape = the shape held in HBM. They differ only for layers
+    whose channel counts are zero-padded to the tensor-core granularity (16): `index` maps, per padded
+    axis, logical position -> physical position. Padded entries are zero, receive exactly-zero
+    gradients (their activations are identically zero) and therefore stay zero under Adam."""
+    __slots__ = ("name", "shape", "kind", "offset", "size", "pshape", "psize", "index")
 
-    def __init__(self, name, shape, kind):
+    def __init__(self, name, shape, kind, pshape=None, index=None):
         self.name, self.shape, self.kind = name, tuple(int(s) for s in shape), kind
         self.size = int(np.prod(self.shape))
+        self.pshape = tuple(int(s) for s in (pshape if pshape is not None else shape))
+        self.psize = int(np.prod(self.pshape))
+        self.index = index if (index and self.pshape != self.shape) else None
         self.offset = -1
+
+    def to_physical(self, logical):
+        """numpy logical array -> zero-padded physical array"""
+        if self.index is None:
+            return np.asarray(logical, dtype=np.float32).reshape(self.pshape)
+        out = np.zeros(self.pshape, dtype=np.float32)
+        ix = np.ix_(*[self.index.get(ax, np.arange(n)) for ax, n in enumerate(self.shape)])
+        out[ix] = np.asarray(logical, dtype=np.float32).reshape(self.shape)
+        return out
+
+    def to_logical(self, physical):
+        if self.index is None:
+            return np.asarray(physical).reshape(self.shape)
+        ix = np.ix_(*[self.index.get(ax, np.arange(n)) for ax, n in enumerate(self.shape)])
+        return np.asarray(physical).reshape(self.pshape)[ix]
 
 
 class ParamTable:
@@ -39,13 +61,14 @@ class ParamTable:
         self._gviews = {}
 
     # ---- registration (trace time) -----------------------------------------------------------
-    def declare(self, name, shape, kind):
+    def declare(self, name, shape, kind, pshape=None, index=None):
         sp = self.specs.get(name)
         if sp is None:
             assert not self.finalized, f"parameter {name} requested after the table was finalised"
-            sp = ParamSpec(name, shape, kind)
+            sp = ParamSpec(name, shape, kind, pshape, index)
             self.specs[name] = sp
         assert sp.shape == tuple(shape), (name, sp.shape, tuple(shape))
+        assert sp.pshape == tuple(pshape if pshape is not None else shape), (name, sp.pshape, pshape)
         return sp
 
     def finalize(self):
@@ -55,7 +78,7 @@ class ParamTable:
             for sp in self.specs.values():
                 if KIND_GROUP[sp.kind] == grp:
                     sp.offset = off
-                    off += -(-sp.size // ALIGN) * ALIGN
+                    off += -(-sp.psize // ALIGN) * ALIGN
             self.group_range[grp] = (start, off)
         self.total = off
         self.finalized = True
@@ -76,14 +99,14 @@ class ParamTable:
         host = np.zeros(self.total, dtype=np.float32)
         for sp in self.specs.values():
             s = (zlib.crc32(sp.name.encode()) + 7919 * seed) % (2 ** 31 - 1)
-            host[sp.offset:sp.offset + sp.size] = init_for_kind[sp.kind](sp.shape, s).reshape(-1)
+            host[sp.offset:sp.offset + sp.psize] = sp.to_physical(init_for_kind[sp.kind](sp.shape, s)).reshape(-1)
         self.w.copy_(torch.from_numpy(host))
 
     def view(self, name):
         v = self._views.get(name)
         if v is None:
             sp = self.specs[name]
-            v = self.w[sp.offset:sp.offset + sp.size].view(sp.shape)
+            v = self.w[sp.offset:sp.offset + sp.psize].view(sp.pshape)
             self._views[name] = v
         return v
 
@@ -91,12 +114,18 @@ class ParamTable:
         v = self._gviews.get(name)
         if v is None:
             sp = self.specs[name]
-            v = self.g[sp.offset:sp.offset + sp.size].view(sp.shape)
+            v = self.g[sp.offset:sp.offset + sp.psize].view(sp.pshape)
             self._gviews[name] = v
         return v
 
     def state_dict(self):
-        return {name: self.view(name).detach().cpu().numpy() for name in self.specs}
+        """reference-shaped (logical) numpy arrays"""
+        return {name: np.ascontiguousarray(sp.to_logical(self.view(name).detach().cpu().numpy()))
+                for name, sp in self.specs.items()}
+
+    def grad_dict(self):
+        return {name: torch.from_numpy(np.ascontiguousarray(sp.to_logical(self.grad(name).detach().cpu().numpy())))
+                for name, sp in self.specs.items()}
 
     def load_state_dict(self, weights, strict=True):
         missing = [n for n in self.specs if n not in weights]
@@ -104,5 +133,5 @@ class ParamTable:
             raise KeyError(f"missing weights: {missing[:5]}{'...' if len(missing) > 5 else ''}")
         for name, sp in self.specs.items():
             if name in weights:
-                t = torch.as_tensor(np.asarray(weights[name]), dtype=torch.float32).reshape(sp.shape)
+                t = torch.from_numpy(sp.to_physical(np.asarray(weights[name], dtype=np.float32)))
                 self.view(name).copy_(t)
