@@ -157,13 +157,23 @@ def dlpack_device_ptr(obj, expect_cuda=True):
     return ptr
 
 
+_STRICT_DLPACK = os.environ.get("M1_PTR_VIA_DLPACK") == "1"
+
+
 def ptr(t):
-    """Raw device pointer of a torch tensor (None -> NULL)."""
+    """Raw device pointer of a tensor (None -> NULL). Foreign tensors (anything exporting __dlpack__:
+    cupy / jax / TF-experimental) always go through the DLPack capsule; for torch tensors the capsule's
+    data pointer IS tensor.data_ptr() (asserted by tests/test_host_logic.py), so the per-launch fast path
+    reads that directly - M1_PTR_VIA_DLPACK=1 forces the capsule route everywhere."""
     if t is None:
         return None
     if isinstance(t, torch.Tensor):
-        assert t.is_contiguous(), "m1b200 kernels take dense tensors"
-        return dlpack_device_ptr(t.detach(), expect_cuda=True) if t.numel() else None
+        if not t.is_cuda:
+            raise M1Error("m1b200 kernels need CUDA device memory; there is no CPU path")
+        if _STRICT_DLPACK:
+            assert t.is_contiguous(), "m1b200 kernels take dense tensors"
+            return dlpack_device_ptr(t.detach(), expect_cuda=True) if t.numel() else None
+        return t.data_ptr() or None
     return dlpack_device_ptr(t)
 
 

@@ -536,19 +536,25 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
   for (int s = 0; s < d->nsrc; ++s) q.g.src[s] = srcs[s];
   const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
   const int64_t out_vox = q.g.out_vox;
+  // tensor-core engine: all produced tensors fused in ONE launch when the plan allows (the gathered
+  // operand - the big one - is then streamed once), else one launch per produced tensor
+  const bool fused_tc = d->engine != M1_ENGINE_SIMT && d->nout > 1 && m1_conv3d_wgrad_tc_supported(d, 0, d->nout);
+  if (fused_tc) {
+    if (m1_conv3d_wgrad_tc(ctx, d, 0, d->nout, srcs, douts, dw, st)) return 1;
+  }
   for (int j = 0; j < d->nout; ++j) {
     q.dout = douts[j];
     q.Cn = d->out_c[j];
     q.dw = dw[j];
     q.st = d->w_stride_tap[j]; q.sr = d->w_stride_red[j]; q.so = d->w_stride_out[j];
     int r_base = 0;
-    const bool use_tc = d->engine != M1_ENGINE_SIMT && m1_conv3d_wgrad_tc_supported(d, j);
+    const bool use_tc = fused_tc || (d->engine != M1_ENGINE_SIMT && m1_conv3d_wgrad_tc_supported(d, j, 1));
     if (d->engine == M1_ENGINE_TCGEN05 && !use_tc) {
       m1_set_error("m1_conv3d_wgrad: launch not supported by the tcgen05 engine");
       return 1;
     }
-    if (use_tc) {
-      if (m1_conv3d_wgrad_tc(ctx, d, j, srcs, douts[j], dw[j], st)) return 1;
+    if (use_tc && !fused_tc) {
+      if (m1_conv3d_wgrad_tc(ctx, d, j, 1, srcs, douts, dw, st)) return 1;
     }
     for (int s = 0; s < d->nsrc && !use_tc; ++s) {
       q.src_index = s;

@@ -27,8 +27,10 @@ constexpr int kMaxBlocks = 64;   // 16-channel blocks over the concatenation han
 
 struct WgParams {
   CUtensorMap tmA[M1_MAX_SRC];
-  CUtensorMap tmB;
+  CUtensorMap tmB[M1_MAX_OUT];
   int nsrc;
+  uint8_t nb_out[kMaxBlocks];    // N block -> dY tensor
+  uint16_t nb_c0[kMaxBlocks];    // N block -> first channel inside that tensor
   uint8_t blk_src[kMaxBlocks];   // M block -> gathered tensor
   uint16_t blk_c0[kMaxBlocks];   // M block -> first channel inside that tensor
   uint16_t blk_goff[kMaxBlocks]; // M block -> first channel over the virtual concatenation
@@ -43,7 +45,9 @@ struct WgParams {
   int kv;                        // voxels per brick (multiple of 16)
   int ck, cb;                    // channels per A / B block
   int n_tile, n_blocks;          // N per CTA, B blocks per CTA
-  int co;                        // produced channels (real)
+  int co;                        // produced channels over all fused dY tensors
+  int nout;
+  int out_start[M1_MAX_OUT + 1];
   int stages;
   uint32_t a_tap_bytes, b_off, stage_bytes;
   uint32_t a_blk_bytes, b_blk_bytes;
@@ -53,8 +57,8 @@ struct WgParams {
   uint32_t a_lbo, b_lbo;         // >> 4
   int splits;
   int64_t bricks_total;
-  float* dw;
-  int64_t st, sr, so;
+  float* dw[M1_MAX_OUT];
+  int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
@@ -129,8 +133,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
                           (int)p.blk_c0[blk], w0 * p.sw + kw0 + tp - p.pw, h0 * p.sh + kh_i - p.ph,
                           d0 * p.sd + kd_i - p.pd, n_img);
             }
-          for (int j = 0; j < p.n_blocks; ++j)
-            tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB, full, n0 + j * p.cb, w0, h0, d0, n_img);
+          for (int j = 0; j < p.n_blocks; ++j) {
+            const int nb = n0 / p.cb + j;
+            tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB[p.nb_out[nb]], full, (int)p.nb_c0[nb], w0, h0,
+                        d0, n_img);
+          }
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -172,17 +179,19 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int tp = 0; tp < p.tpg; ++tp) {
       const int tap = (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
-      float* dst_row = p.dw + tap * p.st + (int64_t)rglob * p.sr;
       for (int j = 0; j < p.n_tile; j += 8) {
         uint32_t v[8];
         tmem_ld8(lane_addr + (uint32_t)(tp * p.n_tile + j), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!row_ok) continue;
+        int n = n0 + j;                       // 8-column groups never straddle two dY tensors (channels % 16 == 0)
+        if (n >= p.co) continue;
+        int o = 0;
+        while (o + 1 < p.nout && n >= p.out_start[o + 1]) ++o;
+        n -= p.out_start[o];
+        float* dst = p.dw[o] + tap * p.st[o] + (int64_t)rglob * p.sr[o] + (int64_t)n * p.so[o];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = n0 + j + i;
-          if (n < p.co) atomicAdd(dst_row + (int64_t)n * p.so, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + (int64_t)i * p.so[o], __uint_as_float(v[i]));
       }
     }
   }
@@ -199,7 +208,7 @@ struct WgPlan {
   uint32_t a_blk_bytes, b_blk_bytes, a_tap_bytes, b_off, stage_bytes, smem_bytes, tmem_cols;
 };
 
-bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
+bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
   if (d->mode != M1_CONV_FWD) return false;
   if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
   for (int i = 0; i < 3; ++i)
@@ -215,14 +224,20 @@ bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
     // fall back to coarser blocks only if every tensor allows it; otherwise refuse
     return false;
   }
-  const int co = d->out_c[j];
-  if (co % 16) return false;
-  int cb = 64;
-  while (co % cb) cb >>= 1;
+  int co = 0, cb = 64;
+  for (int j = j0; j < j0 + jn; ++j) {
+    if (d->out_c[j] % 16) return false;
+    while (d->out_c[j] % cb) cb >>= 1;
+    co += d->out_c[j];
+  }
+  if (co / cb > kMaxBlocks) return false;
   int n_tile = co;
   if (n_tile > 256) {
-    n_tile = 256;
-    while (co % n_tile || n_tile % cb) n_tile -= cb;
+    // largest N tile <= 256 that is a multiple of the block size and divides the total
+    n_tile = 0;
+    for (int c = 256 / cb * cb; c >= cb; c -= cb)
+      if (co % c == 0) { n_tile = c; break; }
+    if (!n_tile) return false;
   }
   int tpg = (d->kernel[2] * n_tile <= 512) ? d->kernel[2] : 1;
   // brick: voxels multiple of 16, <= kv_max, best volume coverage
@@ -271,17 +286,19 @@ bool make_wg_plan(const m1_conv_desc* d, int j, WgPlan* pl) {
 
 }  // namespace
 
-int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j) {
+int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j0, int jn) {
   WgPlan pl;
-  return make_wg_plan(d, j, &pl) ? 1 : 0;
+  return make_wg_plan(d, j0, jn, &pl) ? 1 : 0;
 }
 
-extern "C" int m1_conv3d_wgrad_tc_supported0(const m1_conv_desc* d) { return m1_conv3d_wgrad_tc_supported(d, 0); }
+extern "C" int m1_conv3d_wgrad_tc_supported0(const m1_conv_desc* d) {
+  return m1_conv3d_wgrad_tc_supported(d, 0, d->nout) || m1_conv3d_wgrad_tc_supported(d, 0, 1);
+}
 
-int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* const* srcs, const void* dout,
-                       float* dw, cudaStream_t st) {
+int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const void* const* srcs,
+                       const void* const* douts, float* const* dws, cudaStream_t st) {
   WgPlan pl;
-  M1_CHECK(make_wg_plan(d, j, &pl), "m1_conv3d_wgrad: launch not supported by the tcgen05 engine");
+  M1_CHECK(make_wg_plan(d, j0, jn, &pl), "m1_conv3d_wgrad: launch not supported by the tcgen05 engine");
   M1_CHECK(ctx->encode_tiled != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   static_assert(sizeof(WgParams) < 4000, "kernel parameter block too large");
@@ -303,8 +320,24 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* co
     goff += d->src_c[s];
   }
   {
-    int r = encode_ndhwc(encode, &p.tmB, dout, d->out_c[j], W, H, D, d->batch, pl.cb, pl.bw, pl.bh, pl.bd);
-    M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad B) failed: %d", r);
+    int nb = 0, acc = 0;
+    for (int o = 0; o < jn; ++o) {
+      const int j = j0 + o;
+      int r = encode_ndhwc(encode, &p.tmB[o], douts[j], d->out_c[j], W, H, D, d->batch, pl.cb, pl.bw, pl.bh, pl.bd);
+      M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad B %d) failed: %d", j, r);
+      for (int c0 = 0; c0 < d->out_c[j]; c0 += pl.cb) {
+        p.nb_out[nb] = (uint8_t)o;
+        p.nb_c0[nb] = (uint16_t)c0;
+        ++nb;
+      }
+      p.out_start[o] = acc;
+      acc += d->out_c[j];
+      p.dw[o] = dws[j];
+      p.st[o] = d->w_stride_tap[j]; p.sr[o] = d->w_stride_red[j]; p.so[o] = d->w_stride_out[j];
+    }
+    p.out_start[jn] = acc;
+    p.nout = jn;
+    p.co = acc;
   }
   p.nsrc = d->nsrc;
   p.nblocks = pl.nblocks;
@@ -319,7 +352,6 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* co
   p.kv = pl.kv;
   p.ck = pl.ck; p.cb = pl.cb;
   p.n_tile = pl.n_tile; p.n_blocks = pl.n_blocks;
-  p.co = d->out_c[j];
   p.stages = pl.stages;
   p.a_tap_bytes = pl.a_tap_bytes; p.b_off = pl.b_off; p.stage_bytes = pl.stage_bytes;
   p.a_blk_bytes = pl.a_blk_bytes; p.b_blk_bytes = pl.b_blk_bytes;
@@ -341,8 +373,6 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j, const void* co
   int64_t splits = std::max<int64_t>(1, ((int64_t)ctx->num_sms * 2 + base_ctas - 1) / base_ctas);
   splits = std::min<int64_t>(splits, std::max<int64_t>(1, p.bricks_total / 4));
   p.splits = (int)splits;
-  p.dw = dw;
-  p.st = d->w_stride_tap[j]; p.sr = d->w_stride_red[j]; p.so = d->w_stride_out[j];
 
   static int smem_set = 0;
   if (!smem_set) {

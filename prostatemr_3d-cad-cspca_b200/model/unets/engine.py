@@ -286,15 +286,16 @@ class Engine:
         need = [a for a in srcs if a.needs_grad]
         assert not need or len(need) == len(srcs), "mixed needs_grad inside one concatenation"
         if not transposed:
-            # ---- wgrad: dW_j[tap, r, n] += gathered(src)[r] * dout_j[n]; BiasAddGrad fused
-            for j in live:
-                co = layers[j][1]
-                d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], [co],
-                                  [wstr[j]], act_dtype=_code(srcs[0].dtype), out_dtype=_code(outs[j].dtype),
-                                  engine=auto)
-                self._wgrad(d, [a.t for a in srcs], [outs[j].g], [self.pg(layers[j][0] + "/kernel")],
-                            [self.pg(layers[j][0] + "/bias")], 2 * batch * int(np.prod(out_dhw)) * taps * cin * co,
-                            layers[j][0])
+            # ---- wgrad: dW_j[tap, r, n] += gathered(src)[r] * dout_j[n] for all layers j of the fused launch in
+            # one call (the gathered operand is streamed once); BiasAddGrad per layer
+            cos = [layers[j][1] for j in live]
+            d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], cos,
+                              [wstr[j] for j in live], act_dtype=_code(srcs[0].dtype),
+                              out_dtype=_code(outs[live[0]].dtype), engine=auto)
+            self._wgrad(d, [a.t for a in srcs], [outs[j].g for j in live],
+                        [self.pg(layers[j][0] + "/kernel") for j in live],
+                        [self.pg(layers[j][0] + "/bias") for j in live],
+                        2 * batch * int(np.prod(out_dhw)) * taps * cin * sum(cos), layers[live[0]][0])
             # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j): ONE launch per layer j whose
             # produced channels are split over the gradients of the concatenated tensors
             if need:

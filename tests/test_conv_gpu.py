@@ -326,3 +326,33 @@ def test_conv_strided_wgrad_dgrad_tcgen05(ctx, dhw, cins, cout, k, s):
         got = bfr.double().cpu()
         assert torch.isfinite(got).all()
         assert (got - x.grad).abs().max().item() < 3e-2 * max(1.0, x.grad.abs().max().item())
+
+
+def test_conv_wgrad_tcgen05_fused_outputs(ctx):
+    """conv1||conv4: the weight gradients of both layers from ONE tensor-core launch (N = 16 + 64)."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(12)
+    dhw, cins, couts, k = (4, 16, 16), [64, 32], [16, 64], (3, 3, 3)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g).bfloat16().double() for c in cins]
+    ws = [torch.zeros((*k, cin, co), dtype=torch.float64, requires_grad=True) for co in couts]
+    x = torch.cat(xs, -1)
+    dys = []
+    for w in ws:
+        y = O.conv3d_same(x, w, None, (1, 1, 1))
+        dy = torch.randn(y.shape, generator=g).bfloat16().double()
+        y.backward(dy)
+        dys.append(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, dhw, k, (1, 1, 1), pad, cins, couts,
+                      [(cin * co, co, 1) for co in couts], act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    dws = [torch.zeros(w.shape, device=dev) for w in ws]
+    dbs = [torch.zeros(co, device=dev) for co in couts]
+    ops.conv3d_wgrad(ctx, d, [t.to(dev, torch.bfloat16).contiguous() for t in xs],
+                     [t.to(dev, torch.bfloat16).contiguous() for t in dys], dws, dbs)
+    torch.cuda.synchronize()
+    for w, dw, dy, db in zip(ws, dws, dys, dbs):
+        scale = max(1.0, w.grad.abs().max().item())
+        assert (dw.double().cpu() - w.grad).abs().max().item() < 2e-3 * scale
+        assert (db.double().cpu() - dy.sum(dim=(0, 1, 2, 3))).abs().max().item() < 1e-2 * scale

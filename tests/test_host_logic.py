@@ -132,4 +132,9 @@ def test_dlpack_pointer_export_rejects_cpu_memory():
     t = torch.zeros(4)
     with pytest.raises(_lib.M1Error):
         _lib.ptr(t)
+    with pytest.raises(_lib.M1Error):
+        _lib.dlpack_device_ptr(t)
+    # the capsule's data pointer (+ byte offset) is the tensor's data pointer, also for offset views
     assert _lib.dlpack_device_ptr(t, expect_cuda=False) == t.data_ptr()
+    v = torch.arange(64, dtype=torch.float32)[16:32]
+    assert _lib.dlpack_device_ptr(v, expect_cuda=False) == v.data_ptr()
