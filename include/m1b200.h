@@ -63,6 +63,10 @@ typedef struct {
   int32_t act_dtype;                  /* m1_dtype of the gathered tensors */
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
+  /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
+   * wgrad: tune[0] = max voxels per K brick (16..128), tune[1] = taps sharing one dY tile (1 or kw),
+   *        tune[2] = pipeline stage cap;  conv: tune[0] = stage cap, tune[1] = k-steps per stage */
+  int32_t tune[4];
 } m1_conv_desc;
 
 typedef struct m1_ctx m1_ctx;

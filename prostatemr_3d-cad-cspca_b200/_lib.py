@@ -29,7 +29,7 @@ class ConvDesc(C.Structure):
         ("w_stride_tap", C.c_int64 * M1_MAX_OUT), ("w_stride_red", C.c_int64 * M1_MAX_OUT),
         ("w_stride_out", C.c_int64 * M1_MAX_OUT),
         ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("out_dtype", C.c_int32),
-        ("engine", C.c_int32),
+        ("engine", C.c_int32), ("tune", C.c_int32 * 4),
     ]
 
 

@@ -18,6 +18,8 @@
 // are added to the fp32 gradient with atomics (shared weights accumulate over passes anyway).
 #include "tc_common.cuh"
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 namespace {
 using namespace tc;
@@ -257,8 +259,16 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
         }
     return best > 0;
   };
-  for (int kv_max = 128; kv_max >= 16; kv_max >>= 1) {
-    int bd, bh, bw;
+  // tiling overrides: host autotuning (d->tune) or environment (experiments)
+  static const int g_kv = getenv("M1_WG_KV") ? atoi(getenv("M1_WG_KV")) : 0;
+  static const int g_tpg = getenv("M1_WG_TPG") ? atoi(getenv("M1_WG_TPG")) : 0;
+  static const int g_stages = getenv("M1_WG_STAGES") ? atoi(getenv("M1_WG_STAGES")) : 0;
+  const int env_kv = d->tune[0] ? d->tune[0] : g_kv;
+  const int env_tpg = d->tune[1] ? d->tune[1] : g_tpg;
+  const int env_stages = d->tune[2] ? d->tune[2] : (g_stages ? g_stages : 2);
+  if (env_tpg == 1) tpg = 1;
+  for (int kv_max = env_kv ? env_kv : 128; kv_max >= 16; kv_max >>= 1) {
+    int bd = 1, bh = 1, bw = 1;
     if (!pick(kv_max, &bd, &bh, &bw)) continue;
     const int kv = bd * bh * bw;
     for (int tp = tpg; tp >= 1; tp = (tp == 1 ? 0 : 1)) {
@@ -268,6 +278,7 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
       const uint32_t stage = (b_off + (uint32_t)(n_tile / cb) * b_blk + 1023u) & ~1023u;
       int stages = (int)((227u * 1024u - 2048u) / stage);
       if (stages > 8) stages = 8;
+      if (env_stages && stages > env_stages) stages = env_stages;
       if (stages < 2) continue;
       pl->ck = ck; pl->cb = cb; pl->n_tile = n_tile; pl->n_blocks = n_tile / cb; pl->tpg = tp; pl->kv = kv;
       pl->bd = bd; pl->bh = bh; pl->bw = bw;
@@ -370,8 +381,19 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   const int n_tiles = (p.co + pl.n_tile - 1) / pl.n_tile;
   const int groups = p.kd * p.kh * (p.kw / pl.tpg);
   const int64_t base_ctas = (int64_t)groups * m_tiles * n_tiles;
-  int64_t splits = std::max<int64_t>(1, ((int64_t)ctx->num_sms * 2 + base_ctas - 1) / base_ctas);
-  splits = std::min<int64_t>(splits, std::max<int64_t>(1, p.bricks_total / 4));
+  // split-K factor: ~2-4 CTAs per SM in total, chosen so that the last wave is as full as possible
+  int64_t splits = 1;
+  {
+    const int64_t sms = ctx->num_sms, max_splits = std::max<int64_t>(1, p.bricks_total / 4);
+    double best = -1;
+    for (int64_t sp = 1; sp <= max_splits && base_ctas * sp <= sms * 6; ++sp) {
+      const int64_t total = base_ctas * sp;
+      const double waves = (double)total / sms;
+      const double eff = waves / std::ceil(waves);          // fill of the last wave
+      const double score = eff - (total < sms * 2 ? 0.5 * (1.0 - (double)total / (sms * 2)) : 0.0) - 1e-3 * sp;
+      if (score > best) { best = score; splits = sp; }
+    }
+  }
   p.splits = (int)splits;
 
   static int smem_set = 0;

@@ -104,6 +104,8 @@ class Engine:
         self.noise = None
         self.packs = {}            # key -> (desc, [kernel names], packed tensor)
         self.prof = None           # bench.py: list of (category, flops, start_event, end_event)
+        self.autotune = True       # one-off timing of candidate tcgen05 tilings per layer shape
+        self.tuned = {}
         self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -268,12 +270,45 @@ class Engine:
         for d, ws, packed in self.packs.values():
             ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
 
+    WG_CANDIDATES = ((128, 0, 2), (128, 1, 2), (64, 0, 2), (64, 1, 2), (128, 0, 3), (64, 0, 3))
+
     def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl, label=None):
         on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)
+        if on_tc and self.autotune:
+            key = ("wgrad", label, tuple(srcs_t[0].shape[:4]), tuple(t.shape[-1] for t in srcs_t),
+                   tuple(t.shape[-1] for t in douts_t))
+            cfg = self.tuned.get(key)
+            if cfg is None:
+                cfg = self._tune_wgrad(d, srcs_t, douts_t, dws)
+                self.tuned[key] = cfg
+            d.tune[0], d.tune[1], d.tune[2] = cfg
         self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl,
                     lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
                            tuple(srcs_t[0].shape[1:4])))
+
+    def _tune_wgrad(self, d, srcs_t, douts_t, dws):
+        """One-off per layer shape: time the candidate tilings of the tcgen05 weight-gradient kernel on
+        scratch gradient buffers (CUDA events) and keep the fastest."""
+        scratch = [torch.zeros(w.numel(), dtype=torch.float32, device=self.device) for w in dws]
+        best, best_t = (0, 0, 0), float("inf")
+        for cand in self.WG_CANDIDATES:
+            d.tune[0], d.tune[1], d.tune[2] = cand
+            if not ops.conv3d_wgrad_tc_supported(d):
+                continue
+            ts = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, scratch, None)
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            t = min(ts[1:])
+            if t < best_t:
+                best, best_t = cand, t
+        d.tune[0], d.tune[1], d.tune[2] = 0, 0, 0
+        return best
 
     def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr):
         live = [j for j, o in enumerate(outs) if o.g is not None]
