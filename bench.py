@@ -116,22 +116,24 @@ def oracle_step_fn(dims, threads):
                 w, m, v, vh = O.adam_amsgrad_step(t, t.grad, m, v, vh, step[0], 1e-3)
                 t.copy_(w)
                 state[n] = (m, v, vh)
-        return float(r['loss'])
+        return float(r['loss'].detach())
     return f
 
 
 def pick_cpu_sample(dims, budget_s, nsteps, threads):
-    """Largest (D, H/2^k, W/2^k) crop of the volume whose nsteps training steps fit the budget; the
-    conv cost is linear in the voxel count, so volumes/s = voxel fraction / step time."""
-    probe = (dims[0], max(16, dims[1] // 8), max(16, dims[2] // 8))
+    """Largest crop (H, W multiples of 16 so that the four stride-2 levels nest) of the volume whose
+    nsteps training steps fit the budget; the conv cost is linear in the voxel count, so
+    volumes/s = voxel fraction / step time."""
+    probe = (dims[0], 32, 32)
     f = oracle_step_fn(probe, threads)
     f()
     t0 = time.time(); f(); t_probe = time.time() - t0
     per_voxel = t_probe / (probe[0] * probe[1] * probe[2])
-    k = 0
-    while k < 3 and per_voxel * dims[0] * (dims[1] >> k) * (dims[2] >> k) * nsteps > budget_s:
-        k += 1
-    return (dims[0], dims[1] >> k, dims[2] >> k)
+    cands = [(dims[1], dims[2]), (dims[1], dims[2] // 2), (dims[1] // 2, dims[2] // 2), (80, 48), (48, 48), (32, 32)]
+    for h, w in cands:
+        if h % 16 == 0 and w % 16 == 0 and per_voxel * dims[0] * h * w * nsteps <= budget_s:
+            return (dims[0], h, w)
+    return (dims[0], 32, 32)
 
 
 def cpu_baseline(dims, budget_s=30.0):

@@ -132,6 +132,192 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6, vectorised variants (channel counts that are multiples of 8): a group of G = F/8 lanes owns one
+// theta voxel, every lane 8 channels (one 16-byte access per tensor); 32/G consecutive voxels share
+// a warp, so the phi-gradient atomics of voxels below the same gating voxel are pre-reduced by
+// shuffles (the gating grid is 4-16x coarser along w).
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float group_sum(float v, int G) {   // sum over the G lanes of a voxel group
+  for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int64_t coarse_index(int64_t v, Grid3 fine, Grid3 coarse) {
+  int64_t r = v;
+  const int x = (int)(r % fine.w); r /= fine.w;
+  const int y = (int)(r % fine.h); r /= fine.h;
+  const int z = (int)(r % fine.d); r /= fine.d;
+  const int sd = fine.d / coarse.d, sh = fine.h / coarse.h, sw = fine.w / coarse.w;
+  return ((r * coarse.d + min(z / sd, coarse.d - 1)) * coarse.h + min(y / sh, coarse.h - 1)) * coarse.w +
+         min(x / sw, coarse.w - 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_psi_vec_kernel(const T* __restrict__ theta, const T* __restrict__ phi,
+                                                         const float* __restrict__ w_psi,
+                                                         const float* __restrict__ b_psi, int64_t nvox, Grid3 tg,
+                                                         Grid3 gg, int F, int G, float* __restrict__ psi) {
+  const int lg = threadIdx.x % G;
+  const int64_t per_pass = (int64_t)gridDim.x * (TB / G);
+  const int64_t rounds = (nvox + per_pass - 1) / per_pass;
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t v = it * per_pass + (int64_t)blockIdx.x * (TB / G) + threadIdx.x / G;
+    float s = 0.f;
+    if (v < nvox) {
+      const int64_t gv = coarse_index(v, tg, gg);
+      for (int c = lg * 8; c < F; c += G * 8) {
+        float t8[8], p8[8], w8[8];
+        load8<T>(theta + v * F + c, t8);
+        load8<T>(phi + gv * F + c, p8);
+        load8<float>(w_psi + c, w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(lrelu(t8[i] + p8[i], M1_LRELU_SLOPE), w8[i], s);
+      }
+    }
+    s = group_sum(s, G);
+    if (v < nvox && lg == 0) psi[v] = 1.f / (1.f + __expf(-(s + b_psi[0])));
+  }
+}
+
+// y = up(psi) * x  (dx mode: out (+)= up(psi) * dy)
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_scale_vec_kernel(const T* __restrict__ x, const float* __restrict__ psi,
+                                                           Grid3 xg, Grid3 tg, int Cx, T* __restrict__ y, int acc,
+                                                           int64_t total8) {
+  const int c8 = Cx / 8;
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total8; i += (int64_t)gridDim.x * TB) {
+    const int64_t xv = i / c8;
+    const float p = psi[coarse_index(xv, xg, tg)];
+    float v[8];
+    load8<T>(x + i * 8, v);
+    if (acc) {
+      float o[8];
+      load8<T>(y + i * 8, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], p, o[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= p;
+    }
+    store8<T>(y + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TB) attn_bwd_psi_vec_kernel(
+    const T* __restrict__ dy, const T* __restrict__ theta, const T* __restrict__ phi,
+    const float* __restrict__ w_psi, const float* __restrict__ psi, const T* __restrict__ x, int64_t nvox, Grid3 tg,
+    Grid3 gg, Grid3 xg, int F, int G, T* __restrict__ dtheta, float* __restrict__ dphi,
+    float* __restrict__ dw_psi, float* __restrict__ db_psi) {
+  extern __shared__ float sdw[];  // F + 1
+  for (int i = threadIdx.x; i <= F; i += TB) sdw[i] = 0.f;
+  __syncthreads();
+  const int lg = threadIdx.x % G, lane = threadIdx.x & 31;
+  const int ud = xg.d / tg.d, uh = xg.h / tg.h, uw = xg.w / tg.w;
+  const int64_t per_pass = (int64_t)gridDim.x * (TB / G);
+  const int64_t rounds = (nvox + per_pass - 1) / per_pass;
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t v = it * per_pass + (int64_t)blockIdx.x * (TB / G) + threadIdx.x / G;
+    const bool ok = v < nvox;
+    float dpsi = 0.f;
+    int64_t gv = -1;
+    if (ok) {
+      gv = coarse_index(v, tg, gg);
+      int64_t r = v;
+      const int tx = (int)(r % tg.w); r /= tg.w;
+      const int ty = (int)(r % tg.h); r /= tg.h;
+      const int tz = (int)(r % tg.d); r /= tg.d;
+      for (int a = 0; a < ud; ++a)
+        for (int b = 0; b < uh; ++b)
+          for (int c = 0; c < uw; ++c) {
+            const int64_t xv = ((r * xg.d + tz * ud + a) * xg.h + ty * uh + b) * xg.w + tx * uw + c;
+            for (int ch = lg * 8; ch < F; ch += G * 8) {   // Cx == F for every gate of M1
+              float d8[8], x8[8];
+              load8<T>(dy + xv * F + ch, d8);
+              load8<T>(x + xv * F + ch, x8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dpsi = fmaf(d8[i], x8[i], dpsi);
+            }
+          }
+    }
+    dpsi = group_sum(dpsi, G);
+    const float p = ok ? psi[v] : 0.f;
+    const float ds = dpsi * p * (1.f - p);
+    // do all voxel groups of this warp sit below the same gating voxel? then pre-reduce across them
+    const int64_t gv0 = __shfl_sync(0xffffffffu, gv, 0);
+    const bool same = __all_sync(0xffffffffu, gv == gv0 && ok);
+    for (int c = lg * 8; c < F; c += G * 8) {
+      float dth[8], dwp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dth[i] = 0.f; dwp[i] = 0.f; }
+      if (ok) {
+        float t8[8], p8[8], w8[8];
+        load8<T>(theta + v * F + c, t8);
+        load8<T>(phi + gv * F + c, p8);
+        load8<float>(w_psi + c, w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pre = t8[i] + p8[i];
+          dth[i] = ds * w8[i] * (pre > 0.f ? 1.f : M1_LRELU_SLOPE);
+          dwp[i] = ds * lrelu(pre, M1_LRELU_SLOPE);
+        }
+        store8<T>(dtheta + v * F + c, dth);
+      }
+      // reduce over the voxel groups of the warp (lanes with equal lg)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        for (int o = G; o < 32; o <<= 1) {
+          dwp[i] += __shfl_xor_sync(0xffffffffu, dwp[i], o);
+          if (same) dth[i] += __shfl_xor_sync(0xffffffffu, dth[i], o);
+        }
+      }
+      if (lane < G) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&sdw[c + i], dwp[i]);
+      }
+      if (same) {
+        if (lane < G) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(dphi + gv * F + c + i, dth[i]);
+        }
+      } else if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dphi + gv * F + c + i, dth[i]);
+      }
+    }
+    float dsum = (lg == 0 && ok) ? ds : 0.f;
+    dsum = warp_sum(dsum);
+    if (lane == 0) atomicAdd(&sdw[F], dsum);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F; i += TB) atomicAdd(dw_psi + i, sdw[i]);
+  if (threadIdx.x == 0) atomicAdd(db_psi, sdw[F]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K7 latent heads
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float clip01(float ls) { return fminf(fmaxf(ls, -0.1f), 0.1f); }
@@ -309,6 +495,24 @@ extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, cons
            "m1_attn_fwd: grids must nest by integer factors");
   const int64_t tv = (int64_t)batch * T3.d * T3.h * T3.w;
   const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
+  const int G = F / 8;
+  const bool vec = F % 8 == 0 && Cx % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0;
+  if (vec) {
+    const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
+    if (dtype == M1_BF16) {
+      using T = __nv_bfloat16;
+      attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv, T3, G3, F, G, psi);
+      M1_LAUNCH_CHECK(ctx);
+      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8);
+    } else {
+      using T = float;
+      attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv, T3, G3, F, G, psi);
+      M1_LAUNCH_CHECK(ctx);
+      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8);
+    }
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   if (dtype == M1_BF16) {
     using T = __nv_bfloat16;
     attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, batch,
@@ -334,6 +538,27 @@ extern "C" int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const
   const Grid3 T3 = g3(tg), G3 = g3(gg), X3 = g3(xg);
   const int64_t tv = (int64_t)batch * T3.d * T3.h * T3.w;
   const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
+  const int G = F / 8;
+  const bool vec = F % 8 == 0 && Cx == F && G >= 1 && G <= 32 && (G & (G - 1)) == 0;
+  if (vec) {
+    const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
+    const size_t sm = (F + 1) * sizeof(float);
+    if (dtype == M1_BF16) {
+      using T = __nv_bfloat16;
+      attn_bwd_psi_vec_kernel<T><<<pb, TB, sm, st>>>((const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi,
+                                                   (const T*)x, tv, T3, G3, X3, F, G, (T*)dtheta, dphi, dw_psi, db_psi);
+      M1_LAUNCH_CHECK(ctx);
+      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total / 8);
+    } else {
+      using T = float;
+      attn_bwd_psi_vec_kernel<T><<<pb, TB, sm, st>>>((const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi,
+                                                   (const T*)x, tv, T3, G3, X3, F, G, (T*)dtheta, dphi, dw_psi, db_psi);
+      M1_LAUNCH_CHECK(ctx);
+      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total / 8);
+    }
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   if (dtype == M1_BF16) {
     using T = __nv_bfloat16;
     attn_bwd_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(

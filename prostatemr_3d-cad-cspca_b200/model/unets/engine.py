@@ -211,11 +211,13 @@ class Engine:
                         label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)))
             first = False
 
-    def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None, pad_out=None):
+    def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None, pad_out=None, feeds_norm=False):
         """Conv3D (possibly several layers reading the same input fused along Cout) or
         Conv3DTranspose over the virtual concatenation of `srcs`.
         layers: [(param_prefix, cout)]; returns one Act per layer. pad_out[j]: zero-pad layer j's output
-        channels to the tensor-core granularity (the parameters keep their reference shape logically)."""
+        channels to the tensor-core granularity (the parameters keep their reference shape logically).
+        feeds_norm: the outputs go straight into an InstanceNorm; the bias gradient is then identically zero
+        (d/db of IN(conv + b) = 0: the norm removes the per-channel mean) and BiasAddGrad is not launched."""
         k, s = tuple(k), tuple(s)
         pad_out = pad_out or [False] * len(layers)
         lcin = sum(a.lc for a in srcs)
@@ -261,7 +263,8 @@ class Engine:
                      ws, wstr, bs, [o.t for o in outs], [co for _, co in layers], [False] * len(layers),
                      ("fwd",) + tuple(n for n, _ in layers))
         if self.record:
-            self._rec(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr),
+            self._rec(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr,
+                                             not feeds_norm),
                       [n + sfx for n, _ in layers for sfx in ("/kernel", "/bias")])
         return outs
 
@@ -310,7 +313,7 @@ class Engine:
         d.tune[0], d.tune[1], d.tune[2] = 0, 0, 0
         return best
 
-    def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr):
+    def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr, bias_grad=True):
         live = [j for j, o in enumerate(outs) if o.g is not None]
         if not live:
             return
@@ -329,7 +332,7 @@ class Engine:
                               out_dtype=_code(outs[live[0]].dtype), engine=auto)
             self._wgrad(d, [a.t for a in srcs], [outs[j].g for j in live],
                         [self.pg(layers[j][0] + "/kernel") for j in live],
-                        [self.pg(layers[j][0] + "/bias") for j in live],
+                        [self.pg(layers[j][0] + "/bias") for j in live] if bias_grad else None,
                         2 * batch * int(np.prod(out_dhw)) * taps * cin * sum(cos), layers[live[0]][0])
             # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j): ONE launch per layer j whose
             # produced channels are split over the gradients of the concatenated tensors
@@ -354,7 +357,8 @@ class Engine:
                 self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
                             layers[0][0] + "(T)")
                 off += a.c
-            ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
+            if bias_grad:
+                ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
             # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci] (strided FWD gather);
             # tensors with odd channel counts (latents) go to the CUDA cores, aligned ones to tcgen05
             if need:

@@ -27,11 +27,11 @@ class SEResNetBottleNeck:
             raise NotImplementedError("SEResNetBottleNeck with an identity residual (Cin == filters)")
         # the f/4 bottleneck tensors are zero-padded to 16 channels when f/4 is not a multiple of 16 (f = 32)
         raw1, raw4 = eng.conv(srcs, [(n + "/conv1", f // 4), (n + "/conv4", f)], self.kernel_size, self.strides,
-                              pad_out=[True, False])
+                              pad_out=[True, False], feeds_norm=True)
         a = eng.inorm_act(raw1, n + "/norm1", LRELU)
-        raw2, = eng.conv([a], [(n + "/conv2", f // 4)], (3, 3, 3), pad_out=[True])
+        raw2, = eng.conv([a], [(n + "/conv2", f // 4)], (3, 3, 3), pad_out=[True], feeds_norm=True)
         b = eng.inorm_act(raw2, n + "/norm2", LRELU)
-        raw3, = eng.conv([b], [(n + "/conv3", f)], (1, 1, 1))
+        raw3, = eng.conv([b], [(n + "/conv3", f)], (1, 1, 1), feeds_norm=True)
         return eng.se_tail(raw3, raw4, n, self.reduction, drop)
 
 
@@ -48,7 +48,7 @@ class GridAttentionBlock3D:
         theta, = eng.conv([conv_tensor], [(n + "/conv1", f)], self.sub_samp, self.sub_samp)
         phi, = eng.conv([gating_tensor], [(n + "/conv2", f)], (1, 1, 1))
         y = eng.attn_core(theta, phi, conv_tensor, n)
-        raw, = eng.conv([y], [(n + "/conv4", f)], (1, 1, 1))
+        raw, = eng.conv([y], [(n + "/conv4", f)], (1, 1, 1), feeds_norm=True)
         return eng.inorm_act(raw, n + "/norm4", 1.0)
 
 

@@ -85,7 +85,7 @@ class M1Core:
         need = lambda lvl: (not partial) or (3 - lvl) < last_lat  # noqa: E731 - is uconv{lvl}_ needed?
         out = {}
         # stem (R:networks.py:574-576)
-        raw, = eng.conv(inputs, [(n('conve0'), F[0])], K[0], S[0])
+        raw, = eng.conv(inputs, [(n('conve0'), F[0])], K[0], S[0], feeds_norm=True)
         x = eng.inorm_act(raw, n('norme0'), LRELU)
         # encoder (R:networks.py:579-582); the dropouts are fused into the SE gate kernel
         conv1 = self.serse[1](eng, [x], drop('drope1'))

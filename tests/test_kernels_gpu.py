@@ -121,12 +121,14 @@ def test_se_tail_fwd_bwd(ctx, C, red, rate):
         _close(G[k], R[k].grad, 2e-4, 'd' + k)
 
 
-@pytest.mark.parametrize("sub", [(1, 1, 1), (2, 2, 2)])
-def test_attention_gate_fwd_bwd(ctx, sub):
+@pytest.mark.parametrize("sub,F,xg,gg", [((1, 1, 1), 12, (4, 8, 8), (1, 2, 2)), ((2, 2, 2), 12, (4, 8, 8), (1, 2, 2)),
+                                         ((1, 1, 1), 16, (4, 8, 8), (1, 2, 2)), ((2, 2, 2), 16, (4, 8, 8), (1, 2, 2)),
+                                         ((1, 1, 1), 32, (4, 16, 16), (1, 1, 1)), ((1, 1, 1), 64, (4, 16, 32), (2, 2, 4)),
+                                         ((1, 1, 1), 256, (2, 4, 4), (1, 2, 2))])
+def test_attention_gate_fwd_bwd(ctx, sub, F, xg, gg):
     from m1b200 import ops
     g = _gen(3)
-    F, Cx = 12, 12
-    xg, gg = (4, 8, 8), (1, 2, 2)
+    Cx = F
     tg = tuple(a // s for a, s in zip(xg, sub))
     x = torch.randn((2, *xg, Cx), generator=g)
     theta = torch.randn((2, *tg, F), generator=g)
