@@ -59,6 +59,10 @@ typedef struct {
    * r = reduced (gathered) channel over the concatenation, n = produced channel of output j
    * (one weight tensor per output). */
   int64_t w_stride_tap[M1_MAX_OUT], w_stride_red[M1_MAX_OUT], w_stride_out[M1_MAX_OUT];
+  /* w_by_src = 1 (data gradient of several fused layers at once): one weight tensor per (produced j,
+   * gathered s) pair, w[j * nsrc + s]; the strides above are then indexed by the GATHERED tensor s and
+   * the reduced channel r restarts at 0 for every gathered tensor. */
+  int32_t w_by_src;
   int32_t accumulate;                 /* bit j set: outs[j] += result (gradient accumulation) */
   int32_t act_dtype;                  /* m1_dtype of the gathered tensors */
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */

@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
         ("nout", C.c_int32), ("out_c", C.c_int32 * M1_MAX_OUT),
         ("w_stride_tap", C.c_int64 * M1_MAX_OUT), ("w_stride_red", C.c_int64 * M1_MAX_OUT),
         ("w_stride_out", C.c_int64 * M1_MAX_OUT),
-        ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("w_by_src", C.c_int32), ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("engine", C.c_int32), ("tune", C.c_int32 * 4),
     ]
 

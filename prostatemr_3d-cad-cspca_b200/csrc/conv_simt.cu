@@ -29,7 +29,8 @@ struct SimtParams {
   int nout;
   void* out[M1_MAX_OUT];
   int out_c[M1_MAX_OUT];
-  const float* w[M1_MAX_OUT];
+  const float* w[M1_MAX_OUT * M1_MAX_SRC];   // [j] or, when w_by_src, [j * nsrc + s]
+  int w_by_src;
   const float* bias[M1_MAX_OUT];
   int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
   int accumulate;   // bitmask over outputs
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(TH) conv_simt_kernel(const __grid_constant__ S
           float x = 0.f;
           if (ch < C && n < p.n_total) {
             const int j = out_of(p, n);
-            x = p.w[j][tap * p.st[j] + (int64_t)(r_base + ch) * p.sr[j] + (int64_t)n * p.so[j]];
+            x = p.w_by_src ? p.w[j * p.nsrc + s][tap * p.st[s] + (int64_t)ch * p.sr[s] + (int64_t)n * p.so[s]]
+                           : p.w[j][tap * p.st[j] + (int64_t)(r_base + ch) * p.sr[j] + (int64_t)n * p.so[j]];
           }
           Ws[kk][nn] = x;
         }
@@ -202,7 +204,13 @@ __global__ void __launch_bounds__(128) conv_thin_kernel(const __grid_constant__ 
     float x = 0.f;
     if (n < p.n_total) {
       const int j = out_of(p, n);
-      x = p.w[j][tap * p.st[j] + (int64_t)r * p.sr[j] + (int64_t)n * p.so[j]];
+      if (p.w_by_src) {
+        int s = 0, rl = r;
+        while (s + 1 < p.nsrc && rl >= p.src_c[s]) { rl -= p.src_c[s]; ++s; }
+        x = p.w[j * p.nsrc + s][tap * p.st[s] + (int64_t)rl * p.sr[s] + (int64_t)n * p.so[s]];
+      } else {
+        x = p.w[j][tap * p.st[j] + (int64_t)r * p.sr[j] + (int64_t)n * p.so[j]];
+      }
     }
     wsm[e] = x;
   }
@@ -481,9 +489,13 @@ int fill_params(const m1_conv_desc* d, SimtParams* p) {
   for (int j = 0; j < d->nout; ++j) {
     p->out_start[j] = p->n_total;
     p->out_c[j] = d->out_c[j];
-    p->st[j] = d->w_stride_tap[j]; p->sr[j] = d->w_stride_red[j]; p->so[j] = d->w_stride_out[j];
     p->n_total += d->out_c[j];
   }
+  static_assert(M1_MAX_OUT == M1_MAX_SRC, "stride arrays are shared between the two indexings");
+  for (int j = 0; j < M1_MAX_OUT; ++j) {
+    p->st[j] = d->w_stride_tap[j]; p->sr[j] = d->w_stride_red[j]; p->so[j] = d->w_stride_out[j];
+  }
+  p->w_by_src = d->w_by_src;
   p->out_start[d->nout] = p->n_total;
   p->accumulate = d->accumulate;
   p->out_vox = (int64_t)d->batch * p->Do * p->Ho * p->Wo;
@@ -500,9 +512,10 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   for (int s = 0; s < d->nsrc; ++s) p.src[s] = srcs[s];
   for (int j = 0; j < d->nout; ++j) {
     p.out[j] = outs[j];
-    p.w[j] = w[j];
     p.bias[j] = bias ? bias[j] : nullptr;
   }
+  const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
+  for (int i = 0; i < nw; ++i) p.w[i] = w[i];
   const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
   int k_total = 0;
   for (int s = 0; s < d->nsrc; ++s) k_total += d->src_c[s];

@@ -253,17 +253,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
 // fp32 master weights -> bf16 [tap][n_total][k_total]; one weight tensor per produced tensor
 struct PackArgs {
-  const float* w[M1_MAX_OUT];
+  const float* w[M1_MAX_OUT * M1_MAX_SRC];
   int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
   int out_start[M1_MAX_OUT + 1];
-  int nout;
+  int src_start[M1_MAX_SRC + 1];
+  int nout, nsrc, w_by_src;
 };
-__global__ void pack_weights_kernel(PackArgs a, int n_real, int n_total, int k_total, int taps,
-                                    __nv_bfloat16* __restrict__ out) {
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, int n_real, int n_total, int k_total,
+                                    int taps, __nv_bfloat16* __restrict__ out) {
   const int64_t total = (int64_t)taps * n_total * k_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i % k_total);
+    int r = (int)(i % k_total);
     int n = (int)((i / k_total) % n_total);
     const int tap = (int)(i / ((int64_t)k_total * n_total));
     float v = 0.f;
@@ -271,7 +272,14 @@ __global__ void pack_weights_kernel(PackArgs a, int n_real, int n_total, int k_t
       int j = 0;
       while (j + 1 < a.nout && n >= a.out_start[j + 1]) ++j;
       n -= a.out_start[j];
-      v = a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
+      if (a.w_by_src) {
+        int s = 0;
+        while (s + 1 < a.nsrc && r >= a.src_start[s + 1]) ++s;
+        r -= a.src_start[s];
+        v = a.w[j * a.nsrc + s][tap * a.st[s] + r * a.sr[s] + n * a.so[s]];
+      } else {
+        v = a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
+      }
     }
     out[i] = __float2bfloat16_rn(v);
   }
@@ -400,14 +408,25 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   PackArgs a;
   memset(&a, 0, sizeof(a));
   a.nout = d->nout;
+  a.nsrc = d->nsrc;
+  a.w_by_src = d->w_by_src;
   int acc = 0;
   for (int j = 0; j < d->nout; ++j) {
-    a.w[j] = w[j];
-    a.st[j] = d->w_stride_tap[j]; a.sr[j] = d->w_stride_red[j]; a.so[j] = d->w_stride_out[j];
     a.out_start[j] = acc;
     acc += d->out_c[j];
   }
   a.out_start[d->nout] = acc;
+  acc = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    a.src_start[s] = acc;
+    acc += d->src_c[s];
+  }
+  a.src_start[d->nsrc] = acc;
+  for (int j = 0; j < M1_MAX_OUT; ++j) {
+    a.st[j] = d->w_stride_tap[j]; a.sr[j] = d->w_stride_red[j]; a.so[j] = d->w_stride_out[j];
+  }
+  const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
+  for (int i = 0; i < nw; ++i) a.w[i] = w[i];
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pl.n_real, pl.n_total, pl.k_total, taps,
                                                               reinterpret_cast<__nv_bfloat16*>(w_packed));
   M1_LAUNCH_CHECK(ctx);

@@ -36,6 +36,9 @@ struct WgParams {
   uint8_t blk_src[kMaxBlocks];   // M block -> gathered tensor
   uint16_t blk_c0[kMaxBlocks];   // M block -> first channel inside that tensor
   uint16_t blk_goff[kMaxBlocks]; // M block -> first channel over the virtual concatenation
+  uint8_t blk_tap[kMaxBlocks];   // taps-in-M mode: M block -> tap (layers with <= 64 gathered channels put
+                                 // 128/ck different TAPS of the single channel block into one M tile)
+  int taps_in_m;
   int nblocks;                   // total M blocks (ck channels each)
   int blocks_per_tile;           // 128 / ck
   int cin_total;
@@ -82,9 +85,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   const int mt = t % m_tiles; t /= m_tiles;
   const int group = t;
   const int groups_per_row = p.kw / p.tpg;
-  const int kw0 = (group % groups_per_row) * p.tpg;
-  const int kh_i = (group / groups_per_row) % p.kh;
-  const int kd_i = group / (groups_per_row * p.kh);
+  const int kw0 = p.taps_in_m ? 0 : (group % groups_per_row) * p.tpg;
+  const int kh_i = p.taps_in_m ? 0 : (group / groups_per_row) % p.kh;
+  const int kd_i = p.taps_in_m ? 0 : group / (groups_per_row * p.kh);
   const int blk0 = mt * p.blocks_per_tile;
   const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
   const int n0 = nt * p.n_tile;
@@ -131,9 +134,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
           for (int tp = 0; tp < p.tpg; ++tp)
             for (int j = 0; j < nblk; ++j) {
               const int blk = blk0 + j;
+              int a = kd_i, b = kh_i, c = kw0 + tp;
+              if (p.taps_in_m) {
+                const int tb = p.blk_tap[blk];
+                c = tb % p.kw; b = (tb / p.kw) % p.kh; a = tb / (p.kw * p.kh);
+              }
               tma_load_5d(sbase + tp * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]], full,
-                          (int)p.blk_c0[blk], w0 * p.sw + kw0 + tp - p.pw, h0 * p.sh + kh_i - p.ph,
-                          d0 * p.sd + kd_i - p.pd, n_img);
+                          (int)p.blk_c0[blk], w0 * p.sw + c - p.pw, h0 * p.sh + b - p.ph, d0 * p.sd + a - p.pd,
+                          n_img);
             }
           for (int j = 0; j < p.n_blocks; ++j) {
             const int nb = n0 / p.cb + j;
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     const int rglob = row_ok ? (int)p.blk_goff[rblk] + r % p.ck : 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int tp = 0; tp < p.tpg; ++tp) {
-      const int tap = (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
+      const int tap = (p.taps_in_m && row_ok) ? (int)p.blk_tap[rblk] : (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
       for (int j = 0; j < p.n_tile; j += 8) {
         uint32_t v[8];
         tmem_ld8(lane_addr + (uint32_t)(tp * p.n_tile + j), v);
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
 }
 
 struct WgPlan {
+  int taps_in_m;
   int ck, cb, n_tile, n_blocks, tpg, kv, bd, bh, bw, td, th, tw, stages, nblocks, cin_total;
   uint32_t a_blk_bytes, b_blk_bytes, a_tap_bytes, b_off, stage_bytes, smem_bytes, tmem_cols;
 };
@@ -242,6 +251,10 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
     if (!n_tile) return false;
   }
   int tpg = (d->kernel[2] * n_tile <= 512) ? d->kernel[2] : 1;
+  const int ntaps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+  // few gathered channels (one block per tap): fill the 128 M rows with 128/ck different taps
+  const bool taps_in_m = (cin == ck) && ck < 128 && ntaps > 1 && ntaps <= kMaxBlocks && d->tune[3] != 1;
+  if (taps_in_m) tpg = 1;
   // brick: voxels multiple of 16, <= kv_max, best volume coverage
   const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
   auto pick = [&](int kv_max, int* obd, int* obh, int* obw) {
@@ -283,7 +296,8 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
       pl->ck = ck; pl->cb = cb; pl->n_tile = n_tile; pl->n_blocks = n_tile / cb; pl->tpg = tp; pl->kv = kv;
       pl->bd = bd; pl->bh = bh; pl->bw = bw;
       pl->td = (D + bd - 1) / bd; pl->th = (H + bh - 1) / bh; pl->tw = (W + bw - 1) / bw;
-      pl->stages = stages; pl->nblocks = cin / ck; pl->cin_total = cin;
+      pl->stages = stages; pl->nblocks = taps_in_m ? ntaps : cin / ck; pl->cin_total = cin;
+      pl->taps_in_m = taps_in_m ? 1 : 0;
       pl->a_blk_bytes = a_blk; pl->b_blk_bytes = b_blk; pl->a_tap_bytes = a_tap; pl->b_off = b_off;
       pl->stage_bytes = stage; pl->smem_bytes = 2048u + (uint32_t)stages * stage;
       uint32_t cols = 32;
@@ -322,14 +336,24 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
     int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], d->in_dhw[2], d->in_dhw[1], d->in_dhw[0],
                          d->batch, pl.ck, pl.bw, pl.bh, pl.bd, d->stride[2], d->stride[1], d->stride[0]);
     M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad A %d) failed: %d", s, r);
-    for (int c0 = 0; c0 < d->src_c[s]; c0 += pl.ck) {
-      p.blk_src[blk] = (uint8_t)s;
-      p.blk_c0[blk] = (uint16_t)c0;
-      p.blk_goff[blk] = (uint16_t)(goff + c0);
-      ++blk;
+    if (!pl.taps_in_m) {
+      for (int c0 = 0; c0 < d->src_c[s]; c0 += pl.ck) {
+        p.blk_src[blk] = (uint8_t)s;
+        p.blk_c0[blk] = (uint16_t)c0;
+        p.blk_goff[blk] = (uint16_t)(goff + c0);
+        ++blk;
+      }
     }
     goff += d->src_c[s];
   }
+  if (pl.taps_in_m) {
+    // one channel block (of gathered tensor 0, channels [0, ck)) per tap
+    const int ntaps = d->kernel[0] * d->kernel[1] * d->kernel[2];
+    for (int t = 0; t < ntaps; ++t) {
+      p.blk_src[t] = 0; p.blk_c0[t] = 0; p.blk_goff[t] = 0; p.blk_tap[t] = (uint8_t)t;
+    }
+  }
+  p.taps_in_m = pl.taps_in_m;
   {
     int nb = 0, acc = 0;
     for (int o = 0; o < jn; ++o) {
@@ -379,7 +403,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.bricks_total = (int64_t)d->batch * pl.td * pl.th * pl.tw;
   const int m_tiles = (pl.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
   const int n_tiles = (p.co + pl.n_tile - 1) / pl.n_tile;
-  const int groups = p.kd * p.kh * (p.kw / pl.tpg);
+  const int groups = pl.taps_in_m ? 1 : p.kd * p.kh * (p.kw / pl.tpg);
   const int64_t base_ctas = (int64_t)groups * m_tiles * n_tiles;
   // split-K factor: ~2-4 CTAs per SM in total, chosen so that the last wave is as full as possible
   int64_t splits = 1;

@@ -169,7 +169,7 @@ class Engine:
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
     def _gather(self, cat, mode, batch, in_dhw, out_dhw, k, s, pad, src_t, src_c, ws, wstr, bias, out_t, out_c,
-                acc, key):
+                acc, key, w_by_src=False):
         """One convolution-shaped launch family: outs[j] (+)= gather(concat(src)) * ws[j] (+ bias[j]).
         The tcgen05 engine takes it when every gathered tensor has a multiple of 16 channels; a
         concatenation that mixes such tensors with odd ones (the 1-3 channel latents, R:networks.py:653)
@@ -178,7 +178,7 @@ class Engine:
         vox = batch * int(np.prod(in_dhw if mode == CONV_TRANSPOSED else out_dhw))
         act_code, out_code = _code(src_t[0].dtype), _code(out_t[0].dtype)
         runs = [(0, len(src_t))]
-        if self.use_tc and act_code == BF16 and out_code == BF16:
+        if self.use_tc and act_code == BF16 and out_code == BF16 and not w_by_src:
             ok = [c % 16 == 0 for c in src_c]
             if any(ok) and not all(ok):
                 runs, i = [], 0
@@ -191,11 +191,11 @@ class Engine:
         offs = np.cumsum([0] + list(src_c))
         first = True
         for (i0, i1) in runs:
-            sub_w = [w.view(-1)[int(offs[i0]) * st[1]:] for w, st in zip(ws, wstr)]
+            sub_w = list(ws) if w_by_src else [w.view(-1)[int(offs[i0]) * st[1]:] for w, st in zip(ws, wstr)]
             a_flags = list(acc) if first else [True] * len(out_t)
             d = ops.conv_desc(mode, batch, in_dhw, out_dhw, k, s, pad, list(src_c[i0:i1]), list(out_c), list(wstr),
                               accumulate=a_flags, act_dtype=act_code, out_dtype=out_code,
-                              engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT)
+                              engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT, w_by_src=w_by_src)
             packed = None
             if self.use_tc and ops.conv3d_tc_supported(d):
                 pk = key + (i0,)
@@ -338,13 +338,23 @@ class Engine:
             # produced channels are split over the gradients of the concatenated tensors
             if need:
                 offs = np.cumsum([0] + [a.c for a in srcs])[:-1]
-                for j in live:
-                    co = layers[j][1]
-                    bufs, accs = zip(*[self.grad_buffer(a) for a in srcs])
-                    wv = [ws[j].view(-1)[int(off) * co:] for off in offs]
-                    self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [outs[j].g], [co],
-                                 wv, [(cin * co, 1, co)] * len(srcs), None, list(bufs), [a.c for a in srcs],
-                                 list(accs), ("dgrad", layers[j][0]))
+                bufs, accs = zip(*[self.grad_buffer(a) for a in srcs])
+                cos = [layers[j][1] for j in live]
+                if len(live) > 1 and all(c % 16 == 0 for c in cos) and self.use_tc:
+                    # all fused layers in ONE launch: K runs over [dout_j ...] (per-(produced, gathered) weights)
+                    wv = [ws[j].view(-1)[int(off) * layers[j][1]:] for off in offs for j in live]
+                    self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad,
+                                 [outs[j].g for j in live], cos, wv, [(cin * c, 1, c) for c in cos], None,
+                                 list(bufs), [a.c for a in srcs], list(accs),
+                                 ("dgrad",) + tuple(layers[j][0] for j in live), w_by_src=True)
+                else:
+                    for i, j in enumerate(live):
+                        co = layers[j][1]
+                        wv = [ws[j].view(-1)[int(off) * co:] for off in offs]
+                        self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [outs[j].g],
+                                     [co], wv, [(cin * co, 1, co)] * len(srcs), None, list(bufs),
+                                     [a.c for a in srcs], list(accs) if i == 0 else [True] * len(srcs),
+                                     ("dgrad", layers[j][0]))
         else:
             co = layers[0][1]
             dy = outs[0].g

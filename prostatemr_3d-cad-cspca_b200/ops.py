@@ -21,8 +21,9 @@ def same_pads(size, k, s):
 
 
 def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w_strides,
-              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO, out_dtype=None):
+              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO, out_dtype=None, w_by_src=False):
     d = ConvDesc()
+    d.w_by_src = 1 if w_by_src else 0
     d.mode = mode
     d.batch = batch
     for i in range(3):
@@ -37,7 +38,8 @@ def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w
     d.nout = len(out_c)
     for j, c in enumerate(out_c):
         d.out_c[j] = c
-        d.w_stride_tap[j], d.w_stride_red[j], d.w_stride_out[j] = w_strides[j]
+    for j, st in enumerate(w_strides):        # per produced tensor, or per gathered tensor when w_by_src
+        d.w_stride_tap[j], d.w_stride_red[j], d.w_stride_out[j] = st
     if isinstance(accumulate, (list, tuple)):          # per-output flags -> bitmask
         d.accumulate = sum(1 << j for j, a in enumerate(accumulate) if a)
     else:

@@ -213,7 +213,10 @@ def test_conv_dgrad_tcgen05_multi_output(ctx, dhw, cins, cout, k):
                                              ((4, 16, 32), [32, 32, 32, 32, 32], 32, (1, 3, 3)),
                                              ((5, 10, 10), [256], 512, (3, 3, 3)),
                                              ((4, 16, 16), [16, 48], 16, (3, 3, 3)),
-                                             ((2, 8, 16), [64], 160, (1, 1, 1))])
+                                             ((2, 8, 16), [64], 160, (1, 1, 1)),
+                                             ((4, 16, 16), [16], 16, (3, 3, 3)),      # taps-in-M: 8 taps per M tile
+                                             ((4, 16, 16), [32], 64, (1, 3, 3)),      # taps-in-M: 4 taps per M tile
+                                             ((6, 12, 16), [16], 32, (1, 3, 3))])
 def test_conv_wgrad_tcgen05(ctx, dhw, cins, cout, k):
     """Weight gradient on the tensor cores (MN-major operands straight from NDHWC) vs autograd."""
     from m1b200 import ops, _lib
@@ -356,3 +359,37 @@ def test_conv_wgrad_tcgen05_fused_outputs(ctx):
         scale = max(1.0, w.grad.abs().max().item())
         assert (dw.double().cpu() - w.grad).abs().max().item() < 2e-3 * scale
         assert (db.double().cpu() - dy.sum(dim=(0, 1, 2, 3))).abs().max().item() < 1e-2 * scale
+
+
+@pytest.mark.parametrize("engine_name", ["tcgen05", "simt"])
+def test_conv_dgrad_k_fused(ctx, engine_name):
+    """Data gradient of the fused conv1||conv4 pair in ONE launch: K runs over [dy1 | dy4], one weight tensor
+    per (produced, gathered) pair (m1_conv_desc.w_by_src)."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(13)
+    dhw, cins, couts, k = (4, 16, 16), [64, 32], [16, 64], (3, 3, 3)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g, dtype=torch.float64, requires_grad=True) for c in cins]
+    ws = [(torch.randn((*k, cin, co), generator=g) / (cin * 27) ** 0.5).bfloat16().double() for co in couts]
+    x = torch.cat(xs, -1)
+    dys = []
+    for w in ws:
+        y = O.conv3d_same(x, w, None, (1, 1, 1))
+        dy = torch.randn(y.shape, generator=g).bfloat16().double()
+        y.backward(dy, retain_graph=True)
+        dys.append(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    wd = [w.float().to(dev).contiguous() for w in ws]
+    offs = [sum(cins[:i]) for i in range(len(cins))]
+    wv = [wd[j].view(-1)[o * couts[j]:] for o in offs for j in range(len(couts))]
+    eng = _lib.ENGINE_TCGEN05 if engine_name == "tcgen05" else _lib.ENGINE_SIMT
+    d = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, dhw, k, (1, 1, 1), pad, couts, cins,
+                      [(cin * co, 1, co) for co in couts], act_dtype=_lib.BF16, engine=eng, w_by_src=True)
+    packed = ops.conv3d_pack_weights(ctx, d, wv) if engine_name == "tcgen05" else None
+    bufs = [torch.full(x_.shape, float('nan'), device=dev, dtype=torch.bfloat16) for x_ in xs]
+    ops.conv3d(ctx, d, [t.to(dev, torch.bfloat16).contiguous() for t in dys], wv, None, bufs, packed)
+    torch.cuda.synchronize()
+    for x_, b in zip(xs, bufs):
+        err = (b.double().cpu() - x_.grad).abs().max().item()
+        assert err < 3e-2 * max(1.0, x_.grad.abs().max().item()), err
