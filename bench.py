@@ -276,6 +276,9 @@ def run_ours(args):
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -298,7 +301,8 @@ def run_ours(args):
     peak_src = "measured bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     breakdown = {k: {"launches": v[2] // args.steps, "ms_per_step": v[1] / args.steps,
                      "tflops": (v[0] / 1e12) / (v[1] / 1e3) if v[1] > 0 else None} for k, v in cats.items()}
-    dom = max(cats, key=lambda k: cats[k][1]) if cats else None
+    conv_cats = {k: v for k, v in cats.items() if k.startswith("conv_")}
+    dom = max(conv_cats, key=lambda k: conv_cats[k][1]) if conv_cats else None
     roofline = None
     if dom:
         fl, t_ms, n = cats[dom]

@@ -392,15 +392,18 @@ class Engine:
         if self.tracing:
             return y
         stats = self.new((x.shape[0], c, 2), torch.float32)
-        ops.inorm_stats(self.ctx, x.t, stats, IN_EPS)
-        ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t)
+        def fwd():
+            ops.inorm_stats(self.ctx, x.t, stats, IN_EPS)
+            ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t)
+        self._timed("inorm_fwd", 0, fwd)
 
         def bwd():
             if y.g is None:
                 return
             gbuf, acc = self.grad_buffer(x)
-            ops.inorm_act_bwd(self.ctx, y.g, x.t, stats, gamma, beta, slope, gbuf, acc,
-                              self.pg(name + "/gamma"), self.pg(name + "/beta"))
+            self._timed("inorm_bwd", 0, lambda: ops.inorm_act_bwd(
+                self.ctx, y.g, x.t, stats, gamma, beta, slope, gbuf, acc, self.pg(name + "/gamma"),
+                self.pg(name + "/beta")))
             y.g = None
         if self.record:
             self._rec(bwd, [name + "/gamma", name + "/beta"])
@@ -425,16 +428,19 @@ class Engine:
         n = raw3.shape[0]
         f32 = torch.float32
         st3, st4 = self.new((n, c, 2), f32), self.new((n, c, 2), f32)
-        ops.inorm_stats(self.ctx, raw3.t, st3, IN_EPS)
-        ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
         pool, hidden, gate = self.new((n, c), f32), self.new((n, cr), f32), self.new((n, c), f32)
-        ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
-        ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
         if drop is not None and drop[2] > 0.0:
             dr, keep_alive = self.noise.dropout(self, drop[0], drop[1], raw3.shape, drop[2])
         else:
             dr, keep_alive = ops.make_dropout(0.0), None
-        ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t)
+
+        def fwd():
+            ops.inorm_stats(self.ctx, raw3.t, st3, IN_EPS)
+            ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
+            ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
+            ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
+            ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t)
+        self._timed("se_tail_fwd", 0, fwd)
 
         def bwd():
             if out.g is None:
@@ -442,16 +448,21 @@ class Engine:
             _ = keep_alive
             red = self.new((n, c, 5), f32)
             dgate, dpool = self.new((n, c), f32), self.new((n, c), f32)
-            ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red, dgate)
-            ops.se_excite_bwd(self.ctx, dgate, pool, hidden, gate, w6, w7, dpool,
-                              self.pg(name + "/conv6/kernel"), self.pg(name + "/conv6/bias"),
-                              self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"))
             assert raw3.g is None and raw4.g is None
             raw3.g = self.new(raw3.shape, raw3.dtype)
             raw4.g = self.new(raw4.shape, raw4.dtype)
-            ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red, dpool,
-                                  raw3.g, raw4.g, self.pg(name + "/norm3/gamma"), self.pg(name + "/norm3/beta"),
-                                  self.pg(name + "/norm4/gamma"), self.pg(name + "/norm4/beta"))
+
+            def run():
+                ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
+                                       dgate)
+                ops.se_excite_bwd(self.ctx, dgate, pool, hidden, gate, w6, w7, dpool,
+                                  self.pg(name + "/conv6/kernel"), self.pg(name + "/conv6/bias"),
+                                  self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"))
+                ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
+                                      dpool, raw3.g, raw4.g, self.pg(name + "/norm3/gamma"),
+                                      self.pg(name + "/norm3/beta"), self.pg(name + "/norm4/gamma"),
+                                      self.pg(name + "/norm4/beta"))
+            self._timed("se_tail_bwd", 0, run)
             out.g = None
         if self.record:
             self._rec(bwd, [name + sfx for sfx in ("/norm3/gamma", "/norm3/beta", "/norm4/gamma", "/norm4/beta",
@@ -467,7 +478,7 @@ class Engine:
         if self.tracing:
             return y
         psi = self.new((theta.shape[0],) + theta.grid, torch.float32)
-        ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t)
+        self._timed("attn_fwd", 0, lambda: ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t))
 
         def bwd():
             if y.g is None:
@@ -479,8 +490,9 @@ class Engine:
                 gx, acc = self.grad_buffer(x)
             else:
                 gx, acc = self.new(x.shape, x.dtype), False
-            ops.attn_bwd(self.ctx, y.g, theta.t, phi.t, wpsi, psi, x.t, gx, acc, theta.g, dphi,
-                         self.pg(name + "/conv3/kernel"), self.pg(name + "/conv3/bias"))
+            self._timed("attn_bwd", 0, lambda: ops.attn_bwd(
+                self.ctx, y.g, theta.t, phi.t, wpsi, psi, x.t, gx, acc, theta.g, dphi,
+                self.pg(name + "/conv3/kernel"), self.pg(name + "/conv3/bias")))
             if phi.g is None:
                 phi.g = self.new(phi.shape, phi.dtype)
                 ops.cast(self.ctx, dphi, phi.g)

@@ -479,13 +479,15 @@ class M1(LoadableModel):
         scal = torch.zeros(4, dtype=torch.float32, device=self.device)   # focal, kl, l2, unused
         inv_r = 1.0 / self.world_size
         w_f, w_kl = self.loss_weights
-        for hi, (lg, up) in enumerate(heads):
-            gbuf, _ = eng.grad_buffer(lg, zero=True)
-            ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
-                              1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
-        for ml_q, ml_p in g['kl_pairs']:
-            eng.kl(ml_q, ml_p, scal[1:2])
-            eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
+        def losses():
+            for hi, (lg, up) in enumerate(heads):
+                gbuf, _ = eng.grad_buffer(lg, zero=True)
+                ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
+                                  1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
+            for ml_q, ml_p in g['kl_pairs']:
+                eng.kl(ml_q, ml_p, scal[1:2])
+                eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
+        eng._timed("losses", 0, losses)
         if self.grad_sync is not None:
             self.grad_sync.begin(self.params.g, eng.param_uses)
             eng.backward(self.grad_sync.param_done)
@@ -493,7 +495,7 @@ class M1(LoadableModel):
         else:
             eng.backward()
         if apply_update:
-            self._apply_update(scal[2:3], inv_r)
+            eng._timed("adam+repack", 0, lambda: self._apply_update(scal[2:3], inv_r))
         if isinstance(self.noise, PhiloxNoise):
             self.noise.step += 1
         return dict(detection=det, focal=scal[0:1], kl=scal[1:2], l2=scal[2:3])
