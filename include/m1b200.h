@@ -223,6 +223,17 @@ int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, const void* y_
                      float head_weight, float* loss_out, void* dlogits, float grad_scale,
                      void* stream);
 
+/* K8 fused with the final 1x1x1 logits convolution (StitchingProbDecoder / M1Core.logits,
+ * R:network_blocks.py:275-278, R:networks.py:526,627) and BOTH of its gradients: one pass reads the
+ * decoder features, writes softmax + d(features), accumulates loss, dW [C][nc] and db [nc].
+ * y_true == NULL: softmax only. Returns 2 (and sets the error) if (C, nc) has no instantiation - the
+ * caller then uses m1_conv3d + m1_softmax_focal. */
+int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype, const float* w, const float* bias,
+                            const void* y_true, int ydtype, const float* alpha, float gamma, int batch,
+                            int64_t voxels, int C, int nc, float* prob, int prob_c, int head_off,
+                            float head_weight, float* loss_out, void* dfeat, int acc_dfeat, float* dw,
+                            float* db, float grad_scale, void* stream);
+
 /* ---- K9: Keras Adam(amsgrad=True) + L2 regulariser gradient, train_model.py:113-120 ---------
  * g' = g*gscale + 2*l2*w ; m,v,vhat update; w -= lr_t * m / (sqrt(vhat) + eps)
  * l2_sq_out[0] += l2 * sum w^2 (regularisation loss term, R:networks.py:259-263) if non-NULL. */

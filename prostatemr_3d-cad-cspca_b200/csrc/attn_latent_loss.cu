@@ -477,6 +477,123 @@ __global__ void __launch_bounds__(TB) softmax_focal_kernel(const float* __restri
   if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, acc[0] * a.loss_scale);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K8 fused with the final logits convolution: thread per voxel, features row in registers
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename TY, int C, int NC>
+__global__ void __launch_bounds__(TB) logits_focal_kernel(const T* __restrict__ feat, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const TY* __restrict__ y,
+                                                         FocalArgs a, int64_t total, float* __restrict__ prob,
+                                                         float* __restrict__ loss_out, T* __restrict__ dfeat,
+                                                         int acc_dfeat, float* __restrict__ dw,
+                                                         float* __restrict__ db) {
+  __shared__ float sw[C * NC + NC];
+  __shared__ float sdw[C * NC + NC];
+  __shared__ float sm[TB / 32];
+  for (int i = threadIdx.x; i < C * NC + NC; i += TB) {
+    sw[i] = i < C * NC ? w[i] : bias[i - C * NC];
+    sdw[i] = 0.f;
+  }
+  __syncthreads();
+  float accw[C * NC + NC];
+#pragma unroll
+  for (int i = 0; i < C * NC + NC; ++i) accw[i] = 0.f;
+  float acc[1] = {0.f};
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      float t8[8];
+      load8<T>(feat + i * C + c, t8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[c + k] = t8[k];
+    }
+    float l[NC], p[NC], g[NC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      float s = sw[C * NC + n];
+#pragma unroll
+      for (int c = 0; c < C; ++c) s = fmaf(f[c], sw[c * NC + n], s);
+      l[n] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) { p[n] = expf(l[n] - mx); sum += p[n]; }
+    const float inv = 1.f / sum;
+    float psum = 0.f;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      p[n] *= inv;
+      psum += p[n];
+      if (prob) prob[i * a.prob_c + a.head_off + n] = p[n];
+    }
+    if (y == nullptr) continue;
+    float fl = 0.f, dot = 0.f;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      const float yt = ld_f<TY>(y + i * NC + n);
+      const float qn = p[n] / psum;
+      const float q = fminf(fmaxf(qn, 1e-7f), 1.f - 1e-7f);
+      const float om = 1.f - q;
+      const float pw = powf(om, a.gamma);
+      const float nl = -logf(q);
+      const float wgt = a.alpha[n] * yt * yt;
+      fl = fmaf(wgt * pw, nl, fl);
+      const float inside = (qn >= 1e-7f && qn <= 1.f - 1e-7f) ? 1.f : 0.f;
+      const float dpw = a.gamma == 0.f ? 0.f : a.gamma * powf(om, a.gamma - 1.f);
+      g[n] = wgt * inside * (-dpw * nl - pw / q);
+      dot = fmaf(p[n], g[n], dot);
+    }
+    acc[0] += fl;
+    if (dfeat == nullptr) continue;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      g[n] = a.grad_scale * p[n] * (g[n] - dot);          // dL/dlogit_n
+      accw[C * NC + n] += g[n];
+    }
+    float df[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+        s = fmaf(g[n], sw[c * NC + n], s);
+        accw[c * NC + n] = fmaf(f[c], g[n], accw[c * NC + n]);
+      }
+      df[c] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      float t8[8];
+      if (acc_dfeat) {
+        load8<T>(dfeat + i * C + c, t8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t8[k] += df[c + k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t8[k] = df[c + k];
+      }
+      store8<T>(dfeat + i * C + c, t8);
+    }
+  }
+  if (dw != nullptr) {
+#pragma unroll
+    for (int i = 0; i < C * NC + NC; ++i) {
+      const float v = warp_sum(accw[i]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[i], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * NC + NC; i += TB) {
+      if (i < C * NC) atomicAdd(dw + i, sdw[i]);
+      else atomicAdd(db + (i - C * NC), sdw[i]);
+    }
+  }
+  block_sum<1, TB>(acc, sm);
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, acc[0] * a.loss_scale);
+}
+
 inline unsigned nblocks(const m1_ctx* ctx, int64_t total, int per = TB) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(total, per), (int64_t)ctx->num_sms * 16));
 }
@@ -657,4 +774,45 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
                                                                     prob, loss_out, (float*)dlogits);
   M1_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+template <typename T, typename TY, int C, int NC>
+static void launch_logits_focal(m1_ctx* ctx, const void* feat, const float* w, const float* bias, const void* y,
+                                const FocalArgs& a, int64_t total, float* prob, float* loss_out, void* dfeat,
+                                int acc_dfeat, float* dw, float* db, cudaStream_t st) {
+  logits_focal_kernel<T, TY, C, NC><<<nblocks(ctx, total), TB, 0, st>>>(
+      (const T*)feat, w, bias, (const TY*)y, a, total, prob, loss_out, (T*)dfeat, acc_dfeat, dw, db);
+}
+
+extern "C" int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype, const float* w, const float* bias,
+                                       const void* y_true, int ydtype, const float* alpha, float gamma, int batch,
+                                       int64_t voxels, int C, int nc, float* prob, int prob_c, int head_off,
+                                       float head_weight, float* loss_out, void* dfeat, int acc_dfeat, float* dw,
+                                       float* db, float grad_scale, void* stream) {
+  FocalArgs a;
+  for (int c = 0; c < MAXC; ++c) a.alpha[c] = (alpha && c < nc) ? alpha[c] : 0.f;
+  a.gamma = gamma; a.nc = nc; a.batch = batch; a.prob_c = prob_c; a.head_off = head_off;
+  a.lg = Grid3{1, 1, 1}; a.up = Grid3{1, 1, 1};
+  a.from_probs = 0;
+  a.loss_scale = head_weight / (float)batch;
+  a.grad_scale = grad_scale * head_weight / (float)batch;
+  const int64_t total = (int64_t)batch * voxels;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fb = fdtype == M1_BF16, yb = ydtype == M1_BF16;
+#define M1_LF(CC, NN)                                                                                              \
+  if (C == CC && nc == NN) {                                                                                       \
+    if (fb && yb) launch_logits_focal<__nv_bfloat16, __nv_bfloat16, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st); \
+    else if (fb) launch_logits_focal<__nv_bfloat16, float, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);          \
+    else if (yb) launch_logits_focal<float, __nv_bfloat16, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);          \
+    else launch_logits_focal<float, float, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);                          \
+    M1_LAUNCH_CHECK(ctx);                                                                                          \
+    return 0;                                                                                                      \
+  }
+  M1_LF(32, 2)
+  M1_LF(8, 2)
+  M1_LF(16, 2)
+  M1_LF(32, 3)
+#undef M1_LF
+  m1_set_error("m1_logits_softmax_focal: no instantiation for C=%d nc=%d", C, nc);
+  return 2;
 }

@@ -4,7 +4,7 @@
 //   K5  squeeze (GAP), excite (conv6 -> lrelu -> conv7 -> sigmoid), gate * residual -> lrelu
 //       -> dropout, R:network_blocks.py:68-78 + R:network_blocks.py:137-143 (tf.nn.dropout)
 // All tensors are [batch][voxels][C] (NDHWC flattened); statistics/parameters are fp32.
-// Vectorised 4 channels per thread (16 B fp32 / 8 B bf16 accesses), per-(sample,channel)
+// Vectorised 8 channels per thread (16-byte bf16 / 2 x 16-byte fp32 accesses), per-(sample,channel)
 // reductions go warp-shuffle-free through shared-memory accumulators and one global atomic per
 // (block, channel).
 #include "common.cuh"
@@ -14,32 +14,71 @@ namespace {
 
 constexpr int TB = 256;
 
-// ---- generic loaders: VW = 4 (vector) or 1 (scalar fallback for odd channel counts) ----------
+// ---- generic loaders: VW = 8 / 4 channels per thread (16-byte bf16 / 2x16-byte fp32 accesses) or 1
+// (scalar fallback for odd channel counts); value arrays always have 8 slots --------------------
 template <typename T, int VW>
-__device__ __forceinline__ void ldv(const T* p, float (&v)[4]) {
-  if constexpr (VW == 4) Vec4<T>::load(p, v);
-  else { v[0] = ld_f<T>(p); v[1] = v[2] = v[3] = 0.f; }
+__device__ __forceinline__ void ldv(const T* p, float (&v)[8]) {
+  if constexpr (VW == 8) {
+    if constexpr (sizeof(T) == 2) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  } else if constexpr (VW == 4) {
+    float t[4];
+    Vec4<T>::load(p, t);
+    v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; v[3] = t[3];
+  } else {
+    v[0] = ld_f<T>(p);
+  }
 }
 template <typename T, int VW>
-__device__ __forceinline__ void stv(T* p, const float (&v)[4]) {
-  if constexpr (VW == 4) Vec4<T>::store(p, v);
-  else st_f<T>(p, v[0]);
+__device__ __forceinline__ void stv(T* p, const float (&v)[8]) {
+  if constexpr (VW == 8) {
+    if constexpr (sizeof(T) == 2) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      *reinterpret_cast<uint4*>(p) = u;
+    } else {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else if constexpr (VW == 4) {
+    const float t[4] = {v[0], v[1], v[2], v[3]};
+    Vec4<T>::store(p, t);
+  } else {
+    st_f<T>(p, v[0]);
+  }
 }
 template <int VW>
-__device__ __forceinline__ void ldp(const float* p, float (&v)[4]) {  // parameter vectors
-  if constexpr (VW == 4) { const float4 t = *reinterpret_cast<const float4*>(p); v[0]=t.x; v[1]=t.y; v[2]=t.z; v[3]=t.w; }
-  else { v[0] = *p; v[1] = v[2] = v[3] = 0.f; }
+__device__ __forceinline__ void ldp(const float* p, float (&v)[8]) {  // parameter vectors
+  if constexpr (VW >= 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if constexpr (VW == 8) {
+      const float4 u = *reinterpret_cast<const float4*>(p + 4);
+      v[4] = u.x; v[5] = u.y; v[6] = u.z; v[7] = u.w;
+    }
+  } else {
+    v[0] = *p;
+  }
 }
 // stats are [n][C][2] interleaved (mean, rstd)
 template <int VW>
-__device__ __forceinline__ void ld_stats(const float* st, float (&mean)[4], float (&rstd)[4]) {
+__device__ __forceinline__ void ld_stats(const float* st, float (&mean)[8], float (&rstd)[8]) {
 #pragma unroll
   for (int i = 0; i < VW; ++i) { mean[i] = st[2 * i]; rstd[i] = st[2 * i + 1]; }
 }
 
 // Row-parallel per-(sample, channel) reduction skeleton.
 // grid = (slabs, batch); thread -> channel group cg (VW channels) and row lane; each thread walks
-// rows [slab*rows_per_slab, ...) with stride `lanes`.  F(row_offset, cbase, acc[K][4]) adds.
+// rows [slab*rows_per_slab, ...) with stride `lanes`.  F(row_offset, cbase, acc[K][8]) adds.
 template <int K, int VW, typename F>
 __device__ __forceinline__ void reduce_rows(int64_t voxels, int C, int64_t rows_per_slab, float* smem,
                                             float* gout /* [C][K] of this sample */, float scale, F f) {
@@ -53,11 +92,11 @@ __device__ __forceinline__ void reduce_rows(int64_t voxels, int C, int64_t rows_
   const int64_t r1 = min(r0 + rows_per_slab, voxels);
   if (my_lane < lanes) {
     for (int cg = threadIdx.x % cgs; cg < CG; cg += cgs) {
-      float acc[K][4];
+      float acc[K][8];
 #pragma unroll
       for (int k = 0; k < K; ++k)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
       const int cbase = cg * VW;
       for (int64_t r = r0 + my_lane; r < r1; r += lanes) f(r, cbase, acc);
 #pragma unroll
@@ -83,8 +122,8 @@ __global__ void __launch_bounds__(TB) inorm_sums_kernel(const T* __restrict__ x,
   const int n = blockIdx.y;
   const T* xb = x + (int64_t)n * voxels * C;
   reduce_rows<2, VW>(voxels, C, rows_per_slab, smem, sums + (int64_t)n * C * 2, 1.f,
-                     [&](int64_t r, int cbase, float (&acc)[2][4]) {
-                       float v[4];
+                     [&](int64_t r, int cbase, float (&acc)[2][8]) {
+                       float v[8];
                        ldv<T, VW>(xb + r * C + cbase, v);
 #pragma unroll
                        for (int i = 0; i < VW; ++i) { acc[0][i] += v[i]; acc[1][i] = fmaf(v[i], v[i], acc[1][i]); }
@@ -110,7 +149,7 @@ __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__
   for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * TB) {
     const int cbase = (int)(i % CG) * VW;
     const int n = (int)(i / ((int64_t)CG * voxels));
-    float v[4], mean[4], rstd[4], g[4], b[4];
+    float v[8], mean[8], rstd[8], g[8], b[8];
     ldv<T, VW>(x + i * VW, v);
     ld_stats<VW>(stats + ((int64_t)n * C + cbase) * 2, mean, rstd);
     ldp<VW>(gamma + cbase, g);
@@ -137,8 +176,8 @@ __global__ void __launch_bounds__(TB) inorm_bwd_reduce_kernel(const T* __restric
   const T* db = dy + (int64_t)n * voxels * C;
   const float* st = stats + (int64_t)n * C * 2;
   reduce_rows<2, VW>(voxels, C, rows_per_slab, smem, red + (int64_t)n * C * 2, 1.f,
-                     [&](int64_t r, int cbase, float (&acc)[2][4]) {
-                       float v[4], d[4], mean[4], rstd[4], g[4], b[4];
+                     [&](int64_t r, int cbase, float (&acc)[2][8]) {
+                       float v[8], d[8], mean[8], rstd[8], g[8], b[8];
                        ldv<T, VW>(xb + r * C + cbase, v);
                        ldv<T, VW>(db + r * C + cbase, d);
                        ld_stats<VW>(st + cbase * 2, mean, rstd);
@@ -166,7 +205,7 @@ __global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const T* __restrict
   for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * TB) {
     const int cbase = (int)(i % CG) * VW;
     const int n = (int)(i / ((int64_t)CG * voxels));
-    float v[4], d[4], mean[4], rstd[4], g[4], b[4], o[4];
+    float v[8], d[8], mean[8], rstd[8], g[8], b[8], o[8];
     ldv<T, VW>(x + i * VW, v);
     ldv<T, VW>(dy + i * VW, d);
     ld_stats<VW>(stats + ((int64_t)n * C + cbase) * 2, mean, rstd);
@@ -215,8 +254,8 @@ __global__ void __launch_bounds__(TB) se_squeeze_kernel(const T* __restrict__ ra
   const T* xb = raw3 + (int64_t)n * voxels * C;
   const float* st = stats3 + (int64_t)n * C * 2;
   reduce_rows<1, VW>(voxels, C, rows_per_slab, smem, pool + (int64_t)n * C, inv_v,
-                     [&](int64_t r, int cbase, float (&acc)[1][4]) {
-                       float v[4], mean[4], rstd[4], g[4], b[4];
+                     [&](int64_t r, int cbase, float (&acc)[1][8]) {
+                       float v[8], mean[8], rstd[8], g[8], b[8];
                        ldv<T, VW>(xb + r * C + cbase, v);
                        ld_stats<VW>(st + cbase * 2, mean, rstd);
                        ldp<VW>(gamma3 + cbase, g);
@@ -302,19 +341,30 @@ struct DropArgs {
 
 // keep-mask * scale for the VW elements starting at flat element index e (e % VW == 0)
 template <int VW>
-__device__ __forceinline__ void drop_factors(const DropArgs& dr, int64_t e, float (&f)[4]) {
-  if (dr.rate <= 0.f) { f[0] = f[1] = f[2] = f[3] = 1.f; return; }
-  float u[4];
+__device__ __forceinline__ void drop_factors(const DropArgs& dr, int64_t e, float (&f)[8]) {
+  if (dr.rate <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 1.f;
+    return;
+  }
+  float u[8];
   if (dr.u != nullptr) {
     ldp<VW>(dr.u + e, u);
   } else {
     float q[4];
     philox_uniform4(dr.seed, dr.stream_id, (uint64_t)(e >> 2), q);
-    if constexpr (VW == 4) { u[0] = q[0]; u[1] = q[1]; u[2] = q[2]; u[3] = q[3]; }
-    else { u[0] = q[e & 3]; u[1] = u[2] = u[3] = 0.f; }
+    if constexpr (VW >= 4) {
+      u[0] = q[0]; u[1] = q[1]; u[2] = q[2]; u[3] = q[3];
+      if constexpr (VW == 8) {
+        philox_uniform4(dr.seed, dr.stream_id, (uint64_t)(e >> 2) + 1, q);
+        u[4] = q[0]; u[5] = q[1]; u[6] = q[2]; u[7] = q[3];
+      }
+    } else {
+      u[0] = q[e & 3];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) f[i] = u[i] >= dr.rate ? dr.scale : 0.f;
+  for (int i = 0; i < VW; ++i) f[i] = u[i] >= dr.rate ? dr.scale : 0.f;
 }
 
 struct GateArgs {
@@ -330,7 +380,7 @@ __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ r
     const int cbase = (int)(i % CG) * VW;
     const int n = (int)(i / ((int64_t)CG * voxels));
     const int64_t nc = (int64_t)n * C + cbase;
-    float x3[4], x4[4], m3[4], r3[4], m4[4], r4[4], g3[4], b3[4], g4[4], b4[4], gt[4], f[4], o[4];
+    float x3[8], x4[8], m3[8], r3[8], m4[8], r4[8], g3[8], b3[8], g4[8], b4[8], gt[8], f[8], o[8];
     ldv<T, VW>(raw3 + i * VW, x3);
     ldv<T, VW>(raw4 + i * VW, x4);
     ld_stats<VW>(a.stats3 + nc * 2, m3, r3);
@@ -359,10 +409,10 @@ __global__ void __launch_bounds__(TB) se_gate_bwd_reduce_kernel(const T* __restr
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
   reduce_rows<5, VW>(voxels, C, rows_per_slab, smem, red5 + (int64_t)n * C * 5, 1.f,
-                     [&](int64_t r, int cbase, float (&acc)[5][4]) {
+                     [&](int64_t r, int cbase, float (&acc)[5][8]) {
                        const int64_t e = base + r * C + cbase;
                        const int64_t nc = (int64_t)n * C + cbase;
-                       float x3[4], x4[4], d[4], m3[4], r3[4], m4[4], r4[4], g3[4], b3[4], g4[4], b4[4], gt[4], f[4];
+                       float x3[8], x4[8], d[8], m3[8], r3[8], m4[8], r4[8], g3[8], b3[8], g4[8], b4[8], gt[8], f[8];
                        ldv<T, VW>(raw3 + e, x3);
                        ldv<T, VW>(raw4 + e, x4);
                        ldv<T, VW>(dout + e, d);
@@ -404,7 +454,7 @@ __global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const T* __restri
     const int cbase = (int)(i % CG) * VW;
     const int n = (int)(i / ((int64_t)CG * voxels));
     const int64_t nc = (int64_t)n * C + cbase;
-    float x3[4], x4[4], d[4], m3[4], r3[4], m4[4], r4[4], g3[4], b3[4], g4[4], b4[4], gt[4], f[4], o3[4], o4[4];
+    float x3[8], x4[8], d[8], m3[8], r3[8], m4[8], r4[8], g3[8], b3[8], g4[8], b4[8], gt[8], f[8], o3[8], o4[8];
     ldv<T, VW>(raw3 + i * VW, x3);
     ldv<T, VW>(raw4 + i * VW, x4);
     ldv<T, VW>(dout + i * VW, d);
@@ -441,16 +491,35 @@ inline unsigned ew_blocks(const m1_ctx* ctx, int64_t total_vec) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(total_vec, TB), (int64_t)ctx->num_sms * 16));
 }
 
+#define DISPATCH_VW_(C, ...)                                             \
+  do {                                                                   \
+    if ((C) % 8 == 0) { constexpr int VW = 8; __VA_ARGS__; }             \
+    else if ((C) % 4 == 0) { constexpr int VW = 4; __VA_ARGS__; }        \
+    else { constexpr int VW = 1; __VA_ARGS__; }                          \
+  } while (0)
+#define DISPATCH_VW4_(C, ...)                                            \
+  do {                                                                   \
+    if ((C) % 4 == 0) { constexpr int VW = 4; __VA_ARGS__; }             \
+    else { constexpr int VW = 1; __VA_ARGS__; }                          \
+  } while (0)
+#define DISPATCH_T_VW4(dtype, C, ...)                                    \
+  do {                                                                   \
+    if ((dtype) == M1_BF16) {                                            \
+      using T = __nv_bfloat16;                                           \
+      DISPATCH_VW4_(C, __VA_ARGS__);                                     \
+    } else {                                                             \
+      using T = float;                                                   \
+      DISPATCH_VW4_(C, __VA_ARGS__);                                     \
+    }                                                                    \
+  } while (0)
 #define DISPATCH_T_VW(dtype, C, ...)                                     \
   do {                                                                   \
     if ((dtype) == M1_BF16) {                                            \
       using T = __nv_bfloat16;                                           \
-      if ((C) % 4 == 0) { constexpr int VW = 4; __VA_ARGS__; }           \
-      else { constexpr int VW = 1; __VA_ARGS__; }                        \
+      DISPATCH_VW_(C, __VA_ARGS__);                                      \
     } else {                                                             \
       using T = float;                                                   \
-      if ((C) % 4 == 0) { constexpr int VW = 4; __VA_ARGS__; }           \
-      else { constexpr int VW = 1; __VA_ARGS__; }                        \
+      DISPATCH_VW_(C, __VA_ARGS__);                                      \
     }                                                                    \
   } while (0)
 
@@ -472,7 +541,7 @@ extern "C" int m1_inorm_stats(m1_ctx* ctx, const void* x, int dtype, int batch, 
   M1_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * C * 2 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (inorm_sums_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
+  DISPATCH_T_VW4(dtype, C, (inorm_sums_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
                               reinterpret_cast<const T*>(x), voxels, C, rows, stats)));
   M1_LAUNCH_CHECK(ctx);
   const int total = batch * C;
@@ -504,7 +573,7 @@ extern "C" int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, cons
   M1_CUDA(cudaMemsetAsync(red, 0, (size_t)batch * C * 2 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (inorm_bwd_reduce_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
+  DISPATCH_T_VW4(dtype, C, (inorm_bwd_reduce_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
                               reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta,
                               voxels, C, slope, rows, red)));
   M1_LAUNCH_CHECK(ctx);
@@ -529,7 +598,7 @@ extern "C" int m1_se_squeeze(m1_ctx* ctx, const void* raw3, const float* stats3,
   M1_CUDA(cudaMemsetAsync(pool, 0, (size_t)batch * C * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (se_squeeze_kernel<T, VW><<<grid, TB, C * sizeof(float), st>>>(
+  DISPATCH_T_VW4(dtype, C, (se_squeeze_kernel<T, VW><<<grid, TB, C * sizeof(float), st>>>(
                               reinterpret_cast<const T*>(raw3), stats3, gamma3, beta3, voxels, C, rows,
                               1.f / (float)voxels, pool)));
   M1_LAUNCH_CHECK(ctx);
@@ -581,7 +650,7 @@ extern "C" int m1_se_gate_bwd_reduce(m1_ctx* ctx, const void* dout, const void* 
   M1_CUDA(cudaMemsetAsync(red, 0, (size_t)batch * C * 5 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (se_gate_bwd_reduce_kernel<T, VW><<<grid, TB, 5 * C * sizeof(float), st>>>(
+  DISPATCH_T_VW4(dtype, C, (se_gate_bwd_reduce_kernel<T, VW><<<grid, TB, 5 * C * sizeof(float), st>>>(
                               reinterpret_cast<const T*>(dout), reinterpret_cast<const T*>(raw3),
                               reinterpret_cast<const T*>(raw4), a, dr, voxels, C, rows, red)));
   M1_LAUNCH_CHECK(ctx);

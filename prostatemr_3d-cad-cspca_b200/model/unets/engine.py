@@ -90,6 +90,22 @@ class PhiloxNoise:
         return out
 
 
+class LazyHead:
+    """A final 1x1x1 logits convolution that has not been launched yet: the loss kernel fuses it (K8 reads
+    the decoder features directly and emits d(features), dW, db); `materialize` is the unfused fallback."""
+
+    def __init__(self, eng, feat, name, nc):
+        self.feat, self.name, self.nc = feat, name, nc
+        self.w = eng.p(name + "/kernel", (1, 1, 1, feat.lc, nc), "kernel", (1, 1, 1, feat.c, nc),
+                       {3: np.arange(feat.lc)})
+        self.b = eng.p(name + "/bias", (nc,), "bias")
+        self.shape = feat.shape[:-1] + (nc,)
+
+    def materialize(self, eng):
+        out, = eng.conv([self.feat], [(self.name, self.nc)], (1, 1, 1), out_dtype=torch.float32)
+        return out
+
+
 class Engine:
     def __init__(self, params, precision="bf16", device=None, use_tcgen05=True):
         assert precision in ("bf16", "fp32")

@@ -70,7 +70,5 @@ class StitchingProbDecoder:
         self.num_classes, self.name = num_classes, name
 
     def __call__(self, eng, decoder_features):
-        import torch
-        out, = eng.conv([decoder_features], [(self.name + "/logits", self.num_classes)], (1, 1, 1),
-                        out_dtype=torch.float32)
-        return out
+        from .engine import LazyHead
+        return LazyHead(eng, decoder_features, self.name + "/logits", self.num_classes)

@@ -18,7 +18,7 @@ from ... import ops
 from .. import initializers, regularizers
 from ..losses import EvidenceLowerBound, Focal
 from ..optimizers import Adam
-from .engine import LRELU, Act, Engine, InjectedNoise, PhiloxNoise
+from .engine import LRELU, Act, Engine, InjectedNoise, LazyHead, PhiloxNoise
 from .modelio import LoadableModel, store_config_args
 from .network_blocks import GridAttentionBlock3D, SEResNetBottleNeck, StitchingProbDecoder
 from .params import ParamTable
@@ -137,8 +137,7 @@ class M1Core:
                 uconv_[0] = [deconv0, att[0]]
         if not partial and need_logits:
             uconv[0] = self.sersd[0](eng, uconv_[0], drop('dropd0', rate / 2))      # R:networks.py:523
-            out['logits'], = eng.conv([uconv[0]], [(n('logits'), self.num_classes)], (1, 1, 1),
-                                      out_dtype=torch.float32)
+            out['logits'] = LazyHead(eng, uconv[0], n('logits'), self.num_classes)
         self.shapes = dict(inputs=[a.shape for a in inputs], x=x.shape, conv1=conv1.shape, conv2=conv2.shape,
                            conv3=conv3.shape, convm=convm.shape,
                            att=[None if a is None else a.shape for a in att],
@@ -481,6 +480,17 @@ class M1(LoadableModel):
         w_f, w_kl = self.loss_weights
         def losses():
             for hi, (lg, up) in enumerate(heads):
+                if isinstance(lg, LazyHead):
+                    fresh = lg.feat.g is None
+                    gbuf, acc = eng.grad_buffer(lg.feat)
+                    if lg.feat.c == lg.feat.lc and ops.logits_softmax_focal(
+                            eng.ctx, lg.feat.t, lg.w, lg.b, y, self.focal.alpha, float(self.focal.gamma), det,
+                            nc * hi, 1.0 / len(heads), scal[0:1], gbuf, acc, eng.pg(lg.name + "/kernel"),
+                            eng.pg(lg.name + "/bias"), w_f * inv_r):
+                        continue
+                    if fresh:
+                        lg.feat.g = None
+                    lg = lg.materialize(eng)
                 gbuf, _ = eng.grad_buffer(lg, zero=True)
                 ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
                                   1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
@@ -575,10 +585,20 @@ class M1(LoadableModel):
                           device=self.device)
         kl = torch.zeros(1, dtype=torch.float32, device=self.device)
         for hi, (lg, up) in enumerate(g['heads']):
-            ops.softmax_focal(eng.ctx, lg.t, None, None, 0.0, up, det, nc * hi, 0.0, None, None, 0.0)
+            self._softmax_head(eng, lg, up, det, nc * hi)
         for ml_q, ml_p in g['kl_pairs']:
             eng.kl(ml_q, ml_p, kl)
         return [det, kl]
+
+    def _softmax_head(self, eng, lg, up, out, off):
+        """softmax of one head into out[..., off:off+nc] (inference: no labels, no gradients)"""
+        if isinstance(lg, LazyHead):
+            if lg.feat.c == lg.feat.lc and ops.logits_softmax_focal(
+                    eng.ctx, lg.feat.t, lg.w, lg.b, None, None, 0.0, out, off, 0.0, None, None, False, None, None,
+                    0.0):
+                return
+            lg = lg.materialize(eng)
+        ops.softmax_focal(eng.ctx, lg.t, None, None, 0.0, up, out, off, 0.0, None, None, 0.0)
 
     def get_detect_model(self):
         """R:networks.py:196-206: model reconfigured to predict segment probabilities only."""
@@ -634,7 +654,7 @@ class DetectModel:
         lg = m._infer_graph(eng, B, x=x, pass_name=pass_name)
         nc = m.num_classes
         out = torch.empty((B,) + m.input_spatial_dims + (nc,), dtype=torch.float32, device=m.device)
-        ops.softmax_focal(eng.ctx, lg.t, None, None, 0.0, (1, 1, 1), out, 0, 0.0, None, None, 0.0)
+        m._softmax_head(eng, lg, (1, 1, 1), out, 0)
         if isinstance(m.noise, PhiloxNoise):
             m.noise.step += 1
         return out

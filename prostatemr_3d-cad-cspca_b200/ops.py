@@ -254,3 +254,20 @@ def bias_grad(ctx, dout, dbias):
 
 def philox_normal(ctx, seed, stream_id, out):
     check(lib().m1_philox_normal(ctx.handle, seed, stream_id, ptr(out), out.numel(), current_stream()))
+
+
+def logits_softmax_focal(ctx, feat, w, bias, y_true, alpha, gamma, prob, head_off, head_weight, loss_out, dfeat,
+                         acc_dfeat, dw, db, grad_scale):
+    """Returns False when (C, nc) has no fused instantiation (caller falls back to conv3d + softmax_focal)."""
+    n, v, c = _nvc(feat)
+    nc = w.shape[-1]
+    al = (C.c_float * nc)(*[float(a) for a in alpha]) if alpha is not None else None
+    rc = lib().m1_logits_softmax_focal(
+        ctx.handle, ptr(feat), dtype_code(feat), ptr(w), ptr(bias), ptr(y_true),
+        dtype_code(y_true) if y_true is not None else F32, C.cast(al, C.c_void_p) if al is not None else None,
+        gamma, n, v, c, nc, ptr(prob), prob.shape[-1] if prob is not None else 0, head_off, head_weight,
+        ptr(loss_out), ptr(dfeat), 1 if acc_dfeat else 0, ptr(dw), ptr(db), grad_scale, current_stream())
+    if rc == 2:
+        return False
+    check(rc)
+    return True
