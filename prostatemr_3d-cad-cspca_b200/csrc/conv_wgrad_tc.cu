@@ -61,6 +61,7 @@ struct WgParams {
   uint32_t a_desc_hi, b_desc_hi;
   uint32_t a_lbo, b_lbo;         // >> 4
   int splits;
+  int dbg_noload;                // experiment: producer arrives without loading (MMA-issue-rate probe)
   int64_t bricks_total;
   float* dw[M1_MAX_OUT];
   int64_t st[M1_MAX_OUT], sr[M1_MAX_OUT], so[M1_MAX_OUT];
@@ -129,6 +130,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
           const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8u * stage;
+          if (p.dbg_noload) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(full, (uint32_t)(p.tpg * nblk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes);
           const uint32_t sbase = tiles + stage * p.stage_bytes;
           for (int tp = 0; tp < p.tpg; ++tp)
@@ -419,6 +425,8 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
     }
   }
   p.splits = (int)splits;
+  static const int g_noload = getenv("M1_WG_NOLOAD") ? atoi(getenv("M1_WG_NOLOAD")) : 0;
+  p.dbg_noload = g_noload;
 
   static int smem_set = 0;
   if (!smem_set) {

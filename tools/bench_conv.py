@@ -16,6 +16,9 @@ B = 8
 SHAPES = {
     # name: (dhw, src channels, out channels, kernel, stride, transposed)
     'sersp2': ((20, 40, 40), [128, 128, 128, 128], [32, 128], (3, 3, 3), (1, 1, 1), False),
+    'x_n128': ((20, 40, 40), [128, 128, 128, 128], [128], (3, 3, 3), (1, 1, 1), False),
+    'x_n192': ((20, 40, 40), [128, 128, 128, 128], [64, 128], (3, 3, 3), (1, 1, 1), False),
+    'x_n256': ((20, 40, 40), [128, 128, 128, 128], [256], (3, 3, 3), (1, 1, 1), False),
     'sersd2': ((20, 40, 40), [128, 128, 128], [32, 128], (3, 3, 3), (1, 1, 1), False),
     'sersp3': ((10, 20, 20), [256, 256, 256], [64, 256], (3, 3, 3), (1, 1, 1), False),
     'sersp1': ((20, 80, 80), [64] * 5, [16, 64], (1, 3, 3), (1, 1, 1), False),
