@@ -69,7 +69,7 @@ typedef struct {
   int32_t engine;                     /* m1_engine */
   /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
    * wgrad: tune[0] = max voxels per K brick (16..128), tune[1] = taps sharing one dY tile (1 or kw),
-   *        tune[2] = pipeline stage cap;  conv: tune[0] = stage cap, tune[1] = k-steps per stage */
+   *        tune[2] = pipeline stage cap, tune[3] = 128-row M tiles per CTA (they share the dY tile) */
   int32_t tune[4];
 } m1_conv_desc;
 

@@ -45,6 +45,7 @@ struct WgParams {
   int kd, kh, kw, pd, ph, pw;
   int sd, sh, sw;                // FWD stride: A boxes are loaded with TMA element strides
   int tpg;                       // taps per group (1 or kw)
+  int mpg;                       // M tiles (of 128 rows) per CTA: they share the dY tile of a stage
   int bd, bh, bw, td, th, tw;    // brick, bricks per dim
   int batch;
   int kv;                        // voxels per brick (multiple of 16)
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- work decomposition: blockIdx.x = ((group * m_tiles + m_tile) * n_tiles + n_tile), blockIdx.y = split
-  const int m_tiles = (p.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  const int m_sub = (p.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;   // 128-row tiles in total
+  const int m_tiles = (m_sub + p.mpg - 1) / p.mpg;
   const int n_tiles = (p.co + p.n_tile - 1) / p.n_tile;
   int t = blockIdx.x;
   const int nt = t % n_tiles; t /= n_tiles;
@@ -89,9 +91,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   const int kw0 = p.taps_in_m ? 0 : (group % groups_per_row) * p.tpg;
   const int kh_i = p.taps_in_m ? 0 : (group / groups_per_row) % p.kh;
   const int kd_i = p.taps_in_m ? 0 : group / (groups_per_row * p.kh);
-  const int blk0 = mt * p.blocks_per_tile;
-  const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
   const int n0 = nt * p.n_tile;
+  const int msub = min(p.mpg, m_sub - mt * p.mpg);       // 128-row tiles this CTA owns
   const int64_t per = (p.bricks_total + p.splits - 1) / p.splits;
   const int64_t b_begin = (int64_t)blockIdx.y * per;
   const int64_t b_end = min(b_begin + per, p.bricks_total);
@@ -135,9 +136,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
-          mbar_expect_tx(full, (uint32_t)(p.tpg * nblk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes);
+          int tot_blk = 0;
+          for (int mi = 0; mi < msub; ++mi)
+            tot_blk += min(p.blocks_per_tile, p.nblocks - (mt * p.mpg + mi) * p.blocks_per_tile);
+          mbar_expect_tx(full, (uint32_t)(p.tpg * tot_blk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes);
           const uint32_t sbase = tiles + stage * p.stage_bytes;
-          for (int tp = 0; tp < p.tpg; ++tp)
+          for (int mi = 0; mi < msub; ++mi)
+          for (int tp = 0; tp < p.tpg; ++tp) {
+            const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
+            const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
             for (int j = 0; j < nblk; ++j) {
               const int blk = blk0 + j;
               int a = kd_i, b = kh_i, c = kw0 + tp;
@@ -145,10 +152,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
                 const int tb = p.blk_tap[blk];
                 c = tb % p.kw; b = (tb / p.kw) % p.kh; a = tb / (p.kw * p.kh);
               }
-              tma_load_5d(sbase + tp * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]], full,
-                          (int)p.blk_c0[blk], w0 * p.sw + c - p.pw, h0 * p.sh + b - p.ph, d0 * p.sd + a - p.pd,
-                          n_img);
+              tma_load_5d(sbase + (mi * p.tpg + tp) * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]],
+                          full, (int)p.blk_c0[blk], w0 * p.sw + c - p.pw, h0 * p.sh + b - p.ph,
+                          d0 * p.sd + a - p.pd, n_img);
             }
+          }
           for (int j = 0; j < p.n_blocks; ++j) {
             const int nb = n0 / p.cb + j;
             tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB[p.nb_out[nb]], full, (int)p.nb_c0[nb], w0, h0,
@@ -170,11 +178,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = tiles + stage * p.stage_bytes;
           const uint64_t b_lo = (uint64_t)(((sbase + p.b_off) >> 4) & 0x3FFFu) | ((uint64_t)p.b_lbo << 16);
-          for (int tp = 0; tp < p.tpg; ++tp) {
+          for (int at = 0; at < msub * p.tpg; ++at) {       // accumulator = (M sub-tile, tap)
             const uint64_t a_lo =
-                (uint64_t)(((sbase + tp * p.a_tap_bytes) >> 4) & 0x3FFFu) | ((uint64_t)p.a_lbo << 16);
+                (uint64_t)(((sbase + at * p.a_tap_bytes) >> 4) & 0x3FFFu) | ((uint64_t)p.a_lbo << 16);
             for (int k = 0; k < k16s; ++k)
-              umma_bf16(tmem_base + (uint32_t)(tp * p.n_tile), a_hi | (a_lo + (uint64_t)k * a_kstep),
+              umma_bf16(tmem_base + (uint32_t)(at * p.n_tile), a_hi | (a_lo + (uint64_t)k * a_kstep),
                         b_hi | (b_lo + (uint64_t)k * b_kstep), p.idesc, (it | k) ? 1u : 0u);
           }
           umma_commit(bar_empty + 8u * stage);
@@ -189,15 +197,18 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     mbar_wait(bar_accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int r = threadIdx.x;                       // row of the M tile == TMEM lane
-    const int rblk = blk0 + r / p.ck;
-    const bool row_ok = (r / p.ck) < nblk;
-    const int rglob = row_ok ? (int)p.blk_goff[rblk] + r % p.ck : 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int mi = 0; mi < msub; ++mi)
     for (int tp = 0; tp < p.tpg; ++tp) {
+      const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
+      const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
+      const int rblk = blk0 + r / p.ck;
+      const bool row_ok = (r / p.ck) < nblk;
+      const int rglob = row_ok ? (int)p.blk_goff[rblk] + r % p.ck : 0;
       const int tap = (p.taps_in_m && row_ok) ? (int)p.blk_tap[rblk] : (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
       for (int j = 0; j < p.n_tile; j += 8) {
         uint32_t v[8];
-        tmem_ld8(lane_addr + (uint32_t)(tp * p.n_tile + j), v);
+        tmem_ld8(lane_addr + (uint32_t)((mi * p.tpg + tp) * p.n_tile + j), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!row_ok) continue;
         int n = n0 + j;                       // 8-column groups never straddle two dY tensors (channels % 16 == 0)
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
 }
 
 struct WgPlan {
-  int taps_in_m;
+  int taps_in_m, mpg;
   int ck, cb, n_tile, n_blocks, tpg, kv, bd, bh, bw, td, th, tw, stages, nblocks, cin_total;
   uint32_t a_blk_bytes, b_blk_bytes, a_tap_bytes, b_off, stage_bytes, smem_bytes, tmem_cols;
 };
@@ -259,8 +270,13 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
   int tpg = (d->kernel[2] * n_tile <= 512) ? d->kernel[2] : 1;
   const int ntaps = d->kernel[0] * d->kernel[1] * d->kernel[2];
   // few gathered channels (one block per tap): fill the 128 M rows with 128/ck different taps
-  const bool taps_in_m = (cin == ck) && ck < 128 && ntaps > 1 && ntaps <= kMaxBlocks && d->tune[3] != 1;
+  const bool taps_in_m = (cin == ck) && ck < 128 && ntaps > 1 && ntaps <= kMaxBlocks;
   if (taps_in_m) tpg = 1;
+  // M tiles per CTA (they share the dY tile): tune[3], default 1
+  const int m_sub_total = ((taps_in_m ? ntaps : cin / ck) + 128 / ck - 1) / (128 / ck);
+  int mpg_req = d->tune[3] > 1 ? d->tune[3] : (getenv("M1_WG_MPG") ? atoi(getenv("M1_WG_MPG")) : 1);
+  if (mpg_req > m_sub_total) mpg_req = m_sub_total;
+  if (mpg_req < 1) mpg_req = 1;
   // brick: voxels multiple of 16, <= kv_max, best volume coverage
   const int D = d->out_dhw[0], H = d->out_dhw[1], W = d->out_dhw[2];
   auto pick = [&](int kv_max, int* obd, int* obh, int* obw) {
@@ -291,9 +307,11 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
     if (!pick(kv_max, &bd, &bh, &bw)) continue;
     const int kv = bd * bh * bw;
     for (int tp = tpg; tp >= 1; tp = (tp == 1 ? 0 : 1)) {
+      int mpg = mpg_req;
+      while (mpg > 1 && mpg * tp * n_tile > 512) --mpg;
       const uint32_t a_blk = (uint32_t)kv * ck * 2u, b_blk = (uint32_t)kv * cb * 2u;
       const uint32_t a_tap = (128u / ck) * a_blk;
-      const uint32_t b_off = (uint32_t)tp * a_tap;
+      const uint32_t b_off = (uint32_t)(tp * mpg) * a_tap;
       const uint32_t stage = (b_off + (uint32_t)(n_tile / cb) * b_blk + 1023u) & ~1023u;
       int stages = (int)((227u * 1024u - 2048u) / stage);
       if (stages > 8) stages = 8;
@@ -304,10 +322,11 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
       pl->td = (D + bd - 1) / bd; pl->th = (H + bh - 1) / bh; pl->tw = (W + bw - 1) / bw;
       pl->stages = stages; pl->nblocks = taps_in_m ? ntaps : cin / ck; pl->cin_total = cin;
       pl->taps_in_m = taps_in_m ? 1 : 0;
+      pl->mpg = mpg;
       pl->a_blk_bytes = a_blk; pl->b_blk_bytes = b_blk; pl->a_tap_bytes = a_tap; pl->b_off = b_off;
       pl->stage_bytes = stage; pl->smem_bytes = 2048u + (uint32_t)stages * stage;
       uint32_t cols = 32;
-      while ((int)cols < tp * n_tile) cols <<= 1;
+      while ((int)cols < tp * mpg * n_tile) cols <<= 1;
       pl->tmem_cols = cols;
       return true;
     }
@@ -388,6 +407,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.pd = d->pad[0]; p.ph = d->pad[1]; p.pw = d->pad[2];
   p.sd = d->stride[0]; p.sh = d->stride[1]; p.sw = d->stride[2];
   p.tpg = pl.tpg;
+  p.mpg = pl.mpg;
   p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw; p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
   p.batch = d->batch;
   p.kv = pl.kv;
@@ -407,7 +427,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.b_lbo = pl.b_blk_bytes >> 4;
   M1_CHECK(p.a_lbo < (1u << 14) && p.b_lbo < (1u << 14), "wgrad: block too large for the descriptor LBO field");
   p.bricks_total = (int64_t)d->batch * pl.td * pl.th * pl.tw;
-  const int m_tiles = (pl.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  const int m_tiles = ((pl.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile + pl.mpg - 1) / pl.mpg;
   const int n_tiles = (p.co + pl.n_tile - 1) / pl.n_tile;
   const int groups = pl.taps_in_m ? 1 : p.kd * p.kh * (p.kw / pl.tpg);
   const int64_t base_ctas = (int64_t)groups * m_tiles * n_tiles;

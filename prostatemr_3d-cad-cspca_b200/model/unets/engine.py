@@ -289,7 +289,9 @@ class Engine:
         for d, ws, packed in self.packs.values():
             ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
 
-    WG_CANDIDATES = ((128, 0, 2), (128, 1, 2), (64, 0, 2), (64, 1, 2), (128, 0, 3), (64, 0, 3))
+    # (max voxels per K brick, taps sharing a dY tile [0 = kw if it fits], stage cap, M tiles per CTA)
+    WG_CANDIDATES = ((128, 0, 2, 1), (128, 1, 2, 1), (64, 0, 2, 1), (64, 1, 2, 1), (128, 0, 3, 1), (64, 0, 3, 1),
+                     (128, 1, 2, 2), (64, 1, 2, 2), (64, 0, 2, 2))
 
     def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl, label=None):
         on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)
@@ -300,7 +302,7 @@ class Engine:
             if cfg is None:
                 cfg = self._tune_wgrad(d, srcs_t, douts_t, dws)
                 self.tuned[key] = cfg
-            d.tune[0], d.tune[1], d.tune[2] = cfg
+            d.tune[0], d.tune[1], d.tune[2], d.tune[3] = cfg
         self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl,
                     lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
@@ -310,9 +312,9 @@ class Engine:
         """One-off per layer shape: time the candidate tilings of the tcgen05 weight-gradient kernel on
         scratch gradient buffers (CUDA events) and keep the fastest."""
         scratch = [torch.zeros(w.numel(), dtype=torch.float32, device=self.device) for w in dws]
-        best, best_t = (0, 0, 0), float("inf")
+        best, best_t = (0, 0, 0, 0), float("inf")
         for cand in self.WG_CANDIDATES:
-            d.tune[0], d.tune[1], d.tune[2] = cand
+            d.tune[0], d.tune[1], d.tune[2], d.tune[3] = cand
             if not ops.conv3d_wgrad_tc_supported(d):
                 continue
             ts = []
@@ -326,7 +328,7 @@ class Engine:
             t = min(ts[1:])
             if t < best_t:
                 best, best_t = cand, t
-        d.tune[0], d.tune[1], d.tune[2] = 0, 0, 0
+        d.tune[0], d.tune[1], d.tune[2], d.tune[3] = 0, 0, 0, 0
         return best
 
     def _conv_bwd(self, srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr, bias_grad=True):
