@@ -68,6 +68,8 @@ typedef struct {
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
   /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
+   * conv:  tune[0] = engine variant: 1 = one TMA box per filter tap (conv_tc.cu), 2 = halo tile shared by
+   *        the in-plane taps through row-shifted UMMA descriptors (conv_tc_halo.cu; stride-1 gathers only)
    * wgrad: tune[0] = max voxels per K brick (16..128), tune[1] = taps sharing one dY tile (1 or kw),
    *        tune[2] = pipeline stage cap, tune[3] = 128-row M tiles per CTA (they share the dY tile) */
   int32_t tune[4];
@@ -86,6 +88,8 @@ int  m1_ctx_destroy(m1_ctx* ctx);
 int64_t m1_ctx_launch_count(m1_ctx* ctx, int reset);
 /* 1 if the tcgen05 engine can take this launch (shape/dtype constraints), else 0 */
 int  m1_conv3d_tc_supported(const m1_conv_desc* d);
+/* 1 if m1_conv3d would run this launch on the halo variant of the tcgen05 engine (honours d->tune[0]) */
+int  m1_conv3d_halo_engine(const m1_conv_desc* d);
 
 /* ---- K1/K2: convolution, transposed convolution and their data gradients ----------------
  * replaces tf.keras.layers.Conv3D / Conv3DTranspose (+BiasAdd) at R:networks.py:472,496-553,

@@ -152,6 +152,9 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
 int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                  const void* w_packed, const float* const* bias, void* const* outs,
                  cudaStream_t st);
+int m1_conv3d_halo_supported(const m1_conv_desc* d, int* preferred);
+int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, const void* w_packed,
+                   const float* const* bias, void* const* outs, cudaStream_t st);
 int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j0, int jn);
 int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const void* const* srcs,
                        const void* const* douts, float* const* dws, cudaStream_t st);

@@ -260,6 +260,220 @@ __global__ void __launch_bounds__(128) conv_thin_kernel(const __grid_constant__ 
   }
 }
 
+// ---- 1x1x1 heads ---------------------------------------------------------------------------------
+// The mu/log-sigma heads (R:networks.py:637-641: 128/256/512 -> 2/4/6 channels, fp32 out) and their two
+// gradients are pure streaming: one read of the feature tensor. Lanes own 8-channel chunks (16-byte
+// loads), head weights live in registers, partial dot products meet through warp shuffles.
+//   pw_head_fwd   : out[v][n]  = b[n] + sum_r x[v][r] W[r][n]                 (N <= 8)
+//   pw_head_dgrad : dx[v][r] (+)= sum_n dy[v][n] W[r][n]                      (N <= 8 gathered)
+//   pw_head_wgrad : dW[r][n]  += sum_v x[v][r] dy[v][n]
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(b[i]); v[2 * i + 1] = __high2float(b[i]); }
+}
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+struct HeadParams {
+  const void* x;      // [vox][C] features (fwd, wgrad)
+  const float* dy;    // [vox][N] fp32 (dgrad, wgrad)
+  void* out;          // fwd: float [vox][N]; dgrad: T [vox][C]
+  const float* w;     // W[r * sr + n * so]
+  const float* bias;
+  float* dw;
+  int64_t sr, so;
+  int64_t vox;
+  int C, N, accumulate;
+};
+
+// lanes per voxel LPV = min(32, C/8); a lane owns chunks lane%LPV + i*32 (i < CPL)
+template <typename T, int NP, int CPL>
+__global__ void __launch_bounds__(256) pw_head_fwd_kernel(const HeadParams p) {
+  const int chunks = p.C / 8;
+  const int lpv = chunks < 32 ? chunks : 32;
+  const int lane = threadIdx.x & 31, sub = lane % lpv, vpw = 32 / lpv;   // voxels per warp iteration
+  float w[CPL][8][NP];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i)
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const int ch = (sub + i * 32) * 8 + r;
+        w[i][r][n] = (n < p.N && ch < p.C) ? p.w[(int64_t)ch * p.sr + (int64_t)n * p.so] : 0.f;
+      }
+  float b[NP];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) b[n] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+  const T* x = reinterpret_cast<const T*>(p.x);
+  float* out = reinterpret_cast<float*>(p.out);
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5), wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int64_t v0 = wid * vpw; v0 < p.vox; v0 += warps * vpw) {
+    const int64_t v = v0 + lane / lpv;
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = 0.f;
+    if (v < p.vox) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c0 = (sub + i * 32) * 8;
+        if (c0 < p.C) {
+          float xv[8];
+          ld8<T>(x + v * p.C + c0, xv);
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int n = 0; n < NP; ++n) acc[n] = fmaf(xv[r], w[i][r][n], acc[n]);
+        }
+      }
+    }
+    for (int o = lpv >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (sub == 0 && v < p.vox) {
+#pragma unroll
+      for (int n = 0; n < NP; ++n)
+        if (n < p.N) {
+          float r = acc[n] + b[n];
+          if (p.accumulate) r += out[v * p.N + n];
+          out[v * p.N + n] = r;
+        }
+    }
+  }
+}
+
+// thread = (voxel lane, 8-channel chunk): blockDim.x % (C/8) == 0
+template <typename T, int NP>
+__global__ void __launch_bounds__(256) pw_head_dgrad_kernel(const HeadParams p) {
+  const int chunks = p.C / 8;
+  const int chunk = threadIdx.x % chunks, vl = threadIdx.x / chunks, vpb = blockDim.x / chunks;
+  float w[8][NP];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int n = 0; n < NP; ++n) w[r][n] = n < p.N ? p.w[(int64_t)(chunk * 8 + r) * p.sr + (int64_t)n * p.so] : 0.f;
+  T* dx = reinterpret_cast<T*>(p.out);
+  for (int64_t v = (int64_t)blockIdx.x * vpb + vl; v < p.vox; v += (int64_t)gridDim.x * vpb) {
+    float g[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) g[n] = n < p.N ? p.dy[v * p.N + n] : 0.f;
+    float o[8];
+    T* dst = dx + v * p.C + chunk * 8;
+    if (p.accumulate) {
+      ld8<T>(dst, o);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) o[r] = 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) o[r] = fmaf(g[n], w[r][n], o[r]);
+    st8<T>(dst, o);
+  }
+}
+
+// thread = (voxel lane, 8-channel chunk); 8 x N accumulators, block reduction through shared memory
+template <typename T, int NP>
+__global__ void __launch_bounds__(256) pw_head_wgrad_kernel(const HeadParams p) {
+  extern __shared__ float red[];   // [C][NP]
+  const int chunks = p.C / 8;
+  const int chunk = threadIdx.x % chunks, vl = threadIdx.x / chunks, vpb = blockDim.x / chunks;
+  for (int i = threadIdx.x; i < p.C * NP; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[8][NP];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[r][n] = 0.f;
+  const T* x = reinterpret_cast<const T*>(p.x);
+  for (int64_t v = (int64_t)blockIdx.x * vpb + vl; v < p.vox; v += (int64_t)gridDim.x * vpb) {
+    float g[NP], xv[8];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) g[n] = n < p.N ? p.dy[v * p.N + n] : 0.f;
+    ld8<T>(x + v * p.C + chunk * 8, xv);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) acc[r][n] = fmaf(xv[r], g[n], acc[r][n]);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int n = 0; n < NP; ++n) atomicAdd(&red[(chunk * 8 + r) * NP + n], acc[r][n]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.C * NP; i += blockDim.x) {
+    const int r = i / NP, n = i % NP;
+    if (n < p.N && red[i] != 0.f) atomicAdd(p.dw + (int64_t)r * p.sr + (int64_t)n * p.so, red[i]);
+  }
+}
+
+// chunks = C/8 must divide 256 (dgrad/wgrad thread mapping) and be a power of two <= 32 or a multiple of 32 (fwd)
+inline bool head_shape_ok(int C, int N) {
+  if (N < 1 || N > 8 || C % 8) return false;
+  const int chunks = C / 8;
+  return chunks == 4 || chunks == 8 || chunks == 16 || chunks == 32 || chunks == 64;
+}
+inline bool pointwise_s1(const m1_conv_desc* d) {
+  for (int i = 0; i < 3; ++i)
+    if (d->kernel[i] != 1 || d->stride[i] != 1) return false;
+  return d->nsrc == 1 && d->nout == 1 && !d->w_by_src;
+}
+
+template <typename T>
+int launch_head(m1_ctx* ctx, int which, const HeadParams& p, cudaStream_t st) {
+  const int chunks = p.C / 8;
+  const int np = (p.N + 1) & ~1;   // instantiated widths: 2, 4, 6, 8
+  const int64_t vpb = which == 0 ? (chunks >= 32 ? 8 : 8 * (32 / chunks)) : 256 / chunks;
+  const int threads = 256;
+  int64_t blocks = std::min<int64_t>(cdiv64(p.vox, vpb), (int64_t)ctx->num_sms * (which == 2 ? 4 : 16));
+  if (blocks < 1) blocks = 1;
+#define M1_HEAD_CASE(NP)                                                                                        \
+  case NP:                                                                                                      \
+    if (which == 0) {                                                                                           \
+      if (chunks > 32) pw_head_fwd_kernel<T, NP, 2><<<(unsigned)blocks, 256, 0, st>>>(p);                       \
+      else pw_head_fwd_kernel<T, NP, 1><<<(unsigned)blocks, 256, 0, st>>>(p);                                   \
+    } else if (which == 1) {                                                                                    \
+      pw_head_dgrad_kernel<T, NP><<<(unsigned)blocks, threads, 0, st>>>(p);                                     \
+    } else {                                                                                                    \
+      pw_head_wgrad_kernel<T, NP><<<(unsigned)blocks, threads, (size_t)p.C * NP * sizeof(float), st>>>(p);      \
+    }                                                                                                           \
+    break;
+  switch (np) {
+    M1_HEAD_CASE(2)
+    M1_HEAD_CASE(4)
+    M1_HEAD_CASE(6)
+    M1_HEAD_CASE(8)
+    default: m1_set_error("head kernel: unsupported width %d", p.N); return 1;
+  }
+#undef M1_HEAD_CASE
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 // ---- weight gradient ----------------------------------------------------------------------
 // dW[tap, r, n] += sum_o G(o, tap)[r] * dY[o, n];  block = (64 r x 64 n) tile of one tap over a
 // slab of output voxels, fp32 atomics into dW.
@@ -521,6 +735,25 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   for (int s = 0; s < d->nsrc; ++s) k_total += d->src_c[s];
   const int taps = p.kd * p.kh * p.kw;
   const size_t thin_smem = (size_t)taps * k_total * TN * sizeof(float);
+  if (pointwise_s1(d)) {
+    HeadParams h;
+    memset(&h, 0, sizeof(h));
+    h.vox = p.out_vox;
+    h.w = w[0];
+    h.accumulate = d->accumulate & 1;
+    if (!ob && p.n_total <= 8 && head_shape_ok(k_total, p.n_total)) {
+      // features -> few fp32 channels
+      h.x = srcs[0]; h.out = outs[0]; h.bias = bias ? bias[0] : nullptr;
+      h.C = k_total; h.N = p.n_total; h.sr = d->w_stride_red[0]; h.so = d->w_stride_out[0];
+      return ib ? launch_head<__nv_bfloat16>(ctx, 0, h, st) : launch_head<float>(ctx, 0, h, st);
+    }
+    if (!ib && k_total <= 8 && head_shape_ok(p.n_total, k_total) && !(bias && bias[0])) {
+      // few fp32 gradient channels -> gradient of the features (roles of the weight strides swapped)
+      h.dy = reinterpret_cast<const float*>(srcs[0]); h.out = outs[0];
+      h.C = p.n_total; h.N = k_total; h.sr = d->w_stride_out[0]; h.so = d->w_stride_red[0];
+      return ob ? launch_head<__nv_bfloat16>(ctx, 1, h, st) : launch_head<float>(ctx, 1, h, st);
+    }
+  }
   if ((k_total <= 16 || p.n_total <= 16) && thin_smem <= 48 * 1024) {
     dim3 tgrid((unsigned)cdiv64(p.out_vox, TV), (unsigned)((p.n_total + TN - 1) / TN));
     if (ib && ob) conv_thin_kernel<__nv_bfloat16, __nv_bfloat16><<<tgrid, 128, thin_smem, st>>>(p, k_total);
@@ -573,6 +806,18 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       q.src_index = s;
       q.r_base = r_base;
       const int C = d->src_c[s];
+      if (pointwise_s1(d) && d->out_dtype == M1_F32 && head_shape_ok(C, q.Cn)) {
+        HeadParams h;
+        memset(&h, 0, sizeof(h));
+        h.vox = out_vox;
+        h.x = srcs[s]; h.dy = reinterpret_cast<const float*>(douts[j]);
+        h.dw = q.dw + (int64_t)r_base * q.sr;
+        h.C = C; h.N = q.Cn; h.sr = q.sr; h.so = q.so;
+        if (d->act_dtype == M1_BF16 ? launch_head<__nv_bfloat16>(ctx, 2, h, st) : launch_head<float>(ctx, 2, h, st))
+          return 1;
+        r_base += C;
+        continue;
+      }
       {
         // few-channel layer: exact-work kernel (micro-tiles of 4 x 8 outputs, <= 256 per block)
         const int Rp = (C + SW_RB - 1) / SW_RB * SW_RB, Np = (q.Cn + SW_NB - 1) / SW_NB * SW_NB;

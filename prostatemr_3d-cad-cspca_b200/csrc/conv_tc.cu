@@ -25,12 +25,12 @@
 // 8-row swizzle atoms), so one tcgen05.mma per 16 channels consumes them with no data movement
 // by threads.  One CTA = one M tile x one N tile; several CTAs are co-resident per SM so that the
 // epilogue of one overlaps the main loop of another.
-#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;   // warp 0: TMA producer, warp 1: MMA issuer, all 8 warps: epilogue
 
 struct TcParams {
   CUtensorMap tmA[M1_MAX_SRC];
@@ -50,7 +50,6 @@ struct TcParams {
   int td, th, tw;              // bricks per dim
   int Do, Ho, Wo;              // produced grid
   int n_tile;
-  int n_total;                 // real produced channels (the weight pack is zero-padded to 16)
   int ck;
   int group, stages;
   uint32_t a_alloc, slot_bytes;
@@ -58,13 +57,7 @@ struct TcParams {
   uint32_t tmem_cols;
   uint32_t idesc;
   uint32_t desc_hi;            // upper 32 bits of the UMMA shared-memory descriptors
-  int nout;
-  void* out[M1_MAX_OUT];
-  int out_c[M1_MAX_OUT];
-  int out_start[M1_MAX_OUT + 1];
-  const float* bias[M1_MAX_OUT];
-  int out_bf16;
-  int accumulate;              // bitmask over outputs
+  EpiOut epi;
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -79,7 +72,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const uint32_t tiles = smem_base + 1024u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
 
   // ---- tile coordinates -----------------------------------------------------------------
   int t = blockIdx.x;
@@ -119,7 +112,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const int nstage_iters = (ksteps + p.group - 1) / p.group;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       int tap = tap_begin, src = 0, chunk = 0;
       const int a_d0 = d0 * p.istr_d, a_h0 = h0 * p.istr_h, a_w0 = w0 * p.istr_w;
@@ -146,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       uint32_t stage = 0, phase = 0;
       const uint64_t hi = (uint64_t)p.desc_hi << 32;
@@ -174,13 +167,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     __syncwarp();
   }
 
-  // ===== epilogue: TMEM -> registers -> (+bias) -> global, all four warps =====
+  // ===== epilogue: 8 warps; warps w and w+4 share TMEM lanes 32*(w%4).. and split the columns =====
   // (a phase without taps - kernel smaller than the stride - produces bias only: nothing was issued,
   //  the MMA warp still commits bar_accum and the accumulator is treated as zero)
   mbar_wait(bar_accum, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
-    const int r = threadIdx.x;  // row of the tile == TMEM lane
+    const int r = (warp & 3) * 32 + (threadIdx.x & 31);  // row of the tile == TMEM lane
     const int lw = r % p.bw;
     const int lh = (r / p.bw) % p.bh;
     const int ld = r / (p.bw * p.bh);
@@ -188,59 +181,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               w = (w0 + lw) * p.ostr_w + p.phase_w[ph];
     const bool valid = (ld < p.bd) && d < p.Do && h < p.Ho && w < p.Wo;
     const int64_t vox = (((int64_t)n_img * p.Do + d) * p.Ho + h) * p.Wo + w;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int j = 0; j < p.n_tile; j += 8) {
-      uint32_t v[8];
-      tmem_ld8(lane_addr + (uint32_t)j, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (ksteps == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0u;
-      }
-      int gc = n0 + j;
-      if (!valid || gc >= p.n_total) continue;
-      int o = 0;
-      while (o + 1 < p.nout && gc >= p.out_start[o + 1]) ++o;
-      gc -= p.out_start[o];
-      const bool accum = (p.accumulate >> o) & 1;
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
-      if (p.bias[o] != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(p.bias[o] + gc);
-        const float4 b1 = *reinterpret_cast<const float4*>(p.bias[o] + gc + 4);
-        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-      }
-      const int64_t off = vox * p.out_c[o] + gc;
-      if (p.out_bf16) {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[o]) + off;
-        if (accum) {
-          uint4 old = *reinterpret_cast<const uint4*>(dst);
-          const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            f[2 * i] += __low2float(ob[i]);
-            f[2 * i + 1] += __high2float(ob[i]);
-          }
-        }
-        uint4 pk;
-        __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pb[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        *reinterpret_cast<uint4*>(dst) = pk;
-      } else {
-        float* dst = reinterpret_cast<float*>(p.out[o]) + off;
-        if (accum) {
-          const float4 o0 = *reinterpret_cast<const float4*>(dst);
-          const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
-          f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
-          f[4] += o1.x; f[5] += o1.y; f[6] += o1.z; f[7] += o1.w;
-        }
-        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-      }
-    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    int cb, ce;
+    epi_cols(warp, p.n_tile, &cb, &ce);
+    epilogue_row(p.epi, lane_addr, n0, cb, ce, valid, vox, ksteps == 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -433,9 +377,16 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   return 0;
 }
 
+extern "C" int m1_conv3d_halo_engine(const m1_conv_desc* d) {
+  int pref = 0;
+  if (d->tune[0] == 1 || !m1_conv3d_halo_supported(d, &pref)) return 0;
+  return (d->tune[0] == 2 || pref) ? 1 : 0;
+}
+
 int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                  const void* w_packed, const float* const* bias, void* const* outs,
                  cudaStream_t st) {
+  if (m1_conv3d_halo_engine(d)) return m1_conv3d_halo(ctx, d, srcs, w_packed, bias, outs, st);
   Plan pl;
   M1_CHECK(make_plan(d, &pl), "m1_conv3d: launch not supported by the tcgen05 engine");
   M1_CHECK(w_packed != nullptr, "m1_conv3d: tcgen05 engine needs the bf16 weight pack");
@@ -524,7 +475,6 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
   p.Do = d->out_dhw[0]; p.Ho = d->out_dhw[1]; p.Wo = d->out_dhw[2];
   p.n_tile = pl.n_tile;
-  p.n_total = pl.n_real;
   p.ck = pl.ck;
   p.group = pl.group;
   p.stages = pl.stages;
@@ -540,20 +490,9 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   const uint32_t sbo = (8u * pl.ck * 2u) >> 4;
   const uint32_t layout = pl.ck == 64 ? 2u : pl.ck == 32 ? 4u : 6u;
   p.desc_hi = sbo | (1u << 14) | (layout << 29);
-  p.nout = d->nout;
-  {
-    int acc = 0;
-    for (int j = 0; j < d->nout; ++j) { p.out_start[j] = acc; acc += d->out_c[j]; }
-    p.out_start[d->nout] = acc;
-  }
-  for (int j = 0; j < d->nout; ++j) {
-    p.out[j] = outs[j];
-    p.out_c[j] = d->out_c[j];
-    p.bias[j] = bias ? bias[j] : nullptr;
+  M1_CHECK(epi_fill(&p.epi, d, bias, outs), "m1_conv3d: too many produced channels for the tcgen05 epilogue table");
+  for (int j = 0; j < d->nout; ++j)
     M1_CHECK(((uintptr_t)outs[j] & 15) == 0, "m1_conv3d: produced tensor %d not 16-byte aligned", j);
-  }
-  p.out_bf16 = 1;
-  p.accumulate = d->accumulate;
 
   static int smem_set = 0;
   if (smem_set < (int)pl.smem_bytes) {

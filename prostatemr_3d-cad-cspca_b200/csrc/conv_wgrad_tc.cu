@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   const uint32_t tmem_slot = smem_base + 8u * 33u;
   const uint32_t tiles = smem_base + 1024u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
 
   // ---- work decomposition: blockIdx.x = ((group * m_tiles + m_tile) * n_tiles + n_tile), blockIdx.y = split
   const int m_sub = (p.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;   // 128-row tiles in total
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
 
   if (iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         // ===== TMA producer: one stage = one voxel brick =====
         uint32_t stage = 0, phase = 0;
         for (int it = 0; it < iters; ++it) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         // ===== MMA issuer =====
         uint32_t stage = 0, phase = 0;
         const uint64_t a_hi = (uint64_t)p.a_desc_hi << 32, b_hi = (uint64_t)p.b_desc_hi << 32;

@@ -8,6 +8,22 @@ namespace tc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// One elected lane of a converged warp. The single-thread tcgen05.mma / TMA issue loops MUST be guarded by
+// this and not by `lane == 0`: with a plain lane test the compiler cannot prove a single active thread and
+// wraps every UTCHMMA / UTMALDG (uniform-register operands) in an ELECT + BRA.U.ANY serialisation loop,
+// which costs ~143 cycles per MMA regardless of its shape (measured with tools/probe_umma_shift.cu on B200;
+// elected issue: 128.5 cycles at N=256, 80.5 at N=160, 44.5 at N=48).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

@@ -222,6 +222,14 @@ class Engine:
                 packed = ent[2]
             fl = 2 * vox * taps * int(sum(src_c[i0:i1])) * int(sum(out_c))
             b = bias if first else None
+            if packed is not None and self.autotune:
+                tk = ("conv", mode, batch, tuple(in_dhw), tuple(out_dhw), k, s, tuple(src_c[i0:i1]), tuple(out_c),
+                      bool(w_by_src))
+                var = self.tuned.get(tk)
+                if var is None:
+                    var = self._tune_conv(d, list(src_t[i0:i1]), sub_w, list(out_t), packed)
+                    self.tuned[tk] = var
+                d.tune[0] = var
             self._timed(cat + ("_tcgen05" if packed is not None else "_simt"), fl,
                         lambda: ops.conv3d(self.ctx, d, list(src_t[i0:i1]), sub_w, b, list(out_t), packed),
                         label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)))
@@ -307,6 +315,30 @@ class Engine:
                     lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
                            tuple(srcs_t[0].shape[1:4])))
+
+    def _tune_conv(self, d, srcs_t, ws, outs_t, packed):
+        """One-off per launch shape: time the two variants of the tcgen05 convolution engine (one TMA box per
+        filter tap / one halo tile shared by the in-plane taps) on scratch outputs and keep the faster."""
+        d.tune[0] = 2
+        if not ops.conv3d_halo_engine(d):
+            d.tune[0] = 0
+            return 1
+        scratch = [torch.empty_like(o) for o in outs_t]
+        best, best_t = 1, float("inf")
+        for var in (1, 2):
+            d.tune[0] = var
+            ts = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.conv3d(self.ctx, d, srcs_t, ws, None, scratch, packed)
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            if min(ts[1:]) < best_t:
+                best, best_t = var, min(ts[1:])
+        d.tune[0] = 0
+        return best
 
     def _tune_wgrad(self, d, srcs_t, douts_t, dws):
         """One-off per layer shape: time the candidate tilings of the tcgen05 weight-gradient kernel on

@@ -63,6 +63,11 @@ def conv3d_tc_supported(d):
     return bool(lib().m1_conv3d_tc_supported(C.byref(d)))
 
 
+def conv3d_halo_engine(d):
+    """True if m1_conv3d would run d on the halo variant of the tcgen05 engine (honours d.tune[0])."""
+    return bool(lib().m1_conv3d_halo_engine(C.byref(d)))
+
+
 def conv3d_wgrad_tc_supported(d):
     return bool(lib().m1_conv3d_wgrad_tc_supported0(C.byref(d)))
 

@@ -1,4 +1,6 @@
 """K1/K2/K3 parity: the CUDA convolution engines against the CPU oracle (tests may import oracle/)."""
+import ctypes
+
 import pytest
 import torch
 
@@ -16,7 +18,7 @@ def _mk(batch, dhw, cins, couts, k, seed=0):
     return xs, ws, bs
 
 
-def _run_fwd(ctx, xs, ws, bs, k, s, dtype, engine):
+def _run_fwd(ctx, xs, ws, bs, k, s, dtype, engine, variant=0):
     from m1b200 import ops, _lib
     dev = 'cuda'
     batch, dhw = xs[0].shape[0], xs[0].shape[1:4]
@@ -28,6 +30,9 @@ def _run_fwd(ctx, xs, ws, bs, k, s, dtype, engine):
     d = ops.conv_desc(_lib.CONV_FWD, batch, dhw, out_dhw, k, s, pad, [x.shape[-1] for x in xs],
                       [w.shape[-1] for w in ws], [(cin * w.shape[-1], w.shape[-1], 1) for w in ws],
                       act_dtype=code, engine=engine)
+    d.tune[0] = variant
+    if variant == 2:
+        assert _lib.lib().m1_conv3d_halo_engine(ctypes.byref(d)) == 1, "halo engine refused the launch"
     xd = [x.to(dev, dtype).contiguous() for x in xs]
     wd = [w.to(dev).contiguous() for w in ws]
     bd = [b.to(dev).contiguous() for b in bs]
@@ -393,3 +398,117 @@ def test_conv_dgrad_k_fused(ctx, engine_name):
     for x_, b in zip(xs, bufs):
         err = (b.double().cpu() - x_.grad).abs().max().item()
         assert err < 3e-2 * max(1.0, x_.grad.abs().max().item()), err
+
+
+@pytest.mark.parametrize("C,N,dtype", [(128, 2, torch.bfloat16), (256, 4, torch.bfloat16), (512, 6, torch.bfloat16),
+                                       (32, 2, torch.bfloat16), (64, 8, torch.float32), (128, 3, torch.float32)])
+def test_pointwise_heads(ctx, C, N, dtype):
+    """mu/log-sigma style 1x1x1 heads (R:networks.py:637-641): streaming forward (fp32 out), data gradient
+    (fp32 dy -> activation-dtype dx, overwrite and accumulate) and weight gradient vs autograd of the oracle."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(21)
+    dhw = (3, 7, 9)                                              # ragged voxel count
+    x = torch.randn((2, *dhw, C), generator=g).to(dtype).double().requires_grad_()
+    w = (torch.randn((1, 1, 1, C, N), generator=g, dtype=torch.float64) / C ** 0.5).requires_grad_()
+    b = torch.randn((N,), generator=g, dtype=torch.float64) * 0.1
+    y = O.conv3d_same(x, w, b, (1, 1, 1))
+    dy = torch.randn(y.shape, generator=g).double()
+    y.backward(dy)
+    dev = 'cuda'
+    code = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+    xd = x.detach().to(dev, dtype).contiguous()
+    wd = w.detach().float().to(dev).contiguous()
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, dhw, (1, 1, 1), (1, 1, 1), (0, 0, 0), [C], [N], [(C * N, N, 1)],
+                      act_dtype=code, out_dtype=_lib.F32, engine=_lib.ENGINE_SIMT)
+    out = torch.full((2, *dhw, N), float('nan'), device=dev)
+    before = ctx.launch_count()
+    ops.conv3d(ctx, d, [xd], [wd], [b.float().to(dev)], [out])
+    assert ctx.launch_count() == before + 1
+    torch.cuda.synchronize()
+    assert (out.double().cpu() - y.detach()).abs().max().item() < 1e-4
+    # wgrad (+ bias gradient)
+    dw = torch.full(w.shape, 0.25, device=dev)
+    db = torch.zeros(N, device=dev)
+    dyd = dy.float().to(dev).contiguous()
+    ops.conv3d_wgrad(ctx, d, [xd], [dyd], [dw], [db])
+    torch.cuda.synchronize()
+    scale = max(1.0, w.grad.abs().max().item())
+    assert (dw.double().cpu() - (w.grad + 0.25)).abs().max().item() < 1e-4 * scale
+    assert (db.double().cpu() - dy.sum(dim=(0, 1, 2, 3))).abs().max().item() < 1e-3
+    # dgrad: gathered = dy (N fp32 channels), produced = dx (C channels)
+    dd = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, dhw, (1, 1, 1), (1, 1, 1), (0, 0, 0), [N], [C],
+                       [(C * N, 1, N)], accumulate=[True], act_dtype=_lib.F32, out_dtype=code,
+                       engine=_lib.ENGINE_SIMT)
+    prior = torch.randn(x.shape, generator=g).to(dtype)
+    dx = prior.clone().to(dev)
+    ops.conv3d(ctx, dd, [dyd], [wd], None, [dx])
+    torch.cuda.synchronize()
+    ref = x.grad + prior.double()
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (dx.double().cpu() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+HALO_CASES = [
+    ((2, 12, 40), [64], [32], (1, 3, 3)),                   # SW128, one sub-tile column, H ragged vs G*bh
+    ((3, 16, 44), [32, 32, 32], [16, 32], (1, 3, 3)),       # SW64 chunks over a virtual concat, W ragged (44 = 40 + 4)
+    ((4, 9, 40), [16], [16], (3, 3, 3)),                    # thin 3x3x3 layer (SE conv2 at res0/res1), plane skipping at d = 0, D-1
+    ((3, 10, 20), [64, 64], [16, 64], (3, 3, 3)),           # narrow grid: bw = 20, bh = 5
+    ((2, 7, 80), [32], [32], (1, 3, 3)),                    # two W tiles, H < G*bh
+    ((1, 5, 160), [16, 32], [32, 32, 32], (1, 3, 3)),       # full-resolution row length
+    ((2, 6, 40), [128], [64, 256], (3, 3, 3)),              # N = 320: two N tiles
+    ((2, 8, 40), [32], [8, 32], (1, 1, 3)),                 # taps along W only; 8-channel produced tensor
+    ((2, 8, 40), [32], [48], (3, 3, 1)),                    # taps along D and H only
+]
+
+
+@pytest.mark.parametrize("dhw,cins,couts,k", HALO_CASES)
+def test_conv_fwd_halo(ctx, dhw, cins, couts, k):
+    """Halo variant of the tcgen05 engine (row-shifted UMMA descriptors over one TMA halo tile) vs the oracle."""
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k, seed=31)
+    got = _run_fwd(ctx, xs, ws, bs, k, (1, 1, 1), torch.bfloat16, _lib.ENGINE_TCGEN05, variant=2)
+    ref = _ref_fwd(xs, ws, bs, (1, 1, 1), torch.bfloat16)
+    for g, r in zip(got, ref):
+        assert torch.isfinite(g).all(), "non-finite output (unwritten voxels?)"
+        err = (g - r).abs().max().item()
+        assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("dhw,couts,cins,k", [((3, 12, 40), [16, 32], [32, 32, 32], (1, 3, 3)),
+                                              ((4, 9, 40), [16], [16], (3, 3, 3)),
+                                              ((2, 10, 80), [16, 64], [64, 64], (1, 3, 3))])
+def test_conv_dgrad_halo(ctx, dhw, couts, cins, k):
+    """K-fused data gradient of a stride-1 conv (TRANSPOSED gather, w_by_src) on the halo engine, first
+    produced tensor accumulating onto existing content."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(33)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g, dtype=torch.float64, requires_grad=True) for c in cins]
+    ws = [(torch.randn((*k, cin, co), generator=g) / (cin * 9) ** 0.5).bfloat16().double() for co in couts]
+    x = torch.cat(xs, -1)
+    dys = []
+    for w in ws:
+        y = O.conv3d_same(x, w, None, (1, 1, 1))
+        dy = torch.randn(y.shape, generator=g).bfloat16().double()
+        y.backward(dy, retain_graph=True)
+        dys.append(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    wd = [w.float().to(dev).contiguous() for w in ws]
+    offs = [sum(cins[:i]) for i in range(len(cins))]
+    wv = [wd[j].view(-1)[o * couts[j]:] for o in offs for j in range(len(couts))]
+    d = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, dhw, k, (1, 1, 1), pad, couts, cins,
+                      [(cin * co, 1, co) for co in couts], accumulate=[True] + [False] * (len(cins) - 1),
+                      act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05, w_by_src=True)
+    d.tune[0] = 2
+    assert _lib.lib().m1_conv3d_halo_engine(ctypes.byref(d)) == 1
+    packed = ops.conv3d_pack_weights(ctx, d, wv)
+    prior = torch.randn(xs[0].shape, generator=g).bfloat16()
+    bufs = [prior.clone().to(dev)] + [torch.full(x_.shape, float('nan'), device=dev, dtype=torch.bfloat16)
+                                      for x_ in xs[1:]]
+    ops.conv3d(ctx, d, [t.to(dev, torch.bfloat16).contiguous() for t in dys], wv, None, bufs, packed)
+    torch.cuda.synchronize()
+    for i, (x_, b) in enumerate(zip(xs, bufs)):
+        ref = x_.grad + (prior.double() if i == 0 else 0)
+        err = (b.double().cpu() - ref).abs().max().item()
+        assert err < 3e-2 * max(1.0, ref.abs().max().item()), (i, err)

@@ -23,6 +23,11 @@ SHAPES = {
     'sersp3': ((10, 20, 20), [256, 256, 256], [64, 256], (3, 3, 3), (1, 1, 1), False),
     'sersp1': ((20, 80, 80), [64] * 5, [16, 64], (1, 3, 3), (1, 1, 1), False),
     'sersp0': ((20, 160, 160), [32] * 6, [16, 32], (1, 3, 3), (1, 1, 1), False),
+    'sersd0': ((20, 160, 160), [32] * 5, [16, 32], (1, 3, 3), (1, 1, 1), False),
+    'sersd1': ((20, 80, 80), [64] * 4, [16, 64], (1, 3, 3), (1, 1, 1), False),
+    'conve0': ((20, 160, 160), [16], [32], (1, 3, 3), (1, 1, 1), False),
+    'conv2_r0': ((20, 160, 160), [16], [16], (3, 3, 3), (1, 1, 1), False),
+    'conv2_r1': ((20, 80, 80), [16], [16], (3, 3, 3), (1, 1, 1), False),
     'conv2_r2': ((20, 40, 40), [32], [32], (3, 3, 3), (1, 1, 1), False),
     'conv3_r0': ((20, 160, 160), [16], [32], (1, 1, 1), (1, 1, 1), False),
     'serse2': ((20, 80, 80), [64], [32, 128], (3, 3, 3), (1, 2, 2), False),
@@ -52,6 +57,7 @@ def main():
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--what', default='fwd,dgrad,wgrad')
     ap.add_argument('--batch', type=int, default=B)
+    ap.add_argument('--variant', type=int, default=0, help='m1_conv_desc.tune[0]: 0 heuristic, 1 per-tap, 2 halo')
     args = ap.parse_args()
     what = args.what.split(',')
     ctx = _lib.Context.get(0)
@@ -86,6 +92,7 @@ def main():
         if 'fwd' in what:
             d = ops.conv_desc(mode, nb, dhw, out_dhw, k, s, pad, cins, couts, wstr, act_dtype=_lib.BF16,
                               engine=_lib.ENGINE_TCGEN05)
+            d.tune[0] = args.variant
             packed = ops.conv3d_pack_weights(ctx, d, ws)
             t = timeit(lambda: ops.conv3d(ctx, d, xs, ws, bs, outs, packed), args.iters, flushbuf)
             line += '| fwd %7.3f ms %6.1f TF ' % (t, flops / t / 1e9)
@@ -93,7 +100,17 @@ def main():
             tt = 0.0
             offs = np.cumsum([0] + cins)[:-1]
             dxs = [torch.empty_like(x) for x in xs]
-            for j, co in enumerate(couts):
+            fused = (not tr) and len(couts) > 1 and all(c % 16 == 0 for c in couts)
+            if fused:      # the engine's K-fused launch: K runs over [dy_j ...], per-(produced, gathered) weights
+                dd = ops.conv_desc(_lib.CONV_TRANSPOSED, nb, out_dhw, dhw, k, s, pad, couts, cins,
+                                   [(cin * co, 1, co) for co in couts], act_dtype=_lib.BF16,
+                                   engine=_lib.ENGINE_TCGEN05, accumulate=[True] + [False] * (len(cins) - 1),
+                                   w_by_src=True)
+                dd.tune[0] = args.variant
+                wv = [ws[j].view(-1)[int(o) * couts[j]:] for o in offs for j in range(len(couts))]
+                pk = ops.conv3d_pack_weights(ctx, dd, wv)
+                tt += timeit(lambda: ops.conv3d(ctx, dd, douts, wv, None, dxs, pk), args.iters, flushbuf)
+            for j, co in enumerate([] if fused else couts):
                 if tr:
                     dd = ops.conv_desc(_lib.CONV_FWD, nb, out_dhw, dhw, k, s, pad, [co], cins,
                                        [(co * cin, cin, 1)] * len(cins), act_dtype=_lib.BF16,
@@ -104,6 +121,7 @@ def main():
                                        [(cin * co, 1, co)] * len(cins), act_dtype=_lib.BF16,
                                        engine=_lib.ENGINE_TCGEN05, accumulate=j > 0)
                     wv = [ws[j].view(-1)[int(o) * co:] for o in offs]
+                dd.tune[0] = args.variant
                 pk = ops.conv3d_pack_weights(ctx, dd, wv)
                 tt += timeit(lambda: ops.conv3d(ctx, dd, [douts[j]], wv, None, dxs, pk), args.iters, flushbuf)
             line += '| dgrad %7.3f ms %6.1f TF ' % (tt, flops / tt / 1e9)
