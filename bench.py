@@ -182,6 +182,7 @@ def workload_config(args, world):
                         "step, %dx%dx%d volumes, 4 input channels (3 bpMRI + label ch), batch %d per GPU"
                         % (tuple(args.dims) + (args.batch,)),
             "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+            "step_launch": "whole training step captured once into a CUDA graph and replayed (M1_CUDA_GRAPH=0: eager)",
             "l2_flush": "not needed: every step streams >10 GB of activations, far above the 126 MB L2",
             "filters": list(README_CFG['filters']), "prob_latent_dims": [3, 2, 1, 0]}
 
@@ -265,14 +266,24 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    # ---- headline: K steps, inputs resident in HBM. After its warm-up the model replays the whole step from
+    # a CUDA graph (M1.train_step); kernels launched = replays x kernels captured per step + eager launches.
     ctx.launch_count(reset=True)
-    model.eng.prof = []
+    replays0 = getattr(model, "graph_replays", 0)
     ms = timed(args.steps, dev_step)
     launches = ctx.launch_count(reset=True)
-    prof, model.eng.prof = model.eng.prof, None
+    replays = getattr(model, "graph_replays", 0) - replays0
+    if replays:
+        launches += replays * model.launches_per_graph_step
     clk = clocks.stop() if rank == 0 else None
+    # ---- end to end: pinned host inputs copied in, loss read back, every step
     e2e_step()
     ms_e2e = timed(args.steps, e2e_step)
+    # ---- per-kernel-family durations: the same K steps once more, launched eagerly with a CUDA-event pair
+    # around every launch family (a replayed graph cannot carry per-launch events)
+    model.eng.prof = []
+    ms_prof = timed(args.steps, dev_step)
+    prof, model.eng.prof = model.eng.prof, None
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -309,7 +320,10 @@ def run_ours(args):
         ach = (fl / 1e12) / (t_ms / 1e3)
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
-                    "share_of_step": t_ms / ms, "flop_per_launch_avg": fl / n,
+                    "share_of_step": t_ms / sum(v[1] for v in cats.values()), "flop_per_launch_avg": fl / n,
+                    "timed_with": "CUDA events around every launch family in an eager re-run of the same %d steps "
+                                  "(%.2f ms/step; the headline replays the step as a CUDA graph)"
+                                  % (args.steps, ms_prof / args.steps),
                     "conv_path_tflops_whole_step": (FLOP_PER_VOLUME * B * args.steps / 1e12) / (ms / 1e3),
                     "conv_path_frac_whole_step": (FLOP_PER_VOLUME * B * args.steps / 1e12) / (ms / 1e3) / peak_tf,
                     "breakdown": breakdown}

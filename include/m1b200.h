@@ -155,11 +155,15 @@ int m1_se_excite_bwd(m1_ctx* ctx, const float* dgate, const float* pool, const f
                      void* stream);
 /* dropout source: u != NULL -> injected uniforms (same dtype fp32, one per element);
  * else Philox4x32-10(seed, stream_id, element index).  rate == 0 -> no dropout. */
+/* Philox stream advance per training step when the launch is replayed from a captured CUDA graph:
+ * effective stream = stream_id + (*step) * M1_PHILOX_STEP_STRIDE (step: device-resident counter, or NULL) */
+#define M1_PHILOX_STEP_STRIDE 4096ull
 typedef struct {
   const float* u;
   uint64_t seed;
   uint64_t stream_id;
   float rate;
+  const uint64_t* step;
 } m1_dropout;
 int m1_se_gate_fwd(m1_ctx* ctx, const void* raw3, const void* raw4, const float* stats3,
                    const float* stats4, const float* gamma3, const float* beta3,
@@ -245,6 +249,12 @@ int m1_adam_amsgrad(m1_ctx* ctx, float* w, const float* g, float* m, float* v, f
                     int64_t n, float lr_t, float beta1, float beta2, float eps, float l2,
                     float gscale, float* l2_sq_out, void* stream);
 
+/* Same update with the step size read from DEVICE memory (lr_t_dev[0]): the form that can be captured in a
+ * CUDA graph and replayed while the learning-rate schedule advances on the host. */
+int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat,
+                        int64_t n, const float* lr_t_dev, float beta1, float beta2, float eps, float l2,
+                        float gscale, float* l2_sq_out, void* stream);
+
 /* ---- small utilities used by the host ------------------------------------------------------- */
 int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int ddtype, int64_t n,
             void* stream);
@@ -257,6 +267,9 @@ int m1_axpy(m1_ctx* ctx, const void* x, int dtype, float a, void* y, int64_t n, 
  * tfp MultivariateNormalDiag.sample() (R:networks.py:647,671,695) when no eps is injected */
 int m1_philox_normal(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, float* out, int64_t n,
                      void* stream);
+/* same, stream advanced by a device-resident step counter (graph replay): stream_id + *step_dev * 4096 */
+int m1_philox_normal_step(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, const uint64_t* step_dev, float* out,
+                          int64_t n, void* stream);
 /* decision fusion of the cascaded model, R:networks.py:209-223 (strategy 0 identity, 1 noisy-or,
  * 2 bayes): out [rows][2] = [1-j, j] */
 int m1_decision_fusion(m1_ctx* ctx, const float* prior, const float* follow, int strategy,

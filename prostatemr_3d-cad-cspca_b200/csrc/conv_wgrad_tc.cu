@@ -38,6 +38,7 @@ struct WgParams {
   uint16_t blk_goff[kMaxBlocks]; // M block -> first channel over the virtual concatenation
   uint8_t blk_tap[kMaxBlocks];   // taps-in-M mode: M block -> tap (layers with <= 64 gathered channels put
                                  // 128/ck different TAPS of the single channel block into one M tile)
+  int8_t blk_ka[kMaxBlocks], blk_kb[kMaxBlocks], blk_kc[kMaxBlocks];   // ... and its (kd, kh, kw) index
   int taps_in_m;
   int nblocks;                   // total M blocks (ck channels each)
   int blocks_per_tile;           // 128 / ck
@@ -120,70 +121,90 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   if (iters > 0) {
     if (warp == 0) {
       if (elect_one()) {
-        // ===== TMA producer: one stage = one voxel brick =====
+        // ===== TMA producer: one stage = one voxel brick. 32-bit arithmetic and an incrementally advanced
+        // brick coordinate: 64-bit div/mod per stage in this single thread used to cost more than the MMAs.
         uint32_t stage = 0, phase = 0;
+        int bi = (int)b_begin;
+        int tw_i = bi % p.tw; bi /= p.tw;
+        int th_i = bi % p.th; bi /= p.th;
+        int td_i = bi % p.td;
+        int n_img = bi / p.td;
+        int tot_blk = 0;
+        for (int mi = 0; mi < msub; ++mi)
+          tot_blk += min(p.blocks_per_tile, p.nblocks - (mt * p.mpg + mi) * p.blocks_per_tile);
+        const uint32_t tx = (uint32_t)(p.tpg * tot_blk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes;
+        const int nb0 = n0 / p.cb;
         for (int it = 0; it < iters; ++it) {
-          int64_t b = b_begin + it;
-          const int tw_i = (int)(b % p.tw); b /= p.tw;
-          const int th_i = (int)(b % p.th); b /= p.th;
-          const int td_i = (int)(b % p.td); b /= p.td;
-          const int n_img = (int)b;
           const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8u * stage;
           if (p.dbg_noload) {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
-            continue;
-          }
-          int tot_blk = 0;
-          for (int mi = 0; mi < msub; ++mi)
-            tot_blk += min(p.blocks_per_tile, p.nblocks - (mt * p.mpg + mi) * p.blocks_per_tile);
-          mbar_expect_tx(full, (uint32_t)(p.tpg * tot_blk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes);
-          const uint32_t sbase = tiles + stage * p.stage_bytes;
-          for (int mi = 0; mi < msub; ++mi)
-          for (int tp = 0; tp < p.tpg; ++tp) {
-            const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
-            const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
-            for (int j = 0; j < nblk; ++j) {
-              const int blk = blk0 + j;
-              int a = kd_i, b = kh_i, c = kw0 + tp;
-              if (p.taps_in_m) {
-                const int tb = p.blk_tap[blk];
-                c = tb % p.kw; b = (tb / p.kw) % p.kh; a = tb / (p.kw * p.kh);
+          } else {
+            mbar_expect_tx(full, tx);
+            const uint32_t sbase = tiles + stage * p.stage_bytes;
+            const int aw = w0 * p.sw - p.pw, ah = h0 * p.sh - p.ph, ad = d0 * p.sd - p.pd;
+            uint32_t dst = sbase;
+            for (int mi = 0; mi < msub; ++mi) {
+              const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
+              const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
+              for (int tp = 0; tp < p.tpg; ++tp) {
+                uint32_t dj = dst;
+                for (int j = 0; j < nblk; ++j) {
+                  const int blk = blk0 + j;
+                  // taps-in-M: the block's own tap (host table), else the tap of this CTA's group
+                  const int a = p.taps_in_m ? (int)p.blk_ka[blk] : kd_i, b = p.taps_in_m ? (int)p.blk_kb[blk] : kh_i,
+                            c = p.taps_in_m ? (int)p.blk_kc[blk] : kw0 + tp;
+                  tma_load_5d(dj, &p.tmA[p.blk_src[blk]], full, (int)p.blk_c0[blk], aw + c, ah + b, ad + a, n_img);
+                  dj += p.a_blk_bytes;
+                }
+                dst += p.a_tap_bytes;
               }
-              tma_load_5d(sbase + (mi * p.tpg + tp) * p.a_tap_bytes + j * p.a_blk_bytes, &p.tmA[p.blk_src[blk]],
-                          full, (int)p.blk_c0[blk], w0 * p.sw + c - p.pw, h0 * p.sh + b - p.ph,
-                          d0 * p.sd + a - p.pd, n_img);
+            }
+            uint32_t db = sbase + p.b_off;
+            for (int j = 0; j < p.n_blocks; ++j) {
+              const int nb = nb0 + j;
+              tma_load_5d(db, &p.tmB[p.nb_out[nb]], full, (int)p.nb_c0[nb], w0, h0, d0, n_img);
+              db += p.b_blk_bytes;
             }
           }
-          for (int j = 0; j < p.n_blocks; ++j) {
-            const int nb = n0 / p.cb + j;
-            tma_load_5d(sbase + p.b_off + j * p.b_blk_bytes, &p.tmB[p.nb_out[nb]], full, (int)p.nb_c0[nb], w0, h0,
-                        d0, n_img);
-          }
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+          if (++tw_i == p.tw) {
+            tw_i = 0;
+            if (++th_i == p.th) {
+              th_i = 0;
+              if (++td_i == p.td) { td_i = 0; ++n_img; }
+            }
+          }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       if (elect_one()) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (32-bit descriptor arithmetic only: the issuing thread's instruction latency is exposed)
         uint32_t stage = 0, phase = 0;
         const uint64_t a_hi = (uint64_t)p.a_desc_hi << 32, b_hi = (uint64_t)p.b_desc_hi << 32;
         const uint32_t a_kstep = (16u * p.ck * 2u) >> 4, b_kstep = (16u * p.cb * 2u) >> 4;
+        const uint32_t a_tap16 = p.a_tap_bytes >> 4;
+        const uint32_t a_lbo = p.a_lbo << 16, b_lbo = p.b_lbo << 16;
         const int k16s = p.kv / 16;
+        const int nacc = msub * p.tpg;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_full + 8u * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = tiles + stage * p.stage_bytes;
-          const uint64_t b_lo = (uint64_t)(((sbase + p.b_off) >> 4) & 0x3FFFu) | ((uint64_t)p.b_lbo << 16);
-          for (int at = 0; at < msub * p.tpg; ++at) {       // accumulator = (M sub-tile, tap)
-            const uint64_t a_lo =
-                (uint64_t)(((sbase + at * p.a_tap_bytes) >> 4) & 0x3FFFu) | ((uint64_t)p.a_lbo << 16);
-            for (int k = 0; k < k16s; ++k)
-              umma_bf16(tmem_base + (uint32_t)(at * p.n_tile), a_hi | (a_lo + (uint64_t)k * a_kstep),
-                        b_hi | (b_lo + (uint64_t)k * b_kstep), p.idesc, (it | k) ? 1u : 0u);
+          const uint32_t b0 = ((sbase + p.b_off) >> 4) | b_lbo;
+          uint32_t a_t = (sbase >> 4) | a_lbo;
+          uint32_t d_t = tmem_base;
+          for (int at = 0; at < nacc; ++at) {       // accumulator = (M sub-tile, tap)
+            uint32_t a_k = a_t, b_k = b0;
+            umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, it ? 1u : 0u);
+            for (int k = 1; k < k16s; ++k) {
+              a_k += a_kstep; b_k += b_kstep;
+              umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, 1u);
+            }
+            a_t += a_tap16;
+            d_t += (uint32_t)p.n_tile;
           }
           umma_commit(bar_empty + 8u * stage);
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -376,6 +397,9 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
     const int ntaps = d->kernel[0] * d->kernel[1] * d->kernel[2];
     for (int t = 0; t < ntaps; ++t) {
       p.blk_src[t] = 0; p.blk_c0[t] = 0; p.blk_goff[t] = 0; p.blk_tap[t] = (uint8_t)t;
+      p.blk_kc[t] = (int8_t)(t % d->kernel[2]);
+      p.blk_kb[t] = (int8_t)((t / d->kernel[2]) % d->kernel[1]);
+      p.blk_ka[t] = (int8_t)(t / (d->kernel[2] * d->kernel[1]));
     }
   }
   p.taps_in_m = pl.taps_in_m;

@@ -335,9 +335,15 @@ __global__ void __launch_bounds__(TB) se_excite_bwd_kernel(const float* __restri
 
 struct DropArgs {
   const float* u;
+  const uint64_t* step;          // device step counter of a replayed CUDA graph (or NULL)
   uint64_t seed, stream_id;
   float rate, scale;
 };
+// Philox stream of this launch: m1_dropout.stream_id, advanced by the device-resident step counter when the
+// launch is part of a captured graph (scalar kernel arguments are frozen at capture time)
+__device__ __forceinline__ uint64_t drop_stream(const DropArgs& dr) {
+  return dr.stream_id + (dr.step ? *dr.step * M1_PHILOX_STEP_STRIDE : 0ull);
+}
 
 // keep-mask * scale for the VW elements starting at flat element index e (e % VW == 0)
 template <int VW>
@@ -352,11 +358,12 @@ __device__ __forceinline__ void drop_factors(const DropArgs& dr, int64_t e, floa
     ldp<VW>(dr.u + e, u);
   } else {
     float q[4];
-    philox_uniform4(dr.seed, dr.stream_id, (uint64_t)(e >> 2), q);
+    const uint64_t sid = drop_stream(dr);
+    philox_uniform4(dr.seed, sid, (uint64_t)(e >> 2), q);
     if constexpr (VW >= 4) {
       u[0] = q[0]; u[1] = q[1]; u[2] = q[2]; u[3] = q[3];
       if constexpr (VW == 8) {
-        philox_uniform4(dr.seed, dr.stream_id, (uint64_t)(e >> 2) + 1, q);
+        philox_uniform4(dr.seed, sid, (uint64_t)(e >> 2) + 1, q);
         u[4] = q[0]; u[5] = q[1]; u[6] = q[2]; u[7] = q[3];
       }
     } else {
@@ -528,6 +535,7 @@ DropArgs make_drop(const m1_dropout* d) {
   a.u = d ? d->u : nullptr;
   a.seed = d ? d->seed : 0;
   a.stream_id = d ? d->stream_id : 0;
+  a.step = d ? d->step : nullptr;
   a.rate = d ? d->rate : 0.f;
   a.scale = (d && d->rate > 0.f) ? 1.f / (1.f - d->rate) : 1.f;
   return a;

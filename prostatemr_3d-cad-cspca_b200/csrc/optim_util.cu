@@ -9,10 +9,12 @@ constexpr int TB = 256;
 
 __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                  float* __restrict__ m, float* __restrict__ v,
-                                                 float* __restrict__ vhat, int64_t n, float lr_t, float b1,
+                                                 float* __restrict__ vhat, int64_t n, float lr_t,
+                                                 const float* __restrict__ lr_dev, float b1,
                                                  float b2, float eps, float l2, float gscale,
                                                  float* __restrict__ l2_out) {
   __shared__ float sm[TB / 32];
+  if (lr_dev != nullptr) lr_t = *lr_dev;      // graph replay: the step size lives in device memory
   float acc[1] = {0.f};
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < n4; i += (int64_t)gridDim.x * TB) {
@@ -87,8 +89,10 @@ __global__ void fusion_kernel(const float* __restrict__ prior, const float* __re
   }
 }
 
-__global__ void philox_normal_kernel(uint64_t seed, uint64_t stream_id, float* __restrict__ out, int64_t n) {
+__global__ void philox_normal_kernel(uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ step,
+                                     float* __restrict__ out, int64_t n) {
   const int64_t n4 = (n + 3) / 4;
+  if (step != nullptr) stream_id += *step * M1_PHILOX_STEP_STRIDE;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float u[4];
     philox_uniform4(seed, stream_id, (uint64_t)i, u);
@@ -117,8 +121,20 @@ extern "C" int m1_adam_amsgrad(m1_ctx* ctx, float* w, const float* g, float* m, 
                                float* l2_sq_out, void* stream) {
   M1_CHECK((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vhat) & 15) == 0,
            "m1_adam_amsgrad: buffers must be 16-byte aligned");
-  adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, lr_t, beta1, beta2, eps, l2,
-                                                                   gscale, l2_sq_out);
+  adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, lr_t, nullptr, beta1, beta2,
+                                                                   eps, l2, gscale, l2_sq_out);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat, int64_t n,
+                                   const float* lr_t_dev, float beta1, float beta2, float eps, float l2,
+                                   float gscale, float* l2_sq_out, void* stream) {
+  M1_CHECK((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vhat) & 15) == 0,
+           "m1_adam_amsgrad_dev: buffers must be 16-byte aligned");
+  M1_CHECK(lr_t_dev != nullptr, "m1_adam_amsgrad_dev: lr_t_dev is NULL");
+  adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, 0.f, lr_t_dev, beta1, beta2,
+                                                                   eps, l2, gscale, l2_sq_out);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -170,7 +186,14 @@ extern "C" int m1_decision_fusion(m1_ctx* ctx, const float* prior, const float* 
 
 extern "C" int m1_philox_normal(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, float* out, int64_t n,
                                 void* stream) {
-  philox_normal_kernel<<<nb(ctx, (n + 3) / 4), TB, 0, (cudaStream_t)stream>>>(seed, stream_id, out, n);
+  philox_normal_kernel<<<nb(ctx, (n + 3) / 4), TB, 0, (cudaStream_t)stream>>>(seed, stream_id, nullptr, out, n);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_philox_normal_step(m1_ctx* ctx, uint64_t seed, uint64_t stream_id, const uint64_t* step_dev,
+                                     float* out, int64_t n, void* stream) {
+  philox_normal_kernel<<<nb(ctx, (n + 3) / 4), TB, 0, (cudaStream_t)stream>>>(seed, stream_id, step_dev, out, n);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -76,17 +76,21 @@ class PhiloxNoise:
     def __init__(self, seed=42, rank=0):
         self.seed = int(seed) + 1000003 * int(rank)
         self.step = 0
+        self.step_dev = None      # device step counter while a CUDA graph of the step is being captured
 
     def _stream(self, pass_name, site):
+        """Philox stream = step * 4096 + pass * 64 + site; under graph capture the step term is added on the
+        device from step_dev (M1_PHILOX_STEP_STRIDE), so eager and replayed steps draw identical noise."""
         p = self.PASSES.index(pass_name) if pass_name in self.PASSES else len(self.PASSES)
-        return (self.step * 64 + p) * 64 + self.SITES.index(site)
+        step = 0 if self.step_dev is not None else self.step
+        return (step * 64 + p) * 64 + self.SITES.index(site)
 
     def dropout(self, eng, pass_name, site, shape, rate):
-        return ops.make_dropout(rate, None, self.seed, self._stream(pass_name, site)), None
+        return ops.make_dropout(rate, None, self.seed, self._stream(pass_name, site), self.step_dev), None
 
     def normal(self, eng, pass_name, site, shape):
         out = torch.empty(shape, dtype=torch.float32, device=eng.device)
-        ops.philox_normal(eng.ctx, self.seed, self._stream(pass_name, site), out)
+        ops.philox_normal(eng.ctx, self.seed, self._stream(pass_name, site), out, self.step_dev)
         return out
 
 
@@ -299,7 +303,7 @@ class Engine:
 
     # (max voxels per K brick, taps sharing a dY tile [0 = kw if it fits], stage cap, M tiles per CTA)
     WG_CANDIDATES = ((128, 0, 2, 1), (128, 1, 2, 1), (64, 0, 2, 1), (64, 1, 2, 1), (128, 0, 3, 1), (64, 0, 3, 1),
-                     (128, 1, 2, 2), (64, 1, 2, 2), (64, 0, 2, 2))
+                     (64, 0, 4, 1), (64, 1, 4, 1), (128, 1, 3, 1), (128, 1, 2, 2), (64, 1, 2, 2), (64, 0, 2, 2))
 
     def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl, label=None):
         on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)

@@ -454,16 +454,92 @@ class M1(LoadableModel):
         t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
         return t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
 
+    # ---- CUDA-graph replay of the training step ------------------------------------------------------
+    # One M1 step is ~1 700 kernel launches; issued from Python they cost more host time than the kernels
+    # take on a B200. After GRAPH_WARMUP eager steps (tcgen05 autotuning, weight packs, function attributes)
+    # the whole step - forward, losses, backward, gradient all-reduce, Adam, weight re-pack - is captured
+    # once into a CUDA graph over static input buffers and replayed. Everything that changes per step lives
+    # in device memory: the Philox step counter (m1_dropout.step / m1_philox_normal_step) and the Adam step
+    # size (m1_adam_amsgrad_dev), both written by a tiny fill launch before the replay.
+    GRAPH_WARMUP = 2
+
+    def _graph_ok(self, apply_update):
+        import os
+        if not apply_update or self.eng.prof is not None or not isinstance(self.noise, PhiloxNoise):
+            return False
+        mode = os.environ.get("M1_CUDA_GRAPH", "1")
+        if mode == "0" or getattr(self, "_graph_failed", False):
+            return False
+        if self.world_size > 1 and os.environ.get("M1_CUDA_GRAPH_DP", "1") == "0":
+            return False
+        return True
+
+    def _train_step_graphed(self, x, y):
+        st = getattr(self, "_gs", None)
+        if st is not None and (tuple(x.shape) != tuple(st['x'].shape) or tuple(y.shape) != tuple(st['y'].shape)):
+            st = self._gs = None                      # new input shape: capture again
+            self._graph_eager_steps = 0
+        if st is None:
+            n = getattr(self, "_graph_eager_steps", 0)
+            if n < self.GRAPH_WARMUP:
+                self._graph_eager_steps = n + 1
+                return None
+            st = dict(x=torch.empty_like(x), y=torch.empty_like(y),
+                      step=torch.zeros(1, dtype=torch.int64, device=self.device),
+                      lr=torch.zeros(1, dtype=torch.float32, device=self.device))
+            st['x'].copy_(x); st['y'].copy_(y)
+            st['step'].fill_(self.noise.step); st['lr'].fill_(self.optimizer.lr_t())
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            self.noise.step_dev, self._lr_dev = st['step'], st['lr']
+            before = self.eng.ctx.launch_count()
+            try:
+                with torch.cuda.graph(graph):
+                    st['out'] = self._train_step_eager(st['x'], st['y'], True, graphed=True)
+            except Exception:
+                self.noise.step_dev, self._lr_dev = None, None
+                self._graph_failed = True
+                raise
+            finally:
+                self.noise.step_dev, self._lr_dev = None, None
+            st['graph'] = graph
+            st['launches'] = self.eng.ctx.launch_count() - before
+            self._gs = st
+        else:
+            st['x'].copy_(x, non_blocking=True)
+            st['y'].copy_(y, non_blocking=True)
+        st['step'].fill_(self.noise.step)
+        st['lr'].fill_(self.optimizer.lr_t())
+        st['graph'].replay()
+        self.graph_replays = getattr(self, "graph_replays", 0) + 1
+        self.optimizer.iterations += 1
+        self.noise.step += 1
+        return st['out']
+
+    @property
+    def launches_per_graph_step(self):
+        """kernels of libm1b200 inside one replayed step (counted at capture), or None in eager mode"""
+        st = getattr(self, "_gs", None)
+        return st['launches'] if st else None
+
     def train_step(self, x, y_true, apply_update=True):
         """Forward of the 4-pass graph, focal + KL losses, full backward, (all-reduce), Adam-AMSGrad.
-        x: (B,D,H,W,C) fp32, y_true: one-hot (B,D,H,W,nc). Returns dict of device scalars."""
+        x: (B,D,H,W,C) fp32, y_true: one-hot (B,D,H,W,nc). Returns dict of device scalars (in graph mode:
+        views of the graph's static output buffers, overwritten by the next step)."""
         if self.eng is None:
             raise RuntimeError("M1.train_step: model not built on a GPU (m1b200 has no CPU fallback)")
         if self.optimizer is None:
             self.compile()
-        eng = self.eng
         x = self._to_device(x)
         y = self._to_device(y_true)
+        if self._graph_ok(apply_update):
+            out = self._train_step_graphed(x, y)
+            if out is not None:
+                return out
+        return self._train_step_eager(x, y, apply_update)
+
+    def _train_step_eager(self, x, y, apply_update=True, graphed=False):
+        eng = self.eng
         B = x.shape[0]
         eng.noise = self.noise
         eng.begin(record=True)
@@ -505,21 +581,27 @@ class M1(LoadableModel):
         else:
             eng.backward()
         if apply_update:
-            eng._timed("adam+repack", 0, lambda: self._apply_update(scal[2:3], inv_r))
-        if isinstance(self.noise, PhiloxNoise):
+            eng._timed("adam+repack", 0, lambda: self._apply_update(scal[2:3], inv_r, graphed))
+        if isinstance(self.noise, PhiloxNoise) and not graphed:
             self.noise.step += 1
         return dict(detection=det, focal=scal[0:1], kl=scal[1:2], l2=scal[2:3])
 
-    def _apply_update(self, l2_out, gscale=1.0):
+    def _apply_update(self, l2_out, gscale=1.0, graphed=False):
         opt, P = self.optimizer, self.params
         lr_t = opt.lr_t()
         for grp, l2 in (('kernel', self.l2_kernel), ('bias', self.l2_bias), ('plain', 0.0)):
             a, b = P.group_range[grp]
             if b > a:
                 # L2 term of every rank is scaled 1/R like the data term (MirroredStrategy semantics)
-                ops.adam_amsgrad(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b], lr_t,
-                                 opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0, l2_out if l2 > 0 else None)
-        opt.iterations += 1
+                if graphed:      # step size from device memory: the captured launch is replayed every step
+                    ops.adam_amsgrad_dev(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b],
+                                         self._lr_dev, opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0,
+                                         l2_out if l2 > 0 else None)
+                else:
+                    ops.adam_amsgrad(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b], lr_t,
+                                     opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0, l2_out if l2 > 0 else None)
+        if not graphed:
+            opt.iterations += 1
         self.eng.refresh_packs()
 
     def total_loss(self, r):

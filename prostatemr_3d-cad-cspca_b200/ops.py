@@ -119,12 +119,14 @@ def inorm_act_bwd(ctx, dy, x, stats, gamma, beta, slope, dx, accumulate, dgamma,
 
 
 # ---- K5 squeeze-excite -----------------------------------------------------------------------
-def make_dropout(rate, u=None, seed=0, stream_id=0):
+def make_dropout(rate, u=None, seed=0, stream_id=0, step=None):
+    """step: device uint64 tensor (1 element) holding the training-step counter of a replayed graph."""
     d = Dropout()
     d.u = ptr(u) if u is not None else None
     d.seed = seed
     d.stream_id = stream_id
     d.rate = rate
+    d.step = ptr(step) if step is not None else None
     return d
 
 
@@ -231,6 +233,11 @@ def adam_amsgrad(ctx, w, g, m, v, vhat, lr_t, b1, b2, eps, l2, gscale, l2_out=No
                                 eps, l2, gscale, ptr(l2_out), current_stream()))
 
 
+def adam_amsgrad_dev(ctx, w, g, m, v, vhat, lr_t_dev, b1, b2, eps, l2, gscale, l2_out=None):
+    check(lib().m1_adam_amsgrad_dev(ctx.handle, ptr(w), ptr(g), ptr(m), ptr(v), ptr(vhat), w.numel(), ptr(lr_t_dev),
+                                    b1, b2, eps, l2, gscale, ptr(l2_out), current_stream()))
+
+
 def cast(ctx, src, dst):
     check(lib().m1_cast(ctx.handle, ptr(src), dtype_code(src), ptr(dst), dtype_code(dst), src.numel(),
                         current_stream()))
@@ -257,8 +264,12 @@ def bias_grad(ctx, dout, dbias):
                              current_stream()))
 
 
-def philox_normal(ctx, seed, stream_id, out):
-    check(lib().m1_philox_normal(ctx.handle, seed, stream_id, ptr(out), out.numel(), current_stream()))
+def philox_normal(ctx, seed, stream_id, out, step=None):
+    if step is None:
+        check(lib().m1_philox_normal(ctx.handle, seed, stream_id, ptr(out), out.numel(), current_stream()))
+    else:
+        check(lib().m1_philox_normal_step(ctx.handle, seed, stream_id, ptr(step), ptr(out), out.numel(),
+                                          current_stream()))
 
 
 def logits_softmax_focal(ctx, feat, w, bias, y_true, alpha, gamma, prob, head_off, head_weight, loss_out, dfeat,
