@@ -164,6 +164,9 @@ typedef struct {
   uint64_t stream_id;
   float rate;
   const uint64_t* step;
+  /* optional keep-mask, 1 bit per element ((elements + 7) / 8 bytes, C % 8 == 0): m1_se_gate_fwd writes it,
+   * the two backward kernels read it instead of regenerating the noise (NULL: regenerate) */
+  uint8_t* mask;
 } m1_dropout;
 int m1_se_gate_fwd(m1_ctx* ctx, const void* raw3, const void* raw4, const float* stats3,
                    const float* stats4, const float* gamma3, const float* beta3,

@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
 class Dropout(C.Structure):
     """m1_dropout of include/m1b200.h"""
     _fields_ = [("u", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_uint64),
-                ("rate", C.c_float), ("step", C.c_void_p)]
+                ("rate", C.c_float), ("step", C.c_void_p), ("mask", C.c_void_p)]
 
 
 class M1Error(RuntimeError):

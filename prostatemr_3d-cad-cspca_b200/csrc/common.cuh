@@ -127,6 +127,19 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
+// the 4 raw 32-bit words of Philox4x32-10 for counter (idx4, stream_id) under key seed
+__device__ __forceinline__ void philox_words4(uint64_t seed, uint64_t stream_id, uint64_t idx4, uint32_t (&w)[4]) {
+  uint32_t c[4] = {(uint32_t)idx4, (uint32_t)(idx4 >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = c[i];
+}
 // 4 uniforms in [0,1) for counter (idx4, stream_id) under key seed
 __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream_id, uint64_t idx4,
                                                 float (&u)[4]) {

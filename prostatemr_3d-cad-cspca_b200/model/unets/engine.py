@@ -86,7 +86,12 @@ class PhiloxNoise:
         return (step * 64 + p) * 64 + self.SITES.index(site)
 
     def dropout(self, eng, pass_name, site, shape, rate):
-        return ops.make_dropout(rate, None, self.seed, self._stream(pass_name, site), self.step_dev), None
+        # training: the forward gate kernel leaves 1 keep-bit per element for its two backward kernels (Philox
+        # costs more instructions than the rest of those kernels); inference regenerates nothing anyway
+        mask = None
+        if eng.record and shape[-1] % 8 == 0:
+            mask = torch.empty((int(np.prod(shape)) + 7) // 8, dtype=torch.uint8, device=eng.device)
+        return ops.make_dropout(rate, None, self.seed, self._stream(pass_name, site), self.step_dev, mask), mask
 
     def normal(self, eng, pass_name, site, shape):
         out = torch.empty(shape, dtype=torch.float32, device=eng.device)

@@ -119,14 +119,16 @@ def inorm_act_bwd(ctx, dy, x, stats, gamma, beta, slope, dx, accumulate, dgamma,
 
 
 # ---- K5 squeeze-excite -----------------------------------------------------------------------
-def make_dropout(rate, u=None, seed=0, stream_id=0, step=None):
-    """step: device uint64 tensor (1 element) holding the training-step counter of a replayed graph."""
+def make_dropout(rate, u=None, seed=0, stream_id=0, step=None, mask=None):
+    """step: device uint64 tensor (1 element) holding the training-step counter of a replayed graph;
+    mask: uint8 tensor of numel/8 bytes - keep-bits written by se_gate_fwd and read back by its backward."""
     d = Dropout()
     d.u = ptr(u) if u is not None else None
     d.seed = seed
     d.stream_id = stream_id
     d.rate = rate
     d.step = ptr(step) if step is not None else None
+    d.mask = ptr(mask) if mask is not None else None
     return d
 
 

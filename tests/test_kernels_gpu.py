@@ -280,6 +280,52 @@ def test_philox_dropout_statistics_and_replay(ctx):
     assert not torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_keep_mask_equals_regenerated_noise(ctx, dtype):
+    """m1_dropout.mask: the keep-bits written by se_gate_fwd give the backward kernels exactly the mask that
+    re-running Philox gives them (same draw3/draw4/red), and bit i of byte e/8 is 'element e kept'."""
+    from m1b200 import ops
+    g = _gen(11)
+    C, shape = 32, (2, 4, 8, 8, 32)
+    n = 2
+    raw3 = torch.randn(shape, generator=g).to(DEV, dtype)
+    raw4 = torch.randn(shape, generator=g).to(DEV, dtype)
+    dout = torch.randn(shape, generator=g).to(DEV, dtype)
+    st3, st4 = torch.zeros((n, C, 2), device=DEV), torch.zeros((n, C, 2), device=DEV)
+    ops.inorm_stats(ctx, raw3, st3, 1e-3)
+    ops.inorm_stats(ctx, raw4, st4, 1e-3)
+    g3, b3 = torch.rand(C, generator=g).to(DEV) + 0.5, torch.randn(C, generator=g).to(DEV)
+    g4, b4 = torch.rand(C, generator=g).to(DEV) + 0.5, torch.randn(C, generator=g).to(DEV)
+    gate = torch.rand((n, C), generator=g).to(DEV)
+    dpool = torch.zeros((n, C), device=DEV)
+    res = []
+    for use_mask in (False, True):
+        mask = torch.zeros(raw3.numel() // 8, dtype=torch.uint8, device=DEV) if use_mask else None
+        drop = ops.make_dropout(0.5, None, seed=5, stream_id=9, mask=mask)
+        out = torch.empty_like(raw3)
+        ops.se_gate_fwd(ctx, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, out)
+        red, dgate = torch.zeros((n, C, 5), device=DEV), torch.zeros((n, C), device=DEV)
+        ops.se_gate_bwd_reduce(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, red, dgate)
+        d3, d4 = torch.empty_like(raw3), torch.empty_like(raw3)
+        z = [torch.zeros(C, device=DEV) for _ in range(4)]
+        ops.se_gate_bwd_apply(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, red, dpool, d3, d4, *z)
+        torch.cuda.synchronize()
+        res.append((out, red, d3, d4, mask))
+    (o0, r0, a0, c0, _), (o1, r1, a1, c1, mask) = res
+    assert torch.equal(o0, o1)
+    assert (r0 - r1).abs().max().item() <= 1e-4 * r0.abs().max().item()      # atomics: summation order only
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4                           # draw* depend on red
+    for p_, q_ in ((a0, a1), (c0, c1)):
+        assert (p_.float() - q_.float()).abs().max().item() <= tol * max(1.0, p_.float().abs().max().item())
+        # a mismatching mask bit would flip whole elements: count elements that differ by more than rounding
+        assert ((p_.float() - q_.float()).abs() > 0.05 * p_.float().abs().clamp_min(0.1)).sum().item() == 0
+    bits = ((mask.view(-1, 1) >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).bool().view(-1)
+    kept = (o1.float().view(-1) != 0)
+    z_nonzero = o1.float().view(-1) != 0
+    assert torch.equal(bits[z_nonzero], torch.ones_like(bits[z_nonzero]))     # every surviving output was kept
+    assert abs(bits.float().mean().item() - 0.5) < 0.02 and kept.any()
+
+
 def test_utilities(ctx):
     from m1b200 import ops
     g = _gen(7)
