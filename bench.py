@@ -282,7 +282,12 @@ def run_ours(args):
     # ---- per-kernel-family durations: the same K steps once more, launched eagerly with a CUDA-event pair
     # around every launch family (a replayed graph cannot carry per-launch events)
     model.eng.prof = []
+    ncu_range = os.environ.get("M1_CUDA_PROFILER_RANGE") == "1"     # ncu --profile-from-start off: only this pass
+    if ncu_range:
+        torch.cuda.profiler.start()
     ms_prof = timed(args.steps, dev_step)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     prof, model.eng.prof = model.eng.prof, None
 
     value = world * B * args.steps / (ms / 1e3)

@@ -223,16 +223,77 @@ class Noise:
         return self.t[key]
 
 
+# --------------------------------------------------------------------------------------------
+# bf16-storage emulation (test infrastructure for the product's precision='bf16' mode)
+# --------------------------------------------------------------------------------------------
+# The reference computes in fp32. The product's bf16 mode keeps fp32 arithmetic INSIDE every kernel but stores
+# activations and activation gradients between kernels as bf16 and feeds the tensor cores bf16 weights. With
+# emulate_bf16_storage() the oracle rounds at exactly those storage points (forward values and, through the
+# autograd function below, the gradients that flow back through them), so that the remaining product-vs-oracle
+# difference is summation order only - the deviation of the bf16 mode from the fp32 reference is then shown
+# to be storage precision, not arithmetic.
+_EMU = {'on': False}
+
+
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundBF16Fwd(torch.autograd.Function):      # bf16 operand copy of an fp32 master weight
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _q(x):
+    return _RoundBF16.apply(x) if _EMU['on'] else x
+
+
+def _wq(w):
+    return _RoundBF16Fwd.apply(w) if _EMU['on'] else w
+
+
+class emulate_bf16_storage:
+    """with emulate_bf16_storage(): ... - see above."""
+
+    def __enter__(self):
+        self.prev = _EMU['on']
+        _EMU['on'] = True
+
+    def __exit__(self, *a):
+        _EMU['on'] = self.prev
+
+
+def _fp32_head(name, kinds):
+    """layers the product runs with fp32 weights and fp32 outputs: SE excite (conv6/conv7), the attention psi
+    conv (attX/conv3), the mu/log-sigma heads and every logits head"""
+    leaf = name.rsplit('/', 1)[-1]
+    return (kinds[0] == 'se_kernel' or leaf.startswith('mu_logsig') or leaf.endswith('logits')
+            or (leaf == 'conv3' and '/att' in name))
+
+
 def _conv(ps, name, x, cout, k, s=(1, 1, 1), kinds=('kernel', 'bias')):
     w = ps.get(name + '/kernel', tuple(k) + (x.shape[-1], cout), kinds[0])
     b = ps.get(name + '/bias', (cout,), kinds[1])
-    return conv3d_same(x, w, b, s)
+    if _fp32_head(name, kinds):
+        return conv3d_same(x, w, b, s)
+    return _q(conv3d_same(x, _wq(w), b, s))
 
 
 def _convt(ps, name, x, cout, k, s):
     w = ps.get(name + '/kernel', tuple(k) + (cout, x.shape[-1]), 'kernel')
     b = ps.get(name + '/bias', (cout,), 'bias')
-    return conv3d_transpose_same(x, w, b, s)
+    return _q(conv3d_transpose_same(x, _wq(w), b, s))
 
 
 def _inorm(ps, name, x):
@@ -243,8 +304,8 @@ def _inorm(ps, name, x):
 def se_block(ps, name, x, filters, k, s, reduction):
     """SEResNetBottleNeck.call (R:network_blocks.py:48-80). NOTE Q5: the 'residual addition' is a
     multiplication; Q6: the squeeze sees norm3's output."""
-    a = lrelu(_inorm(ps, name + '/norm1', _conv(ps, name + '/conv1', x, filters // 4, k, s)))
-    b = lrelu(_inorm(ps, name + '/norm2', _conv(ps, name + '/conv2', a, filters // 4, (3, 3, 3))))
+    a = _q(lrelu(_inorm(ps, name + '/norm1', _conv(ps, name + '/conv1', x, filters // 4, k, s))))
+    b = _q(lrelu(_inorm(ps, name + '/norm2', _conv(ps, name + '/conv2', a, filters // 4, (3, 3, 3)))))
     x_ = _inorm(ps, name + '/norm3', _conv(ps, name + '/conv3', b, filters, (1, 1, 1)))
     residual = x
     if x_.shape[-1] != residual.shape[-1]:
@@ -265,8 +326,8 @@ def attention_gate(ps, name, x, g, inter, sub_samp):
     f = lrelu(theta + phi)
     psi = torch.sigmoid(_conv(ps, name + '/conv3', f, 1, (1, 1, 1)))
     psi = upsample_nearest(psi, [x.shape[1 + i] // psi.shape[1 + i] for i in range(3)])
-    y = psi * x
-    wy = _inorm(ps, name + '/norm4', _conv(ps, name + '/conv4', y, inter, (1, 1, 1)))
+    y = _q(psi * x)
+    wy = _q(_inorm(ps, name + '/norm4', _conv(ps, name + '/conv4', y, inter, (1, 1, 1))))
     return wy, psi
 
 
@@ -291,12 +352,14 @@ def m1core(ps, net, cfg, inputs, prob_mean=False, prob_z_q=None, noise=None, pas
     n = lambda s: net + '/' + s  # noqa: E731
 
     def drop(site, t, r=rate):
+        # (the product stores the SE block's output once, AFTER the dropout that always follows it)
         if not drop_on or r == 0.0:
-            return t
-        return dropout(t, r, noise.uniform((pass_name, site), t.shape))
+            return _q(t)
+        return _q(dropout(t, r, noise.uniform((pass_name, site), t.shape)))
 
     out = {}
-    x = lrelu(_inorm(ps, n('norme0'), _conv(ps, n('conve0'), inputs, Fs[0], K[0], S[0])))
+    inputs = _q(inputs)
+    x = _q(lrelu(_inorm(ps, n('norme0'), _conv(ps, n('conve0'), inputs, Fs[0], K[0], S[0]))))
     conv1 = drop('drope1', se_block(ps, n('serse1'), x, Fs[1], K[1], S[1], red[1]))
     conv2 = drop('drope2', se_block(ps, n('serse2'), conv1, Fs[2], K[2], S[2], red[2]))
     conv3 = drop('drope3', se_block(ps, n('serse3'), conv2, Fs[3], K[3], S[3], red[3]))
@@ -372,9 +435,9 @@ def m1core(ps, net, cfg, inputs, prob_mean=False, prob_z_q=None, noise=None, pas
                 if prob_z_q is not None:
                     z = prob_z_q[len(used)]
                 elif prob_mean:
-                    z = mu
+                    z = _q(mu)
                 else:
-                    z = mu + sigma * noise.normal((pass_name, 'eps%d' % lvl), mu.shape)
+                    z = _q(mu + sigma * noise.normal((pass_name, 'eps%d' % lvl), mu.shape))
                 dists.append((mu, sigma))
                 used.append(z)
                 if partial and i == last_lat:

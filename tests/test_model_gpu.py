@@ -51,7 +51,8 @@ def _perturb(ps, seed=17):
                 t.add_(0.2 * torch.randn(t.shape, generator=g).to(t.dtype))
 
 
-def _oracle_step(cfg, x, y, ds_in_prob, dtype=torch.float64, seed=5, round_bf16=False):
+def _oracle_step(cfg, x, y, ds_in_prob, dtype=torch.float64, seed=5, round_bf16=False, emulate=False):
+    import contextlib
     ps = O.ParamStore(dtype=dtype, seed=3, requires_grad=True)
     if round_bf16:
         x = x.bfloat16().float()
@@ -59,8 +60,9 @@ def _oracle_step(cfg, x, y, ds_in_prob, dtype=torch.float64, seed=5, round_bf16=
         O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), O.Noise(0, dtype), ds_in_prob=ds_in_prob)
     _perturb(ps)
     noise = O.Noise(seed, dtype)
-    r = O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0,
-                     ds_in_prob=ds_in_prob)
+    with (O.emulate_bf16_storage() if emulate else contextlib.nullcontext()):
+        r = O.train_loss(ps, cfg, x.to(dtype), y.to(dtype), noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0,
+                         ds_in_prob=ds_in_prob)
     data_loss = r['detection_loss'] + (10.0 * r['KL_loss'] if cfg['probabilistic'] else 0.0)
     data_loss.backward()
     return ps, noise, r
@@ -161,6 +163,41 @@ def test_probabilistic_train_step_bf16_tcgen05(ctx):
     d = (out['detection'] - out2['detection']).abs()
     print(f'tcgen05 vs SIMT (both bf16): mean {d.mean().item():.2e} max {d.max().item():.2e}')
     assert d.mean().item() < 1e-2
+
+
+def test_bf16_mode_equals_bf16_storage_restatement(ctx):
+    """precision='bf16' against the oracle run with emulate_bf16_storage(): the oracle then rounds activations,
+    activation gradients and tensor-core weights to bf16 at the product's storage points, everything else stays
+    the reference arithmetic. What is left is summation order (plus the rare rounding flips it causes), so the
+    agreement must be MUCH tighter than against the fp32 reference - i.e. the bf16 deviation is storage
+    precision, not kernel arithmetic."""
+    model, cfg, x, y = _build(MID, (8, 32, 32), 2, 'bf16', True, True, True)
+    ps, noise, r = _oracle_step(cfg, x, y, 'reference', dtype=torch.float32, round_bf16=True, emulate=True)
+    ps32, noise32, r32 = _oracle_step(cfg, x, y, 'reference', dtype=torch.float32, round_bf16=True)
+    model.set_weights({n: t.detach().float().numpy() for n, t in ps.p.items()})
+    model.set_noise(noise.t)
+    out = model.train_step(x, y, apply_update=False)
+    torch.cuda.synchronize()
+    det = out['detection'].double().cpu()
+    e = (det - r['detection'].detach().double()).abs().flatten()
+    e32 = (det - r32['detection'].detach().double()).abs().flatten()
+    print(f'softmax abs err vs bf16-storage oracle: mean {e.mean().item():.2e} max {e.max().item():.2e} | '
+          f'vs fp32 oracle: mean {e32.mean().item():.2e} max {e32.max().item():.2e}')
+    grads = model.gradients()
+    a = torch.cat([grads[n].double().cpu().flatten() for n in ps.p])
+
+    def cos_with(pstore):
+        b = torch.cat([(t.grad if t.grad is not None else torch.zeros_like(t)).double().flatten()
+                       for t in pstore.p.values()])
+        return (a @ b).item() / (a.norm().item() * b.norm().item())
+    c_emu, c_32 = cos_with(ps), cos_with(ps32)
+    print(f'grad cosine vs bf16-storage oracle {c_emu:.5f} | vs fp32 oracle {c_32:.5f}')
+    assert e.max().item() < 2e-2, e.max().item()                       # the north star's bf16 bound
+    assert e.mean().item() < 0.5 * e32.mean().item()
+    assert abs(out['focal'].item() - r['detection_loss'].item()) < 1e-3 * abs(r['detection_loss'].item())
+    assert abs(out['kl'].item() - r['KL'].item()) < 2e-3 * abs(r['KL'].item())
+    assert c_emu >= 0.99, c_emu
+    assert c_emu > c_32
 
 
 def test_adam_update_and_second_step(ctx):

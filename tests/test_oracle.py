@@ -228,3 +228,26 @@ def test_orthogonal_init_is_orthogonal():
     assert np.allclose(w.T @ w, np.eye(8), atol=1e-10)
     b = O.init_truncated_normal((1000,), 1e-3, 0)
     assert np.abs(b).max() <= 2e-3
+
+
+def test_bf16_storage_emulation_switch():
+    """emulate_bf16_storage(): off = bit-identical to the plain oracle; on = values and gradients rounded at the
+    product's storage points (every stored activation is then exactly representable in bf16)."""
+    cfg = O.default_config(probabilistic=False, dense_skip=False, deep_supervision=False,
+                           dropout_mode='monte-carlo', **TINY)
+    x, y = O.synthetic_batch(1, (4, 16, 16), probabilistic=False, seed=2)
+    ps = O.ParamStore(dtype=torch.float32, seed=1, requires_grad=True)
+    r0 = O.train_loss(ps, cfg, x, y, O.Noise(3, torch.float32))
+    r1 = O.train_loss(ps, cfg, x, y, O.Noise(3, torch.float32))
+    assert torch.equal(r0['detection'], r1['detection'])
+    with O.emulate_bf16_storage():
+        r2 = O.train_loss(ps, cfg, x, y, O.Noise(3, torch.float32))
+        t = O._q(torch.tensor([1.0 + 2 ** -10, 3.14159], requires_grad=True))
+        assert torch.equal(t.detach(), t.detach().bfloat16().float())
+        t.sum().backward()
+    r3 = O.train_loss(ps, cfg, x, y, O.Noise(3, torch.float32))
+    assert torch.equal(r0['detection'], r3['detection'])           # the switch is restored
+    d = (r2['detection'] - r0['detection']).abs().max().item()
+    assert 0 < d < 5e-2, d
+    r2['loss'].backward()
+    assert all(torch.isfinite(p.grad).all() for p in ps.p.values() if p.grad is not None)

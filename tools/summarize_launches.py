@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) per kernel: launches, total
-time, share of the captured window. Usage: summarize_launches.py launches.csv > summary.md"""
+time, share of the captured window. Usage: summarize_launches.py launches.csv [last N launches] > summary.md"""
 import csv
 import re
 import sys
 from collections import defaultdict
 
 
-def main(path):
+def main(path, last=None):
     rows = []
     with open(path, newline='') as fh:
         lines = [ln for ln in fh if not ln.startswith('==')]
@@ -24,6 +24,8 @@ def main(path):
         name = (m.group(1) + (m.group(2) or '')) if m else name
         name = name if len(name) < 70 else name[:67] + '...'
         rows.append((name, val * scale))
+    if last:
+        rows = rows[-int(last):]        # e.g. the launches of the final (eager, profiled) step of bench.py
     tot = sum(t for _, t in rows)
     agg = defaultdict(lambda: [0, 0.0])
     for n, t in rows:
@@ -37,4 +39,4 @@ def main(path):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
