@@ -11,8 +11,9 @@ arch = T.TINY if prec == 'fp32' else T.MID
 dims = (8, 32, 32) if prec == 'fp32' else (8, 32, 32)
 tc = (sys.argv[2] != 'notc') if len(sys.argv) > 2 else True
 model, cfg, x, y = T._build(arch, dims, 2, prec, True, True, True, use_tcgen05=tc)
+emu = len(sys.argv) > 3 and sys.argv[3] == 'emu'
 ps, noise, r = T._oracle_step(cfg, x, y, 'reference', dtype=torch.float64 if prec == 'fp32' else torch.float32,
-                              round_bf16=prec != 'fp32')
+                              round_bf16=prec != 'fp32', emulate=emu)
 model.set_weights({n: t.detach().float().numpy() for n, t in ps.p.items()})
 model.set_noise(noise.t)
 out = model.train_step(x, y, apply_update=False)
@@ -40,6 +41,9 @@ import torch as _t
 A = _t.cat([grads[n].double().cpu().flatten() for n in ps.p]); Bv = _t.cat([(t.grad if t.grad is not None else _t.zeros_like(t)).double().flatten() for t in ps.p.values()])
 print('GLOBAL COS', (A @ Bv).item() / (A.norm().item() * Bv.norm().item()))
 rows.sort(key=lambda r: -r[4])
+import statistics
+cs = [r[0] for r in rows if r[0] == r[0]]
+print('per-tensor cosine: median %.5f  p10 %.5f  min %.5f  (n=%d)' % (statistics.median(cs), sorted(cs)[len(cs) // 10], min(cs), len(cs)))
 print('largest abs diffs:')
 for cos, n, na, nb, d in rows[:15]:
     print(f'{cos:9.5f} {n:45s} |ours| {na:.3e} |ref| {nb:.3e} |diff| {d:.3e}')
