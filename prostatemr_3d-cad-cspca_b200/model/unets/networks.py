@@ -460,7 +460,8 @@ class M1(LoadableModel):
     # the whole step - forward, losses, backward, gradient all-reduce, Adam, weight re-pack - is captured
     # once into a CUDA graph over static input buffers and replayed. Everything that changes per step lives
     # in device memory: the Philox step counter (m1_dropout.step / m1_philox_normal_step) and the Adam step
-    # size (m1_adam_amsgrad_dev), both written by a tiny fill launch before the replay.
+    # size (m1_adam_amsgrad_dev), both written by a tiny fill launch before the replay. No collective is ever
+    # captured: data-parallel runs all-reduce the flat gradient buffer between the two graphs of a step.
     GRAPH_WARMUP = 2
 
     def _graph_ok(self, apply_update):
@@ -490,19 +491,23 @@ class M1(LoadableModel):
             st['x'].copy_(x); st['y'].copy_(y)
             st['step'].fill_(self.noise.step); st['lr'].fill_(self.optimizer.lr_t())
             torch.cuda.synchronize(self.device)
-            graph = torch.cuda.CUDAGraph()
+            # two graphs: [forward, losses, backward] and [Adam, weight re-pack]. In data-parallel runs the
+            # gradient all-reduce is issued between the two replays, OUTSIDE any capture (one NCCL call on
+            # the flat gradient buffer: 256 MB, ~1 ms over NVLink, against ~85 ms of kernels).
+            g_bwd, g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             self.noise.step_dev, self._lr_dev = st['step'], st['lr']
             before = self.eng.ctx.launch_count()
             try:
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(g_bwd):
                     st['out'] = self._train_step_eager(st['x'], st['y'], True, graphed=True)
+                with torch.cuda.graph(g_upd, pool=g_bwd.pool()):
+                    self._apply_update(st['out']['l2'], 1.0 / self.world_size, graphed=True)
             except Exception:
-                self.noise.step_dev, self._lr_dev = None, None
                 self._graph_failed = True
                 raise
             finally:
                 self.noise.step_dev, self._lr_dev = None, None
-            st['graph'] = graph
+            st['graph'], st['graph_update'] = g_bwd, g_upd
             st['launches'] = self.eng.ctx.launch_count() - before
             self._gs = st
         else:
@@ -511,6 +516,11 @@ class M1(LoadableModel):
         st['step'].fill_(self.noise.step)
         st['lr'].fill_(self.optimizer.lr_t())
         st['graph'].replay()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.params.g, op=dist.ReduceOp.SUM,
+                            group=self.grad_sync.group if self.grad_sync is not None else None)
+        st['graph_update'].replay()
         self.graph_replays = getattr(self, "graph_replays", 0) + 1
         self.optimizer.iterations += 1
         self.noise.step += 1
@@ -574,13 +584,13 @@ class M1(LoadableModel):
                 eng.kl(ml_q, ml_p, scal[1:2])
                 eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
         eng._timed("losses", 0, losses)
-        if self.grad_sync is not None:
+        if self.grad_sync is not None and not graphed:
             self.grad_sync.begin(self.params.g, eng.param_uses)
             eng.backward(self.grad_sync.param_done)
             self.grad_sync.finish()
         else:
             eng.backward()
-        if apply_update:
+        if apply_update and not graphed:
             eng._timed("adam+repack", 0, lambda: self._apply_update(scal[2:3], inv_r, graphed))
         if isinstance(self.noise, PhiloxNoise) and not graphed:
             self.noise.step += 1
