@@ -324,7 +324,11 @@ def run_ours(args):
         fl, t_ms, n = cats[dom]
         ach = (fl / 1e12) / (t_ms / 1e3)
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak_tf, "traffic": None,
+                    "traffic_note": "per-launch DRAM bytes of the family's largest launches are in "
+                                    "profiles/r01_summary.md (ncu --set full): sersp2 wgrad 0.56 GB vs 0.35 GB "
+                                    "algorithmic; the family mixes 168 launch shapes, so no single figure applies",
+                    "peak_source": peak_src,
                     "share_of_step": t_ms / sum(v[1] for v in cats.values()), "flop_per_launch_avg": fl / n,
                     "timed_with": "CUDA events around every launch family in an eager re-run of the same %d steps "
                                   "(%.2f ms/step; the headline replays the step as a CUDA graph)"
