@@ -16,6 +16,14 @@
 // A CTA owns one (tap group, M tile, N tile) and a slab of voxel bricks (split-K); the taps of a
 // group differ only in kw and share the B blocks (one accumulator per tap in TMEM); partial dW tiles
 // are added to the fp32 gradient with atomics (shared weights accumulate over passes anyway).
+//
+// SHIFT mode (m1_conv_desc.tune[1] == 2; stride 1, kw == 3): the three kw taps of a group also share ONE
+// activation box. A brick is bh full-width lines loaded with a row pitch P >= W + 2 for BOTH operands
+// (bh * P % 16 == 0): the X box starts at w = -1, the dY box at w = 0, columns beyond the volume are
+// zero-filled by TMA. Row q of dY then pairs with row q + c of X for tap c - a row shift of the MN-major
+// UMMA descriptor (tcgen05 swizzles on absolute address bits, tools/probe_umma_shift.cu). dY rows whose
+// column is >= W are zero, so the halo rows of X (and the up to two rows read past a block, kept finite by
+// zeroed pad rows) contribute nothing. TMA lines of X per brick: one third of the per-tap scheme.
 #include "tc_common.cuh"
 #include <algorithm>
 #include <cmath>
@@ -46,6 +54,8 @@ struct WgParams {
   int kd, kh, kw, pd, ph, pw;
   int sd, sh, sw;                // FWD stride: A boxes are loaded with TMA element strides
   int tpg;                       // taps per group (1 or kw)
+  int shift;                     // SHIFT mode: the tpg taps read ONE X box at row shifts 0..tpg-1
+  uint32_t a_box_bytes;          // bytes TMA writes per X block (a_blk_bytes minus the pad rows in SHIFT mode)
   int mpg;                       // M tiles (of 128 rows) per CTA: they share the dY tile of a stage
   int bd, bh, bw, td, th, tw;    // brick, bricks per dim
   int batch;
@@ -113,6 +123,18 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     mbar_init(bar_accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (p.shift) {
+    // pad rows behind every X block (read by the shifted descriptors of taps 1, 2; never written by TMA)
+    const uint32_t pad = p.a_blk_bytes - p.a_box_bytes;                  // 8 rows
+    const uint32_t blocks_per_stage = p.b_off / p.a_blk_bytes;
+    for (int s = 0; s < p.stages; ++s)
+      for (uint32_t b = 0; b < blocks_per_stage; ++b) {
+        uint8_t* q = smem_gen + 1024u + s * p.stage_bytes + b * p.a_blk_bytes + p.a_box_bytes;
+        for (uint32_t i = threadIdx.x * 16u; i < pad; i += kThreads * 16u)
+          *reinterpret_cast<uint4*>(q + i) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -132,7 +154,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
         int tot_blk = 0;
         for (int mi = 0; mi < msub; ++mi)
           tot_blk += min(p.blocks_per_tile, p.nblocks - (mt * p.mpg + mi) * p.blocks_per_tile);
-        const uint32_t tx = (uint32_t)(p.tpg * tot_blk) * p.a_blk_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes;
+        const int a_slots = p.shift ? 1 : p.tpg;             // X boxes per block: one per tap, or one shared
+        const uint32_t tx = (uint32_t)(a_slots * tot_blk) * p.a_box_bytes + (uint32_t)p.n_blocks * p.b_blk_bytes;
         const int nb0 = n0 / p.cb;
         for (int it = 0; it < iters; ++it) {
           const int d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
@@ -143,12 +166,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
           } else {
             mbar_expect_tx(full, tx);
             const uint32_t sbase = tiles + stage * p.stage_bytes;
+            // (SHIFT mode: tpg == kw, kw0 == 0 - the one shared X box sits at tap c = 0, one column left of dY)
             const int aw = w0 * p.sw - p.pw, ah = h0 * p.sh - p.ph, ad = d0 * p.sd - p.pd;
             uint32_t dst = sbase;
             for (int mi = 0; mi < msub; ++mi) {
               const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
               const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
-              for (int tp = 0; tp < p.tpg; ++tp) {
+              for (int tp = 0; tp < a_slots; ++tp) {
                 uint32_t dj = dst;
                 for (int j = 0; j < nblk; ++j) {
                   const int blk = blk0 + j;
@@ -186,25 +210,29 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
         const uint64_t a_hi = (uint64_t)p.a_desc_hi << 32, b_hi = (uint64_t)p.b_desc_hi << 32;
         const uint32_t a_kstep = (16u * p.ck * 2u) >> 4, b_kstep = (16u * p.cb * 2u) >> 4;
         const uint32_t a_tap16 = p.a_tap_bytes >> 4;
+        const uint32_t a_row16 = (2u * p.ck) >> 4;           // SHIFT mode: tap c reads the shared box c rows further
         const uint32_t a_lbo = p.a_lbo << 16, b_lbo = p.b_lbo << 16;
         const int k16s = p.kv / 16;
-        const int nacc = msub * p.tpg;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_full + 8u * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = tiles + stage * p.stage_bytes;
           const uint32_t b0 = ((sbase + p.b_off) >> 4) | b_lbo;
-          uint32_t a_t = (sbase >> 4) | a_lbo;
+          uint32_t a_m = (sbase >> 4) | a_lbo;
           uint32_t d_t = tmem_base;
-          for (int at = 0; at < nacc; ++at) {       // accumulator = (M sub-tile, tap)
-            uint32_t a_k = a_t, b_k = b0;
-            umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, it ? 1u : 0u);
-            for (int k = 1; k < k16s; ++k) {
-              a_k += a_kstep; b_k += b_kstep;
-              umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, 1u);
+          for (int mi = 0; mi < msub; ++mi) {
+            uint32_t a_t = a_m;
+            for (int tp = 0; tp < p.tpg; ++tp) {   // accumulator = (M sub-tile, tap)
+              uint32_t a_k = a_t, b_k = b0;
+              umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, it ? 1u : 0u);
+              for (int k = 1; k < k16s; ++k) {
+                a_k += a_kstep; b_k += b_kstep;
+                umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, 1u);
+              }
+              a_t += p.shift ? a_row16 : a_tap16;
+              d_t += (uint32_t)p.n_tile;
             }
-            a_t += a_tap16;
-            d_t += (uint32_t)p.n_tile;
+            a_m += p.shift ? a_tap16 : a_tap16 * (uint32_t)p.tpg;
           }
           umma_commit(bar_empty + 8u * stage);
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -252,7 +280,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
 }
 
 struct WgPlan {
-  int taps_in_m, mpg;
+  int taps_in_m, mpg, shift;
+  uint32_t a_box_bytes;
   int ck, cb, n_tile, n_blocks, tpg, kv, bd, bh, bw, td, th, tw, stages, nblocks, cin_total;
   uint32_t a_blk_bytes, b_blk_bytes, a_tap_bytes, b_off, stage_bytes, smem_bytes, tmem_cols;
 };
@@ -323,6 +352,48 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
   const int env_tpg = d->tune[1] ? d->tune[1] : g_tpg;
   const int env_stages = d->tune[2] ? d->tune[2] : (g_stages ? g_stages : 2);
   if (env_tpg == 1) tpg = 1;
+  pl->shift = 0;
+  if (env_tpg == 2) {
+    // ---- SHIFT mode: bh full-width lines at row pitch P >= W + 2 for both operands, bh * P % 16 == 0
+    if (taps_in_m || d->kernel[2] != 3 || d->pad[2] != 1 || tpg != 3) return false;
+    for (int i = 0; i < 3; ++i)
+      if (d->stride[i] != 1) return false;
+    const int kv_cap = env_kv ? std::max(env_kv, 48) : 192;
+    double best = -1;
+    int bP = 0, bbh = 0;
+    for (int P = W + 2; P <= std::min(256, W + 2 + 15); ++P)
+      for (int bh = 1; bh <= H && bh * P <= kv_cap; ++bh) {
+        if ((bh * P) % 16) continue;
+        const int th = (H + bh - 1) / bh;
+        const double eff = (double)W * H / ((double)P * bh * th);          // useful K rows / issued K rows
+        const double score = eff + 1e-3 * (bh * P) / kv_cap;
+        if (score > best) { best = score; bP = P; bbh = bh; }
+      }
+    if (best < 0) return false;
+    const int kv = bbh * bP;
+    int mpg = mpg_req;
+    while (mpg > 1 && mpg * tpg * n_tile > 512) --mpg;
+    const uint32_t a_box = (uint32_t)kv * ck * 2u, a_blk = a_box + 8u * ck * 2u, b_blk = (uint32_t)kv * cb * 2u;
+    const uint32_t a_tap = (128u / ck) * a_blk;
+    const uint32_t b_off = (uint32_t)mpg * a_tap;
+    const uint32_t stage = (b_off + (uint32_t)(n_tile / cb) * b_blk + 1023u) & ~1023u;
+    int stages = (int)((227u * 1024u - 2048u) / stage);
+    const int cap = d->tune[2] ? d->tune[2] : (g_stages ? g_stages : 4);
+    if (stages > cap) stages = cap;
+    if (stages < 2) return false;
+    pl->shift = 1; pl->a_box_bytes = a_box;
+    pl->ck = ck; pl->cb = cb; pl->n_tile = n_tile; pl->n_blocks = n_tile / cb; pl->tpg = tpg; pl->kv = kv;
+    pl->bd = 1; pl->bh = bbh; pl->bw = bP;
+    pl->td = D; pl->th = (H + bbh - 1) / bbh; pl->tw = 1;
+    pl->stages = stages; pl->nblocks = cin / ck; pl->cin_total = cin;
+    pl->taps_in_m = 0; pl->mpg = mpg;
+    pl->a_blk_bytes = a_blk; pl->b_blk_bytes = b_blk; pl->a_tap_bytes = a_tap; pl->b_off = b_off;
+    pl->stage_bytes = stage; pl->smem_bytes = 2048u + (uint32_t)stages * stage;
+    uint32_t cols = 32;
+    while ((int)cols < tpg * mpg * n_tile) cols <<= 1;
+    pl->tmem_cols = cols;
+    return true;
+  }
   for (int kv_max = env_kv ? env_kv : 128; kv_max >= 16; kv_max >>= 1) {
     int bd = 1, bh = 1, bw = 1;
     if (!pick(kv_max, &bd, &bh, &bw)) continue;
@@ -344,6 +415,7 @@ bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
       pl->stages = stages; pl->nblocks = taps_in_m ? ntaps : cin / ck; pl->cin_total = cin;
       pl->taps_in_m = taps_in_m ? 1 : 0;
       pl->mpg = mpg;
+      pl->a_box_bytes = a_blk;
       pl->a_blk_bytes = a_blk; pl->b_blk_bytes = b_blk; pl->a_tap_bytes = a_tap; pl->b_off = b_off;
       pl->stage_bytes = stage; pl->smem_bytes = 2048u + (uint32_t)stages * stage;
       uint32_t cols = 32;
@@ -432,6 +504,8 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.sd = d->stride[0]; p.sh = d->stride[1]; p.sw = d->stride[2];
   p.tpg = pl.tpg;
   p.mpg = pl.mpg;
+  p.shift = pl.shift;
+  p.a_box_bytes = pl.a_box_bytes;
   p.bd = pl.bd; p.bh = pl.bh; p.bw = pl.bw; p.td = pl.td; p.th = pl.th; p.tw = pl.tw;
   p.batch = d->batch;
   p.kv = pl.kv;

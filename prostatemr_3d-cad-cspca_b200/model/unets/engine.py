@@ -310,6 +310,9 @@ class Engine:
     WG_CANDIDATES = ((128, 0, 2, 1), (128, 1, 2, 1), (64, 0, 2, 1), (64, 1, 2, 1), (128, 0, 3, 1), (64, 0, 3, 1),
                      (64, 0, 4, 1), (64, 1, 4, 1), (128, 1, 3, 1), (128, 1, 2, 2), (64, 1, 2, 2), (64, 0, 2, 2))
 
+    # SHIFT-mode tilings of the weight-gradient kernel (tune[1] == 2; M1_WG_SHIFT=0 removes them)
+    WG_SHIFT_CANDIDATES = ((192, 2, 3, 1), (192, 2, 2, 1), (96, 2, 4, 1), (192, 2, 2, 2))
+
     def _wgrad(self, d, srcs_t, douts_t, dws, dbs, fl, label=None):
         on_tc = self.use_tc and ops.conv3d_wgrad_tc_supported(d)
         if on_tc and self.autotune:
@@ -354,7 +357,11 @@ class Engine:
         scratch gradient buffers (CUDA events) and keep the fastest."""
         scratch = [torch.zeros(w.numel(), dtype=torch.float32, device=self.device) for w in dws]
         best, best_t = (0, 0, 0, 0), float("inf")
-        for cand in self.WG_CANDIDATES:
+        import os
+        cands = self.WG_CANDIDATES
+        if os.environ.get("M1_WG_SHIFT", "1") == "1":
+            cands = cands + self.WG_SHIFT_CANDIDATES
+        for cand in cands:
             d.tune[0], d.tune[1], d.tune[2], d.tune[3] = cand
             if not ops.conv3d_wgrad_tc_supported(d):
                 continue

@@ -512,3 +512,41 @@ def test_conv_dgrad_halo(ctx, dhw, couts, cins, k):
         ref = x_.grad + (prior.double() if i == 0 else 0)
         err = (b.double().cpu() - ref).abs().max().item()
         assert err < 3e-2 * max(1.0, ref.abs().max().item()), (i, err)
+
+
+@pytest.mark.parametrize("dhw,cins,couts,k", [((4, 16, 16), [128], [64], (3, 3, 3)),
+                                              ((6, 20, 20), [128, 128, 64], [128], (3, 3, 3)),
+                                              ((4, 16, 32), [32, 32, 32, 32, 32], [32], (1, 3, 3)),
+                                              ((5, 10, 10), [256], [64, 64], (3, 3, 3)),
+                                              ((3, 13, 40), [64, 32], [16, 64], (3, 3, 3)),     # fused outputs, ragged H
+                                              ((2, 9, 44), [128], [32, 128], (1, 3, 3))])
+def test_conv_wgrad_tcgen05_shift_mode(ctx, dhw, cins, couts, k):
+    """SHIFT mode of the weight-gradient kernel (tune[1] = 2): the kw taps share one activation box through
+    row-shifted MN-major descriptors; full-width lines at a common row pitch, zero-filled halo columns."""
+    from m1b200 import ops, _lib
+    g = torch.Generator().manual_seed(19)
+    cin = sum(cins)
+    xs = [torch.randn((2, *dhw, c), generator=g).bfloat16().double() for c in cins]
+    ws = [torch.zeros((*k, cin, co), dtype=torch.float64, requires_grad=True) for co in couts]
+    x = torch.cat(xs, -1)
+    dys = []
+    for w in ws:
+        y = O.conv3d_same(x, w, None, (1, 1, 1))
+        dy = torch.randn(y.shape, generator=g).bfloat16().double()
+        y.backward(dy)
+        dys.append(dy)
+    dev = 'cuda'
+    pad = [ops.same_pads(dhw[i], k[i], 1)[1] for i in range(3)]
+    d = ops.conv_desc(_lib.CONV_FWD, 2, dhw, dhw, k, (1, 1, 1), pad, cins, couts,
+                      [(cin * co, co, 1) for co in couts], act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
+    d.tune[1] = 2
+    assert ops.conv3d_wgrad_tc_supported(d), "SHIFT mode refused the launch"
+    dws = [torch.full(w.shape, 0.5, device=dev) for w in ws]
+    ops.conv3d_wgrad(ctx, d, [t.to(dev, torch.bfloat16).contiguous() for t in xs],
+                     [t.to(dev, torch.bfloat16).contiguous() for t in dys], dws, None)
+    torch.cuda.synchronize()
+    for w, dw in zip(ws, dws):
+        ref = w.grad + 0.5
+        scale = max(1.0, ref.abs().max().item())
+        assert torch.isfinite(dw).all()
+        assert (dw.double().cpu() - ref).abs().max().item() < 2e-3 * scale
