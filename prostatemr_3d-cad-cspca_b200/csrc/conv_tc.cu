@@ -24,7 +24,9 @@
 // Both land in shared memory in the canonical K-major swizzled UMMA layout (rows of ck*2 bytes,
 // 8-row swizzle atoms), so one tcgen05.mma per 16 channels consumes them with no data movement
 // by threads.  One CTA = one M tile x one N tile; several CTAs are co-resident per SM so that the
-// epilogue of one overlaps the main loop of another.
+// epilogue of one overlaps the main loop of another. Warp 0 = elected TMA producer, warp 1 = elected MMA
+// issuer (elect.sync, see tc_common.cuh), all 8 warps run the epilogue (tc_epilogue.cuh). Stride-1 launches
+// with in-plane taps may be routed to the halo variant (conv_tc_halo.cu) - m1_conv_desc.tune[0].
 #include "tc_epilogue.cuh"
 
 namespace {

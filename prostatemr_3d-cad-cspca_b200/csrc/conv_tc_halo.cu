@@ -3,8 +3,9 @@
 // in-plane taps.
 //
 // conv_tc.cu loads one 128-voxel TMA box per (tap, channel chunk): every activation byte crosses L2->SM
-// kh*kw times, and the full-resolution layers of M1 (R:network_blocks.py:37-46 at 160x160 / 80x80) sit
-// on the L2 throughput cap. Here the M tile is 128 consecutive rows of a LINEARISED halo tile:
+// kh*kw times, and TMA throughput is per LINE (<= 128 B inner run, ~2 cycles each), so the few-channel /
+// full-resolution layers of M1 (R:network_blocks.py:37-46 at 160x160 / 80x80) are bound by the number of
+// boxes they issue, not by the tensor cores. Here the M tile is 128 consecutive rows of a LINEARISED halo tile:
 //   - the A box of a (plane, channel chunk) is the (L = G*bh + kh-1) x (P = bw + kw-1) voxel halo
 //     rectangle around G stacked sub-tiles of bh x bw output voxels, rows in (line, column) order,
 //     P rows per line, canonical K-major swizzled layout as written by TMA (OOB zero fill == SAME pad);

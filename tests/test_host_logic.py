@@ -138,3 +138,52 @@ def test_dlpack_pointer_export_rejects_cpu_memory():
     assert _lib.dlpack_device_ptr(t, expect_cuda=False) == t.data_ptr()
     v = torch.arange(64, dtype=torch.float32)[16:32]
     assert _lib.dlpack_device_ptr(v, expect_cuda=False) == v.data_ptr()
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of m1_conv_desc / m1_dropout have the size and field offsets gcc gives the C structs
+    of include/m1b200.h (a drifted binding would silently corrupt every launch)."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "m1b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(m1_conv_desc), offsetof(m1_conv_desc, src_c),\n'
+        '         offsetof(m1_conv_desc, w_stride_tap), offsetof(m1_conv_desc, w_by_src),\n'
+        '         offsetof(m1_conv_desc, accumulate), offsetof(m1_conv_desc, engine), offsetof(m1_conv_desc, tune));\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(m1_dropout), offsetof(m1_dropout, seed),\n'
+        '         offsetof(m1_dropout, stream_id), offsetof(m1_dropout, rate), offsetof(m1_dropout, step),\n'
+        '         offsetof(m1_dropout, mask));\n'
+        '  printf("%llu\\n", (unsigned long long)M1_PHILOX_STEP_STRIDE);\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    inc = os.path.dirname(_lib.HEADER_PATH)
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    cd, dr = _lib.ConvDesc, _lib.Dropout
+    assert [int(v) for v in out[0].split()] == [ctypes.sizeof(cd), cd.src_c.offset, cd.w_stride_tap.offset,
+                                                cd.w_by_src.offset, cd.accumulate.offset, cd.engine.offset,
+                                                cd.tune.offset]
+    assert [int(v) for v in out[1].split()] == [ctypes.sizeof(dr), dr.seed.offset, dr.stream_id.offset,
+                                                dr.rate.offset, dr.step.offset, dr.mask.offset]
+    assert int(out[2]) == 4096
+
+
+def test_philox_streams_eager_and_graph_agree():
+    """PhiloxNoise: the stream id of an eager step equals the captured-graph stream id plus
+    step * M1_PHILOX_STEP_STRIDE (added on the device from the step counter), for every (pass, site)."""
+    from m1b200.model.unets.engine import PhiloxNoise
+    n = PhiloxNoise(seed=7, rank=1)
+    seen = set()
+    for step in (0, 5, 123):
+        for p in PhiloxNoise.PASSES:
+            for s in PhiloxNoise.SITES:
+                n.step, n.step_dev = step, None
+                eager = n._stream(p, s)
+                n.step_dev = object()                      # capturing: the step term moves to the device
+                graph = n._stream(p, s)
+                assert eager == graph + step * 4096
+                assert 0 <= graph < 4096
+                seen.add(eager)
+    assert len(seen) == 3 * len(PhiloxNoise.PASSES) * len(PhiloxNoise.SITES)        # no collisions
+    assert PhiloxNoise(seed=7, rank=0).seed != n.seed                              # ranks draw different noise
