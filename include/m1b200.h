@@ -89,6 +89,13 @@ int  m1_ctx_destroy(m1_ctx* ctx);
 int64_t m1_ctx_launch_count(m1_ctx* ctx, int reset);
 /* 1 if the tcgen05 engine can take this launch (shape/dtype constraints), else 0 */
 int  m1_conv3d_tc_supported(const m1_conv_desc* d);
+/* Tiling the tcgen05 engines would use for d (host-side planning only, no GPU needed): which = 0 per-tap
+ * convolution {ck, n_tile, n_tiles, bd, bh, bw, stages, k-steps per stage, smem bytes, TMEM columns, CTAs},
+ * 1 halo convolution {ck, n_tile, n_tiles, G, bh, bw, P, L, stages, smem bytes, TMEM columns, CTAs per SM,
+ * stage bytes, activation-tile bytes}, 2 weight gradient {ck, cb, n_tile, taps per group, M tiles per CTA,
+ * voxels per brick, bd, bh, bw, stages, smem bytes, TMEM columns, shift mode, taps-in-M, stage bytes}.
+ * Returns the number of values written to out (>= 16 slots), 0 if the engine does not take the launch. */
+int  m1_conv3d_plan_info(const m1_conv_desc* d, int which, int32_t* out);
 /* 1 if m1_conv3d would run this launch on the halo variant of the tcgen05 engine (honours d->tune[0]) */
 int  m1_conv3d_halo_engine(const m1_conv_desc* d);
 

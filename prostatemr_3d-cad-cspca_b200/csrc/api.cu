@@ -67,3 +67,11 @@ extern "C" int m1_conv3d(m1_ctx* ctx, const m1_conv_desc* d, const void* const* 
   M1_CHECK(w != nullptr, "m1_conv3d: SIMT engine needs the fp32 master weights");
   return m1_conv3d_simt(ctx, d, srcs, w, bias, outs, st);
 }
+
+extern "C" int m1_conv3d_plan_info(const m1_conv_desc* d, int which, int32_t* out) {
+  if (!d || !out) return 0;
+  if (which == 0) return m1_conv3d_tc_plan_info(d, out);
+  if (which == 1) return m1_conv3d_halo_plan_info(d, out);
+  if (which == 2) return m1_conv3d_wgrad_plan_info(d, out);
+  return 0;
+}

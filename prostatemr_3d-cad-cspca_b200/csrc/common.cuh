@@ -166,6 +166,9 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                  const void* w_packed, const float* const* bias, void* const* outs,
                  cudaStream_t st);
 int m1_conv3d_halo_supported(const m1_conv_desc* d, int* preferred);
+int m1_conv3d_tc_plan_info(const m1_conv_desc* d, int32_t* out);
+int m1_conv3d_halo_plan_info(const m1_conv_desc* d, int32_t* out);
+int m1_conv3d_wgrad_plan_info(const m1_conv_desc* d, int32_t* out);
 int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, const void* w_packed,
                    const float* const* bias, void* const* outs, cudaStream_t st);
 int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j0, int jn);

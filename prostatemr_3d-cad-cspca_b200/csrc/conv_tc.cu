@@ -379,6 +379,17 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   return 0;
 }
 
+// which = 0: per-tap engine. out: ck, n_tile, n_tiles, bd, bh, bw, stages, group, smem_bytes, tmem_cols, ctas
+int m1_conv3d_tc_plan_info(const m1_conv_desc* d, int32_t* out) {
+  Plan pl;
+  if (!make_plan(d, &pl)) return 0;
+  const int32_t v[11] = {pl.ck, pl.n_tile, pl.n_tiles, pl.bd, pl.bh, pl.bw, pl.stages, pl.group,
+                         (int32_t)pl.smem_bytes, (int32_t)pl.tmem_cols,
+                         (int32_t)((int64_t)d->batch * pl.td * pl.th * pl.tw * pl.n_tiles * pl.nphase)};
+  for (int i = 0; i < 11; ++i) out[i] = v[i];
+  return 11;
+}
+
 extern "C" int m1_conv3d_halo_engine(const m1_conv_desc* d) {
   int pref = 0;
   if (d->tune[0] == 1 || !m1_conv3d_halo_supported(d, &pref)) return 0;

@@ -310,6 +310,17 @@ int m1_conv3d_halo_supported(const m1_conv_desc* d, int* preferred) {
   return 1;
 }
 
+// out: ck, n_tile, n_tiles, G, bh, bw, P, L, stages, smem_bytes, tmem_cols, ctas_per_sm, stage_bytes, a_alloc
+int m1_conv3d_halo_plan_info(const m1_conv_desc* d, int32_t* out) {
+  HaloPlan pl;
+  if (!make_halo_plan(d, &pl)) return 0;
+  const int32_t v[14] = {pl.ck, pl.n_tile, pl.n_tiles, pl.G, pl.bh, pl.bw, pl.P, pl.L, pl.stages,
+                         (int32_t)pl.smem_bytes, (int32_t)pl.tmem_cols, pl.ctas_per_sm, (int32_t)pl.stage_bytes,
+                         (int32_t)pl.a_alloc};
+  for (int i = 0; i < 14; ++i) out[i] = v[i];
+  return 14;
+}
+
 int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, const void* w_packed,
                    const float* const* bias, void* const* outs, cudaStream_t st) {
   HaloPlan pl;

@@ -434,6 +434,17 @@ int m1_conv3d_wgrad_tc_supported(const m1_conv_desc* d, int j0, int jn) {
   return make_wg_plan(d, j0, jn, &pl) ? 1 : 0;
 }
 
+// out: ck, cb, n_tile, tpg, mpg, kv, bd, bh, bw, stages, smem_bytes, tmem_cols, shift, taps_in_m, stage_bytes
+int m1_conv3d_wgrad_plan_info(const m1_conv_desc* d, int32_t* out) {
+  WgPlan pl;
+  if (!make_wg_plan(d, 0, d->nout, &pl) && !make_wg_plan(d, 0, 1, &pl)) return 0;
+  const int32_t v[15] = {pl.ck, pl.cb, pl.n_tile, pl.tpg, pl.mpg, pl.kv, pl.bd, pl.bh, pl.bw, pl.stages,
+                         (int32_t)pl.smem_bytes, (int32_t)pl.tmem_cols, pl.shift, pl.taps_in_m,
+                         (int32_t)pl.stage_bytes};
+  for (int i = 0; i < 15; ++i) out[i] = v[i];
+  return 15;
+}
+
 extern "C" int m1_conv3d_wgrad_tc_supported0(const m1_conv_desc* d) {
   return m1_conv3d_wgrad_tc_supported(d, 0, d->nout) || m1_conv3d_wgrad_tc_supported(d, 0, 1);
 }

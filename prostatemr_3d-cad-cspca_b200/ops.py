@@ -68,6 +68,14 @@ def conv3d_halo_engine(d):
     return bool(lib().m1_conv3d_halo_engine(C.byref(d)))
 
 
+def conv3d_plan_info(d, which):
+    """Tiling of the tcgen05 engines for d (0 per-tap conv, 1 halo conv, 2 weight gradient) as a list of ints;
+    [] if the engine does not take the launch. Pure host-side planning: works without a GPU."""
+    out = (C.c_int32 * 16)()
+    n = lib().m1_conv3d_plan_info(C.byref(d), which, out)
+    return [int(out[i]) for i in range(n)]
+
+
 def conv3d_wgrad_tc_supported(d):
     return bool(lib().m1_conv3d_wgrad_tc_supported0(C.byref(d)))
 
