@@ -132,6 +132,7 @@ class Engine:
         self.autotune = True       # one-off timing of candidate tcgen05 tilings per layer shape
         self.tuned = {}
         self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
+        self.trace_log = []        # TRACE mode: one record per convolution launch (tools/list_launches.py, tests)
 
     # ---- helpers -----------------------------------------------------------------------------
     def new(self, shape, dtype=None, zero=False):
@@ -291,6 +292,12 @@ class Engine:
         vox = batch * (np.prod(in_dhw) if transposed else np.prod(out_dhw))
         self.conv_flops += 2 * int(vox) * taps * lcin * sum(lco)      # algorithmic (reference) FLOPs
         if self.tracing:
+            self.trace_log.append(dict(names=[n for n, _ in layers], transposed=bool(transposed), batch=batch,
+                                       in_dhw=tuple(in_dhw), out_dhw=tuple(out_dhw), kernel=k, stride=s, pad=pad,
+                                       src_c=[a.c for a in srcs], out_c=[co for _, co in layers],
+                                       out_fp32=out_dtype == torch.float32,
+                                       needs_dgrad=all(a.needs_grad for a in srcs), feeds_norm=bool(feeds_norm),
+                                       flops=2 * int(vox) * taps * lcin * sum(lco)))
             return outs
         self._gather("conv_fwd", mode, batch, in_dhw, out_dhw, k, s, pad, [a.t for a in srcs], [a.c for a in srcs],
                      ws, wstr, bs, [o.t for o in outs], [co for _, co in layers], [False] * len(layers),

@@ -105,3 +105,43 @@ def test_wgrad_plans(dhw, cins, couts, k):
     assert stages >= 2 and smem <= SMEM_MAX and 3 * mpg * n_tile <= tmem <= 512
     assert stage_bytes >= (128 // ck) * (kv + 8) * ck * 2 * mpg + (n_tile // cb) * kv * cb * 2
     assert dhw[2] * bh >= 0.8 * kv                                  # <= 20 % zero-filled K rows
+
+
+def test_every_launch_of_the_training_step_is_planned():
+    """Shape-only trace of the cfg-2 training step (tools/list_launches.py): every bf16 convolution launch is
+    taken by the tcgen05 engine (only the fp32-output heads stay on the CUDA cores), the algorithmic FLOPs match
+    SURVEY.md section 8(d), and the plan invariants hold for every real launch shape."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import list_launches as LL
+    log = LL.trace(batch=B)
+    assert len(log) > 150
+    gflop_per_volume = sum(r['flops'] for r in log) / B / 1e9
+    assert abs(gflop_per_volume - 1675.31) < 0.01 * 1675.31, gflop_per_volume      # fwd 837.65 GMAC
+    n_halo = n_shift = 0
+    for r in log:
+        d = LL.fwd_desc(r)
+        if r['out_fp32']:
+            assert not ops.conv3d_tc_supported(d), r['names']                       # mu/log-sigma heads
+            continue
+        assert ops.conv3d_tc_supported(d), r['names']
+        ck, n_tile, n_tiles, bd, bh, bw, stages, group, smem, tmem, ctas = ops.conv3d_plan_info(d, 0)
+        assert smem <= SMEM_MAX and n_tile <= tmem <= 512 and bd * bh * bw <= 128 and stages >= 1
+        halo = ops.conv3d_plan_info(d, 1)
+        if halo:
+            n_halo += 1
+            assert not r['transposed'] and tuple(r['stride']) == (1, 1, 1)
+            ck, n_tile, n_tiles, G, hb, wb, P, L, st, smem, tmem, ctas_sm, stage_bytes, a_alloc = halo
+            assert (hb - 1) * P + wb <= 128 and G * n_tile <= tmem <= 512 and st * stage_bytes + 2048 == smem <= SMEM_MAX
+        if not r['transposed']:
+            assert ops.conv3d_wgrad_tc_supported(d), r['names']
+            info = ops.conv3d_plan_info(d, 2)
+            assert info[5] % 16 == 0 and info[10] <= SMEM_MAX and info[11] <= 512
+            d.tune[1] = 2
+            sh = ops.conv3d_plan_info(d, 2)
+            if sh and sh[12]:
+                n_shift += 1
+                assert sh[8] >= r['out_dhw'][2] + 2 and sh[5] == sh[7] * sh[8] and sh[5] % 16 == 0
+                assert sh[10] <= SMEM_MAX and sh[11] <= 512 and sh[9] >= 2
+    assert n_halo >= 40 and n_shift >= 12, (n_halo, n_shift)
