@@ -28,6 +28,8 @@
 // issuer (elect.sync, see tc_common.cuh), all 8 warps run the epilogue (tc_epilogue.cuh). Stride-1 launches
 // with in-plane taps may be routed to the halo variant (conv_tc_halo.cu) - m1_conv_desc.tune[0].
 #include "tc_epilogue.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace {
 using namespace tc;
@@ -193,6 +195,168 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- multi-tile variant (m1_conv_desc.tune[0] == 3; EXPERIMENTAL, not selected by default, not yet run on a GPU)
+// Launches with a handful of k-steps per tile (1x1x1 convolutions, the output phases of transposed
+// convolutions, few-channel layers: ~24 ms of the step at 20-400 TFLOP/s) are dominated by per-CTA fixed costs:
+// TMEM allocation, barrier initialisation, the first TMA round trip, the drain of the epilogue. Here a CTA owns
+// `tiles_per_cta` consecutive M tiles: the producer warp streams k-steps across tile boundaries (the smem ring
+// never drains), accumulators are double-buffered in TMEM (tile i+1 is multiplied while tile i is stored), and
+// eight dedicated epilogue warps (warps 2-9; warp w reads TMEM lanes 32*(w%4).., warps 2-5 / 6-9 split the
+// columns) hand each accumulator back through bar_free.
+constexpr int kThreadsMulti = 320;
+
+__global__ void __launch_bounds__(kThreadsMulti)
+conv_tc_multi_kernel(const __grid_constant__ TcParams p, int tiles_per_cta, int total_tiles, uint32_t acc_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_base;                 // stages x 8 B
+  const uint32_t bar_empty = smem_base + 8u * 16u;     // stages x 8 B (<= 16 stages)
+  const uint32_t bar_accum = smem_base + 8u * 32u;     // 2 x 8 B: accumulator buffer complete (MMA -> epilogue)
+  const uint32_t bar_free = smem_base + 8u * 34u;      // 2 x 8 B: accumulator buffer drained (epilogue -> MMA)
+  const uint32_t tmem_slot = smem_base + 8u * 36u;
+  const uint32_t tiles = smem_base + 1024u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(t_begin + tiles_per_cta, total_tiles);
+  const int n0 = blockIdx.y * p.n_tile;
+  const int ph = blockIdx.z;
+  const int tap_begin = p.phase_tap0[ph], tap_end = p.phase_tap0[ph + 1];
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(2u * acc_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accum + 8u * b, 1);
+      mbar_init(bar_free + 8u * b, 8);                 // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + 8u * 36u);
+
+  int total_chunks = 0;
+  for (int s = 0; s < p.nsrc; ++s) total_chunks += p.src_chunks[s];
+  const int ksteps = (tap_end - tap_begin) * total_chunks;
+  const int nstage_iters = (ksteps + p.group - 1) / p.group;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===== TMA producer: k-steps of tile after tile, the ring position carries over
+      uint32_t stage = 0, phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int t = tile;
+        const int tw_i = t % p.tw; t /= p.tw;
+        const int th_i = t % p.th; t /= p.th;
+        const int td_i = t % p.td;
+        const int n_img = t / p.td;
+        const int a_d0 = td_i * p.bd * p.istr_d, a_h0 = th_i * p.bh * p.istr_h, a_w0 = tw_i * p.bw * p.istr_w;
+        int tap = tap_begin, src = 0, chunk = 0;
+        for (int it = 0; it < nstage_iters; ++it) {
+          const int g = min(p.group, ksteps - it * p.group);
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8u * stage;
+          mbar_expect_tx(full, p.tx_per_kstep * (uint32_t)g);
+          for (int j = 0; j < g; ++j) {
+            const uint32_t slot = tiles + (stage * p.group + j) * p.slot_bytes;
+            const int c_in = chunk * p.ck;
+            tma_load_5d(slot, &p.tmA[src], full, c_in, a_w0 + p.tap_ow[tap], a_h0 + p.tap_oh[tap],
+                        a_d0 + p.tap_od[tap], n_img);
+            tma_load_3d(slot + p.a_alloc, &p.tmB, full, p.src_koff[src] + c_in, n0, (int)p.tap_w[tap]);
+            if (++chunk == p.src_chunks[src]) {
+              chunk = 0;
+              if (++src == p.nsrc) { src = 0; ++tap; }
+            }
+          }
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===== MMA issuer: accumulator buffer = tile parity
+      uint32_t stage = 0, phase = 0;
+      const uint64_t hi = (uint64_t)p.desc_hi << 32;
+      const int k16s = p.ck / 16;
+      int ti = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+        const uint32_t buf = (uint32_t)ti & 1u;
+        if (ti >= 2) {                                   // the epilogue of tile ti-2 has drained this buffer
+          mbar_wait(bar_free + 8u * buf, (uint32_t)((ti >> 1) - 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d_tmem = tmem_base + buf * acc_cols;
+        uint32_t acc = 0;
+        for (int it = 0; it < nstage_iters; ++it) {
+          const int g = min(p.group, ksteps - it * p.group);
+          mbar_wait(bar_full + 8u * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int j = 0; j < g; ++j) {
+            const uint32_t slot = (tiles + (stage * p.group + j) * p.slot_bytes) >> 4;
+            const uint32_t slot_b = slot + (p.a_alloc >> 4);
+            for (int k = 0; k < k16s; ++k) {
+              umma_bf16(d_tmem, hi | (uint64_t)(slot + 2u * k), hi | (uint64_t)(slot_b + 2u * k), p.idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(bar_empty + 8u * stage);
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_accum + 8u * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 2..9
+    const int q = warp - 2;
+    const int quarter = warp & 3;                        // the TMEM lane quarter this warp may read
+    const int r = quarter * 32 + (threadIdx.x & 31);
+    const int lw = r % p.bw;
+    const int lh = (r / p.bw) % p.bh;
+    const int ld = r / (p.bw * p.bh);
+    int cb, ce;
+    epi_cols(q < 4 ? 0 : 4, p.n_tile, &cb, &ce);
+    int ti = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+      const uint32_t buf = (uint32_t)ti & 1u;
+      int t = tile;
+      const int tw_i = t % p.tw; t /= p.tw;
+      const int th_i = t % p.th; t /= p.th;
+      const int td_i = t % p.td;
+      const int n_img = t / p.td;
+      const int d = (td_i * p.bd + ld) * p.ostr_d + p.phase_d[ph], h = (th_i * p.bh + lh) * p.ostr_h + p.phase_h[ph],
+                w = (tw_i * p.bw + lw) * p.ostr_w + p.phase_w[ph];
+      const bool valid = (ld < p.bd) && d < p.Do && h < p.Ho && w < p.Wo;
+      const int64_t vox = (((int64_t)n_img * p.Do + d) * p.Ho + h) * p.Wo + w;
+      mbar_wait(bar_accum + 8u * buf, (uint32_t)(ti >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem_base + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+      epilogue_row(p.epi, lane_addr, n0, cb, ce, valid, vox, ksteps == 0);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8u * buf) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * acc_cols)
                  : "memory");
   }
 }
@@ -392,7 +556,7 @@ int m1_conv3d_tc_plan_info(const m1_conv_desc* d, int32_t* out) {
 
 extern "C" int m1_conv3d_halo_engine(const m1_conv_desc* d) {
   int pref = 0;
-  if (d->tune[0] == 1 || !m1_conv3d_halo_supported(d, &pref)) return 0;
+  if (d->tune[0] == 1 || d->tune[0] == 3 || !m1_conv3d_halo_supported(d, &pref)) return 0;
   return (d->tune[0] == 2 || pref) ? 1 : 0;
 }
 
@@ -507,6 +671,24 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   for (int j = 0; j < d->nout; ++j)
     M1_CHECK(((uintptr_t)outs[j] & 15) == 0, "m1_conv3d: produced tensor %d not 16-byte aligned", j);
 
+  static const int g_multi = getenv("M1_CONV_MULTI") ? atoi(getenv("M1_CONV_MULTI")) : 0;
+  if (d->tune[0] == 3 || g_multi) {
+    // EXPERIMENTAL multi-tile variant (see conv_tc_multi_kernel)
+    uint32_t acc_cols = 32;
+    while ((int)acc_cols < pl.n_tile) acc_cols <<= 1;
+    const int total_tiles = d->batch * pl.td * pl.th * pl.tw;
+    const int64_t ctas1 = (int64_t)total_tiles * pl.n_tiles * pl.nphase;
+    int per = (int)std::max<int64_t>(1, std::min<int64_t>(16, ctas1 / ((int64_t)ctx->num_sms * 8)));
+    static int multi_set = 0;
+    if (!multi_set) {
+      M1_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      multi_set = 1;
+    }
+    dim3 mgrid((unsigned)((total_tiles + per - 1) / per), (unsigned)pl.n_tiles, (unsigned)pl.nphase);
+    conv_tc_multi_kernel<<<mgrid, kThreadsMulti, pl.smem_bytes, st>>>(p, per, total_tiles, acc_cols);
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   static int smem_set = 0;
   if (smem_set < (int)pl.smem_bytes) {
     M1_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -550,3 +550,32 @@ def test_conv_wgrad_tcgen05_shift_mode(ctx, dhw, cins, couts, k):
         scale = max(1.0, ref.abs().max().item())
         assert torch.isfinite(dw).all()
         assert (dw.double().cpu() - ref).abs().max().item() < 2e-3 * scale
+
+
+MULTI = pytest.mark.skipif(__import__("os").environ.get("M1_TEST_EXPERIMENTAL") != "1",
+                           reason="experimental multi-tile conv variant (tune[0] = 3): written at the end of round 1 "
+                                  "without GPU time left to run it; enable with M1_TEST_EXPERIMENTAL=1")
+
+
+@MULTI
+@pytest.mark.parametrize("dhw,cins,couts,k", TC_CASES)
+def test_conv_fwd_tcgen05_multi_tile(ctx, dhw, cins, couts, k):
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k, seed=1)
+    got = _run_fwd(ctx, xs, ws, bs, k, (1, 1, 1), torch.bfloat16, _lib.ENGINE_TCGEN05, variant=3)
+    ref = _ref_fwd(xs, ws, bs, (1, 1, 1), torch.bfloat16)
+    for g, r in zip(got, ref):
+        assert torch.isfinite(g).all(), "non-finite output (unwritten voxels?)"
+        assert (g - r).abs().max().item() < 2e-2
+
+
+@MULTI
+@pytest.mark.parametrize("dhw,cins,couts,k,s", STRIDED_TC)
+def test_conv_fwd_strided_tcgen05_multi_tile(ctx, dhw, cins, couts, k, s):
+    from m1b200 import _lib
+    xs, ws, bs = _mk(2, dhw, cins, couts, k, seed=5)
+    got = _run_fwd(ctx, xs, ws, bs, k, s, torch.bfloat16, _lib.ENGINE_TCGEN05, variant=3)
+    ref = _ref_fwd(xs, ws, bs, s, torch.bfloat16)
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape and torch.isfinite(g).all()
+        assert (g - r).abs().max().item() < 2e-2
