@@ -8,6 +8,15 @@
 Workload (BASELINE.json configs[1]): full M1 — probabilistic + dense_skip + deep_supervision — training
 step (4-pass forward, focal + KL, backward, Adam-AMSGrad), bf16, batch 8 per GPU, synthetic 20x160x160
 volumes with 4 input channels (3 bpMRI + label channel). A "step" is one such training step.
+
+Timed regions (CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks):
+  value      K steps, inputs resident in HBM; after its warm-up the model replays the step from two CUDA graphs
+             ([forward, losses, backward] and [Adam, weight re-pack]; with N > 1 the NCCL all-reduce of the flat
+             gradient buffer runs between them)
+  e2e        K steps through the public API with pinned HOST inputs copied in and the loss read back every step
+  roofline   the same K steps launched eagerly with a CUDA-event pair around every kernel family (per position
+             in the step: median over the K steps), dominant conv family vs the measured bf16 peak
+  cpu_baseline / --impl reference   the oracle port of the reference on the host cores (TF 2.5 cannot run here)
 """
 import argparse
 import json
