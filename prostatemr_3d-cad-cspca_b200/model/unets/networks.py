@@ -262,7 +262,10 @@ class M1(LoadableModel):
         assert ndims == 3, 'the sm_100a kernels implement the 3-D model (the only one M1Core can build)'
         assert ds_in_prob in ('reference', 'intended')
         if cascaded is not False:
-            raise NotImplementedError("cascaded two-stage M1 (R:networks.py:109-193): use CascadedM1")
+            raise NotImplementedError(
+                "cascaded two-stage M1 (R:networks.py:109-193) is not wired yet: the m1_decision_fusion kernel and "
+                "its oracle exist, the second stage's input concat and the gradient through the stage-1 softmax "
+                "do not (SURVEY.md section 8(f), rank n4); build the two stages as separate M1 objects meanwhile")
         self.name = name
         self.input_spatial_dims = tuple(int(d) for d in input_spatial_dims)
         self.input_channels, self.num_classes = int(input_channels), int(num_classes)
