@@ -9,7 +9,8 @@ PARITY UNPINNED: the reference cannot be executed in this image (TensorFlow 2.5,
 0.14, tensorflow_probability 0.13 and sonnet are absent, Python 3.12, no network) and ships no
 tests, golden vectors or saved weights.  The semantics of those third-party layers are restated
 from their documented behaviour; the oracle is pinned only by the
-known-answer tests of tests/test_oracle.py (adjoint identities, closed forms, torch.distributions).
+known-answer tests of tests/test_oracle.py (loop restatements of the defining sums of Conv3D /
+Conv3DTranspose / Focal, adjoint identities, closed forms, torch.distributions).
 
 Reference map (R: = /root/reference/tf2.5/scripts/model/unets/, L: = .../model/losses.py)
   same_pads / conv3d_same             tf.keras.layers.Conv3D(padding='same')      R:networks.py:259,472

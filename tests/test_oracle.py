@@ -251,3 +251,94 @@ def test_bf16_storage_emulation_switch():
     assert 0 < d < 5e-2, d
     r2['loss'].backward()
     assert all(torch.isfinite(p.grad).all() for p in ps.p.values() if p.grad is not None)
+
+
+def _np_conv3d_same(x, w, b, s):
+    """SURVEY.md section 8 row a6, written out with loops (independent of torch's convolution):
+    y[n,d,h,w,co] = b[co] + sum x_pad[n, d*sd+kd, h*sh+kh, w*sw+kw, ci] * W[kd,kh,kw,ci,co], TF SAME padding
+    (pad_before = total // 2), cross-correlation (no kernel flip), kernel layout (kd,kh,kw,Cin,Cout)."""
+    import numpy as np
+    n, D, H, W, ci = x.shape
+    kd, kh, kw, _, co = w.shape
+    geo = [O.same_pads(sz, k, st) for sz, k, st in zip((D, H, W), (kd, kh, kw), s)]
+    (Do, pd, pda), (Ho, ph, pha), (Wo, pw, pwa) = geo
+    xp = np.zeros((n, D + pd + pda, H + ph + pha, W + pw + pwa, ci))
+    xp[:, pd:pd + D, ph:ph + H, pw:pw + W] = x
+    y = np.zeros((n, Do, Ho, Wo, co))
+    for d in range(Do):
+        for h in range(Ho):
+            for ww in range(Wo):
+                patch = xp[:, d * s[0]:d * s[0] + kd, h * s[1]:h * s[1] + kh, ww * s[2]:ww * s[2] + kw, :]
+                y[:, d, h, ww, :] = np.einsum('nabci,abcio->no', patch, w) + b
+    return y
+
+
+def _np_conv3d_transpose_same(x, w, b, s):
+    """row a7: scatter every input voxel times W[kd,kh,kw,Cout,Cin] into a buffer of length (in-1)*s+k, keep
+    [pad_before : pad_before + in*s] with pad_before of the FORWARD conv of that kernel/stride."""
+    import numpy as np
+    n, D, H, W, ci = x.shape
+    kd, kh, kw, co, _ = w.shape
+    full = np.zeros((n, (D - 1) * s[0] + kd, (H - 1) * s[1] + kh, (W - 1) * s[2] + kw, co))
+    for d in range(D):
+        for h in range(H):
+            for ww in range(W):
+                full[:, d * s[0]:d * s[0] + kd, h * s[1]:h * s[1] + kh, ww * s[2]:ww * s[2] + kw, :] += \
+                    np.einsum('ni,abcoi->nabco', x[:, d, h, ww, :], w)
+    out = []
+    sl = [slice(None)]
+    for dim, (size, k, st) in enumerate(zip((D, H, W), (kd, kh, kw), s)):
+        n_out = size * st
+        pb = O.same_pads(n_out, k, st)[1]
+        have = full.shape[1 + dim]
+        if have < pb + n_out:
+            padw = [(0, 0)] * 5
+            padw[1 + dim] = (0, pb + n_out - have)
+            full = np.pad(full, padw)
+        sl.append(slice(pb, pb + n_out))
+    return full[tuple(sl + [slice(None)])] + b
+
+
+@pytest.mark.parametrize("dhw,k,s", [((4, 6, 5), (1, 3, 3), (1, 1, 1)), ((4, 6, 8), (1, 3, 3), (1, 2, 2)),
+                                     ((5, 7, 9), (3, 3, 3), (2, 2, 2)), ((4, 8, 6), (3, 3, 3), (1, 2, 2)),
+                                     ((3, 4, 4), (2, 2, 2), (2, 2, 2)), ((3, 5, 4), (1, 1, 1), (1, 1, 1))])
+def test_conv_and_transpose_match_the_written_out_definition(dhw, k, s):
+    """The oracle's convolution / transposed convolution against loop restatements of the defining sums
+    (absolute semantics: kernel orientation, weight layout and SAME pad placement - which the adjoint
+    identity alone would not pin)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    cin, cout = 3, 4
+    x = rng.standard_normal((2, *dhw, cin))
+    w = rng.standard_normal((*k, cin, cout))
+    b = rng.standard_normal(cout)
+    y = O.conv3d_same(torch.tensor(x), torch.tensor(w), torch.tensor(b), s).numpy()
+    ref = _np_conv3d_same(x, w, b, s)
+    assert y.shape == ref.shape and np.abs(y - ref).max() < 1e-12
+    small = tuple(-(-d // st) for d, st in zip(dhw, s))
+    xt = rng.standard_normal((2, *small, cout))
+    wt = rng.standard_normal((*k, cin, cout))                 # Keras ConvT layout (k, Cout_T = cin, Cin_T = cout)
+    bt = rng.standard_normal(cin)
+    yt = O.conv3d_transpose_same(torch.tensor(xt), torch.tensor(wt), torch.tensor(bt), s).numpy()
+    reft = _np_conv3d_transpose_same(xt, wt, bt, s)
+    assert yt.shape == reft.shape == (2, *(d * st for d, st in zip(small, s)), cin)
+    assert np.abs(yt - reft).max() < 1e-12
+
+
+def test_focal_written_out():
+    """losses.py:32-49 with loops: renormalise, clip to [eps, 1-eps], alpha_c * y * (1-p)^gamma * (-log p),
+    summed over voxels and classes, mean over the batch."""
+    import numpy as np
+    rng = np.random.default_rng(6)
+    p = rng.random((2, 3, 4, 5, 2)) + 0.05
+    y = np.eye(2)[rng.integers(0, 2, (2, 3, 4, 5))]
+    alpha, gamma = (0.75, 0.25), 2.0
+    tot = 0.0
+    for n in range(2):
+        for idx in np.ndindex(3, 4, 5):
+            q = p[(n,) + idx] / p[(n,) + idx].sum()
+            q = np.clip(q, 1e-7, 1 - 1e-7)
+            for c in range(2):
+                tot += alpha[c] * y[(n,) + idx + (c,)] * (1 - q[c]) ** gamma * (-np.log(q[c]))
+    got = O.focal_loss(torch.tensor(y), torch.tensor(p), alpha=alpha, gamma=gamma).item()
+    assert abs(got - tot / 2) < 1e-9 * abs(tot)
