@@ -233,46 +233,59 @@ class Noise:
 # autograd function below, the gradients that flow back through them), so that the remaining product-vs-oracle
 # difference is summation order only - the deviation of the bf16 mode from the fp32 reference is then shown
 # to be storage precision, not arithmetic.
-_EMU = {'on': False}
+# 'fwd' / 'bwd': which KINDS of storage points round their values / their gradients ('conv' = raw convolution
+# outputs before a norm or another consumer, 'act' = every other stored activation: norm+LeakyReLU outputs, SE
+# block outputs, gated attention tensors, latents, the input image); 'w': bf16 tensor-core weights. The product
+# rounds everything; the subsets exist for precision studies (tools/bf16_precision_study.py).
+_EMU = {'on': False, 'fwd': ('conv', 'act'), 'bwd': ('conv', 'act'), 'w': True, 'vdtype': torch.bfloat16}
 
 
 class _RoundBF16(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return x.to(_EMU['vdtype']).to(x.dtype) if fwd else x          # gradients always round to bf16
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(torch.bfloat16).to(g.dtype)
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
 
 
 class _RoundBF16Fwd(torch.autograd.Function):      # bf16 operand copy of an fp32 master weight
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return x.to(_EMU['vdtype']).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
         return g
 
 
-def _q(x):
-    return _RoundBF16.apply(x) if _EMU['on'] else x
+def _q(x, kind='act'):
+    if not _EMU['on']:
+        return x
+    fwd, bwd = kind in _EMU['fwd'], kind in _EMU['bwd']
+    return _RoundBF16.apply(x, fwd, bwd) if (fwd or bwd) else x
 
 
 def _wq(w):
-    return _RoundBF16Fwd.apply(w) if _EMU['on'] else w
+    return _RoundBF16Fwd.apply(w) if (_EMU['on'] and _EMU['w']) else w
 
 
 class emulate_bf16_storage:
-    """with emulate_bf16_storage(): ... - see above."""
+    """with emulate_bf16_storage(): ... - see above. fwd / bwd / weights select subsets (precision studies)."""
+
+    def __init__(self, fwd=('conv', 'act'), bwd=('conv', 'act'), weights=True, value_dtype=torch.bfloat16):
+        """value_dtype: storage type of forward values and tensor-core weights (torch.float16 for the 'what if
+        the forward pass were fp16' study); gradients always round to bf16."""
+        self.cfg = dict(on=True, fwd=tuple(fwd), bwd=tuple(bwd), w=bool(weights), vdtype=value_dtype)
 
     def __enter__(self):
-        self.prev = _EMU['on']
-        _EMU['on'] = True
+        self.prev = dict(_EMU)
+        _EMU.update(self.cfg)
 
     def __exit__(self, *a):
-        _EMU['on'] = self.prev
+        _EMU.update(self.prev)
 
 
 def _fp32_head(name, kinds):
@@ -288,13 +301,13 @@ def _conv(ps, name, x, cout, k, s=(1, 1, 1), kinds=('kernel', 'bias')):
     b = ps.get(name + '/bias', (cout,), kinds[1])
     if _fp32_head(name, kinds):
         return conv3d_same(x, w, b, s)
-    return _q(conv3d_same(x, _wq(w), b, s))
+    return _q(conv3d_same(x, _wq(w), b, s), 'conv')
 
 
 def _convt(ps, name, x, cout, k, s):
     w = ps.get(name + '/kernel', tuple(k) + (cout, x.shape[-1]), 'kernel')
     b = ps.get(name + '/bias', (cout,), 'bias')
-    return _q(conv3d_transpose_same(x, _wq(w), b, s))
+    return _q(conv3d_transpose_same(x, _wq(w), b, s), 'act')      # feeds convolutions directly: must be bf16
 
 
 def _inorm(ps, name, x):
