@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--dims", type=int, nargs=3, default=[20, 160, 160])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core convolutions only")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="storage type of the activation values (fp16: the mode that meets the parity bounds)")
     return ap.parse_args()
 
 
@@ -216,7 +218,7 @@ def run_ours(args):
     B = args.batch
     model = unets.networks.M1(dims, 4, 2, dropout_rate=0.5, dropout_mode='monte-carlo', att_sub_samp=((1, 1, 1),) * 4,
                               dense_skip=True, deep_supervision=True, probabilistic=True,
-                              prob_latent_dims=(3, 2, 1, 0), summary=False, precision='bf16', seed=0,
+                              prob_latent_dims=(3, 2, 1, 0), summary=False, precision=args.precision, seed=0,
                               device=dev, use_tcgen05=not args.no_tc, **README_CFG)
     sched = optimizers.CosineDecayRestarts(1e-3, 1000, t_mul=2.0, m_mul=1.0, alpha=1e-3)
     model.compile(optimizer=optimizers.Adam(learning_rate=sched, amsgrad=True),
@@ -359,7 +361,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
         "clocks": clk,
         "e2e": {"value": e2e, "unit": "volumes/s", "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

@@ -10,8 +10,8 @@
  *
  * Conventions
  *   - all tensors are dense NDHWC ("channels last"), caller-owned DEVICE memory, 16-byte aligned;
- *   - activations are bf16 or fp32 (m1_dtype); statistics, parameters, gradients of parameters
- *     and all reductions are fp32;
+ *   - activations are fp16, bf16 or fp32 (m1_dtype; gradients of fp16 activations are bf16); statistics,
+ *     parameters, gradients of parameters and all reductions are fp32;
  *   - every call takes the cudaStream_t to launch on (as void*), never synchronises, and returns
  *     0 on success; on failure it returns non-zero and m1_last_error() (thread-local) says why;
  *   - there is no CPU fallback: a call on a machine without an sm_100 device fails.
@@ -28,7 +28,14 @@ extern "C" {
 #define M1_MAX_SRC 8
 #define M1_MAX_OUT 8
 
-typedef enum { M1_F32 = 0, M1_BF16 = 1 } m1_dtype;
+/* element types. Activation VALUES are fp32, bf16 or fp16; the GRADIENT of an activation is stored as
+ * m1_grad_dtype(value type): fp32 -> fp32, bf16 -> bf16, fp16 -> bf16 (fp16 has too little range for
+ * gradients; bf16 gradient storage is harmless). Backward entry points take the
+ * VALUE dtype and derive the gradient dtype by this rule. */
+typedef enum { M1_F32 = 0, M1_BF16 = 1, M1_F16 = 2 } m1_dtype;
+#define M1_GRAD_DTYPE(dt) ((dt) == M1_F16 ? M1_BF16 : (dt))
+/* m1_softmax_focal only: the fp32 input already holds probabilities (the softmax is skipped) */
+#define M1_PROBS 16
 
 /* gather direction of a convolution launch (see m1_conv_desc) */
 typedef enum {
@@ -67,6 +74,11 @@ typedef struct {
   int32_t act_dtype;                  /* m1_dtype of the gathered tensors */
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
+  /* tcgen05 engine: element type of the packed weight operand (m1_conv3d_pack_weights), M1_BF16 or M1_F16;
+   * 0 = the type of the gathered tensors. tcgen05.mma.kind::f16 takes the two operand formats independently:
+   * the fp16 mode multiplies bf16 gradients with fp16 weights (data gradient) and fp16 activations with bf16
+   * gradients (weight gradient). */
+  int32_t w_dtype;
   /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
    * conv:  tune[0] = engine variant: 1 = one TMA box per filter tap (conv_tc.cu), 2 = halo tile shared by
    *        the in-plane taps through row-shifted UMMA descriptors (conv_tc_halo.cu; stride-1 gathers only),
@@ -231,7 +243,7 @@ int m1_kl_bwd(m1_ctx* ctx, const float* ml_q, const float* ml_p, int batch, int6
               int L, float scale, float* dml_q, float* dml_p, void* stream);
 
 /* ---- K8: softmax + focal loss, R:networks.py:388-390,751-755 and L:32-49 --------------------
- * logits [batch][lg][nc] fp32 (ldtype M1_F32; ldtype 2 = the tensor already holds probabilities,
+ * logits [batch][lg][nc] fp32 (ldtype M1_F32; ldtype M1_PROBS = the tensor already holds probabilities,
  * the softmax is skipped - Focal.FL called on predictions), nearest-upsampled by `up` to the label grid
  * xg = lg*up (deep-supervision heads: the 1x1x1 conv commutes with the nearest upsample);
  * softmax written to prob[..., head_off : head_off+nc] of a [batch][xg][prob_c] fp32 tensor;

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libm1b200.so")
 
 M1_MAX_SRC = 8
 M1_MAX_OUT = 8
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+PROBS = 16      # m1_softmax_focal: the fp32 input already holds probabilities
 CONV_FWD, CONV_TRANSPOSED = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 
@@ -29,7 +30,7 @@ class ConvDesc(C.Structure):
         ("w_stride_tap", C.c_int64 * M1_MAX_OUT), ("w_stride_red", C.c_int64 * M1_MAX_OUT),
         ("w_stride_out", C.c_int64 * M1_MAX_OUT),
         ("w_by_src", C.c_int32), ("accumulate", C.c_int32), ("act_dtype", C.c_int32), ("out_dtype", C.c_int32),
-        ("engine", C.c_int32), ("tune", C.c_int32 * 4),
+        ("engine", C.c_int32), ("w_dtype", C.c_int32), ("tune", C.c_int32 * 4),
     ]
 
 
@@ -177,12 +178,28 @@ def ptr(t):
     return dlpack_device_ptr(t)
 
 
-def dtype_code(t):
-    if t.dtype == torch.float32:
+def code_of(dtype):
+    """m1_dtype code of a torch dtype"""
+    if dtype == torch.float32:
         return F32
-    if t.dtype == torch.bfloat16:
+    if dtype == torch.bfloat16:
         return BF16
-    raise M1Error(f"unsupported activation dtype {t.dtype}")
+    if dtype == torch.float16:
+        return F16
+    raise M1Error(f"unsupported activation dtype {dtype}")
+
+
+def dtype_code(t):
+    return code_of(t.dtype)
+
+
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+
+
+def grad_dtype(dtype):
+    """storage type of the GRADIENT of an activation stored as `dtype` (M1_GRAD_DTYPE of include/m1b200.h):
+    fp16 values have bf16 gradients - fp16 has too little range for gradients."""
+    return torch.bfloat16 if dtype == torch.float16 else dtype
 
 
 def ptr_array(ptrs):

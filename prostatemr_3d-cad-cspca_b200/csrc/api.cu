@@ -37,6 +37,11 @@ extern "C" int m1_ctx_create(int device, m1_ctx** out) {
   if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = fn;
   c->scratch_bytes = 1 << 20;
   M1_CUDA(cudaMalloc(&c->scratch, c->scratch_bytes));
+  c->partial_bytes = 48u << 20;
+  M1_CUDA(cudaMalloc(&c->partial, c->partial_bytes));
+  c->counter_bytes = 64u << 10;
+  M1_CUDA(cudaMalloc(&c->counters, c->counter_bytes));
+  M1_CUDA(cudaMemset(c->counters, 0, c->counter_bytes));
   *out = c;
   return 0;
 }
@@ -44,6 +49,8 @@ extern "C" int m1_ctx_create(int device, m1_ctx** out) {
 extern "C" int m1_ctx_destroy(m1_ctx* ctx) {
   if (!ctx) return 0;
   cudaFree(ctx->scratch);
+  cudaFree(ctx->partial);
+  cudaFree(ctx->counters);
   delete ctx;
   return 0;
 }

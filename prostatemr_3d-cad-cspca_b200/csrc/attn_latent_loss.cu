@@ -80,12 +80,12 @@ __global__ void __launch_bounds__(TB) attn_bwd_x_kernel(const T* __restrict__ dy
 
 // one warp per theta voxel: dpsi = sum over its x block of <dy, x>; ds = dpsi psi (1-psi);
 // dtheta = ds w_psi lrelu'(theta+phi); dphi += dtheta (atomics, fp32); dw_psi/db_psi via smem
-template <typename T>
-__global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ dy, const T* __restrict__ theta,
+template <typename T, typename TG>
+__global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const TG* __restrict__ dy, const T* __restrict__ theta,
                                                          const T* __restrict__ phi, const float* __restrict__ w_psi,
                                                          const float* __restrict__ psi, const T* __restrict__ x,
                                                          int batch, Grid3 tg, Grid3 gg, Grid3 xg, int F, int Cx,
-                                                         T* __restrict__ dtheta, float* __restrict__ dphi,
+                                                         TG* __restrict__ dtheta, float* __restrict__ dphi,
                                                          float* __restrict__ dw_psi, float* __restrict__ db_psi) {
   extern __shared__ float sdw[];  // F + 1
   for (int i = threadIdx.x; i <= F; i += TB) sdw[i] = 0.f;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ 
         for (int c = 0; c < uw; ++c) {
           const int64_t xv = (((int64_t)n * xg.d + tz * ud + a) * xg.h + ty * uh + b) * xg.w + tx * uw + c;
           for (int ch = lane; ch < Cx; ch += 32)
-            dpsi = fmaf(ld_f<T>(dy + xv * Cx + ch), ld_f<T>(x + xv * Cx + ch), dpsi);
+            dpsi = fmaf(ld_f<TG>(dy + xv * Cx + ch), ld_f<T>(x + xv * Cx + ch), dpsi);
         }
     // x voxels beyond tg*u (floor ratio remainder) map to the last psi: handled only when grids divide
     dpsi = warp_sum(dpsi);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ 
       const float pre = ld_f<T>(theta + v * F + c) + ld_f<T>(phi + gv * F + c);
       const float f = lrelu(pre, M1_LRELU_SLOPE);
       const float dth = ds * w_psi[c] * (pre > 0.f ? 1.f : M1_LRELU_SLOPE);
-      st_f<T>(dtheta + v * F + c, dth);
+      st_f<TG>(dtheta + v * F + c, dth);
       atomicAdd(dphi + gv * F + c, dth);
       atomicAdd(&sdw[c], ds * f);
     }
@@ -137,29 +137,8 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_kernel(const T* __restrict__ 
 // a warp, so the phi-gradient atomics of voxels below the same gating voxel are pre-reduced by
 // shuffles (the gating grid is 4-16x coarser along w).
 // ---------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
-template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-}
-template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
-template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]) { ld8v<T>(p, v); }
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]) { st8v<T>(p, v); }
 __device__ __forceinline__ float group_sum(float v, int G) {   // sum over the G lanes of a voxel group
   for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -226,11 +205,11 @@ __global__ void __launch_bounds__(TB) attn_scale_vec_kernel(const T* __restrict_
   }
 }
 
-template <typename T>
+template <typename T, typename TG>
 __global__ void __launch_bounds__(TB) attn_bwd_psi_vec_kernel(
-    const T* __restrict__ dy, const T* __restrict__ theta, const T* __restrict__ phi,
+    const TG* __restrict__ dy, const T* __restrict__ theta, const T* __restrict__ phi,
     const float* __restrict__ w_psi, const float* __restrict__ psi, const T* __restrict__ x, int64_t nvox, Grid3 tg,
-    Grid3 gg, Grid3 xg, int F, int G, T* __restrict__ dtheta, float* __restrict__ dphi,
+    Grid3 gg, Grid3 xg, int F, int G, TG* __restrict__ dtheta, float* __restrict__ dphi,
     float* __restrict__ dw_psi, float* __restrict__ db_psi) {
   extern __shared__ float sdw[];  // F + 1
   for (int i = threadIdx.x; i <= F; i += TB) sdw[i] = 0.f;
@@ -256,7 +235,7 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_vec_kernel(
             const int64_t xv = ((r * xg.d + tz * ud + a) * xg.h + ty * uh + b) * xg.w + tx * uw + c;
             for (int ch = lg * 8; ch < F; ch += G * 8) {   // Cx == F for every gate of M1
               float d8[8], x8[8];
-              load8<T>(dy + xv * F + ch, d8);
+              load8<TG>(dy + xv * F + ch, d8);
               load8<T>(x + xv * F + ch, x8);
 #pragma unroll
               for (int i = 0; i < 8; ++i) dpsi = fmaf(d8[i], x8[i], dpsi);
@@ -284,7 +263,7 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_vec_kernel(
           dth[i] = ds * w8[i] * (pre > 0.f ? 1.f : M1_LRELU_SLOPE);
           dwp[i] = ds * lrelu(pre, M1_LRELU_SLOPE);
         }
-        store8<T>(dtheta + v * F + c, dth);
+        store8<TG>(dtheta + v * F + c, dth);
       }
       // reduce over the voxel groups of the warp (lanes with equal lg)
 #pragma unroll
@@ -358,7 +337,7 @@ __global__ void latent_bwd_kernel(const T* __restrict__ dz, const float* __restr
 }
 
 __global__ void __launch_bounds__(TB) kl_fwd_kernel(const float* __restrict__ q, const float* __restrict__ p, int L,
-                                                   int64_t rows, float scale, float* __restrict__ out) {
+                                                   int64_t rows, float scale, float* __restrict__ out, GridSum gs) {
   __shared__ float sm[TB / 32];
   float acc[1] = {0.f};
   const int64_t total = rows * L;
@@ -371,7 +350,7 @@ __global__ void __launch_bounds__(TB) kl_fwd_kernel(const float* __restrict__ q,
     acc[0] += (lp - lq) + (__expf(2.f * lq) + dm * dm) * 0.5f * __expf(-2.f * lp) - 0.5f;
   }
   block_sum<1, TB>(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(out, acc[0] * scale);
+  grid_sum_add<TB>(acc[0], scale, out, gs, sm);
 }
 
 __global__ void kl_bwd_kernel(const float* __restrict__ q, const float* __restrict__ p, int L, int64_t rows,
@@ -414,7 +393,7 @@ template <typename TY>
 __global__ void __launch_bounds__(TB) softmax_focal_kernel(const float* __restrict__ logits, const TY* __restrict__ y,
                                                           FocalArgs a, float* __restrict__ prob,
                                                           float* __restrict__ loss_out,
-                                                          float* __restrict__ dlogits) {
+                                                          float* __restrict__ dlogits, GridSum gs) {
   __shared__ float sm[TB / 32];
   const Grid3 xg{a.lg.d * a.up.d, a.lg.h * a.up.h, a.lg.w * a.up.w};
   const int64_t total = (int64_t)a.batch * xg.d * xg.h * xg.w;
@@ -474,19 +453,19 @@ __global__ void __launch_bounds__(TB) softmax_focal_kernel(const float* __restri
     }
   }
   block_sum<1, TB>(acc, sm);
-  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, acc[0] * a.loss_scale);
+  if (loss_out) grid_sum_add<TB>(acc[0], a.loss_scale, loss_out, gs, sm);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K8 fused with the final logits convolution: thread per voxel, features row in registers
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename TY, int C, int NC>
+template <typename T, typename TG, typename TY, int C, int NC>
 __global__ void __launch_bounds__(TB) logits_focal_kernel(const T* __restrict__ feat, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const TY* __restrict__ y,
                                                          FocalArgs a, int64_t total, float* __restrict__ prob,
-                                                         float* __restrict__ loss_out, T* __restrict__ dfeat,
+                                                         float* __restrict__ loss_out, TG* __restrict__ dfeat,
                                                          int acc_dfeat, float* __restrict__ dw,
-                                                         float* __restrict__ db) {
+                                                         float* __restrict__ db, GridSum gs) {
   __shared__ float sw[C * NC + NC];
   __shared__ float sdw[C * NC + NC];
   __shared__ float sm[TB / 32];
@@ -568,14 +547,14 @@ __global__ void __launch_bounds__(TB) logits_focal_kernel(const T* __restrict__ 
     for (int c = 0; c < C; c += 8) {
       float t8[8];
       if (acc_dfeat) {
-        load8<T>(dfeat + i * C + c, t8);
+        load8<TG>(dfeat + i * C + c, t8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) t8[k] += df[c + k];
       } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) t8[k] = df[c + k];
       }
-      store8<T>(dfeat + i * C + c, t8);
+      store8<TG>(dfeat + i * C + c, t8);
     }
   }
   if (dw != nullptr) {
@@ -591,7 +570,7 @@ __global__ void __launch_bounds__(TB) logits_focal_kernel(const T* __restrict__ 
     }
   }
   block_sum<1, TB>(acc, sm);
-  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, acc[0] * a.loss_scale);
+  if (loss_out) grid_sum_add<TB>(acc[0], a.loss_scale, loss_out, gs, sm);
 }
 
 inline unsigned nblocks(const m1_ctx* ctx, int64_t total, int per = TB) {
@@ -616,37 +595,22 @@ extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, cons
   const bool vec = F % 8 == 0 && Cx % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0;
   if (vec) {
     const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
-    if (dtype == M1_BF16) {
-      using T = __nv_bfloat16;
-      attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv, T3, G3, F, G, psi);
-      M1_LAUNCH_CHECK(ctx);
-      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8);
-    } else {
-      using T = float;
-      attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv, T3, G3, F, G, psi);
-      M1_LAUNCH_CHECK(ctx);
-      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8);
-    }
+    M1_DISPATCH_T(dtype, T, (attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv,
+                                                                      T3, G3, F, G, psi)));
+    M1_LAUNCH_CHECK(ctx);
+    M1_DISPATCH_T(dtype, T, (attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8)));
     M1_LAUNCH_CHECK(ctx);
     return 0;
   }
-  if (dtype == M1_BF16) {
-    using T = __nv_bfloat16;
-    attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, batch,
-                                                                T3, G3, F, psi);
-    M1_LAUNCH_CHECK(ctx);
-    attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total);
-  } else {
-    using T = float;
-    attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, batch,
-                                                                T3, G3, F, psi);
-    M1_LAUNCH_CHECK(ctx);
-    attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total);
-  }
+  M1_DISPATCH_T(dtype, T, (attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi,
+                                                                                       w_psi, b_psi, batch, T3, G3, F, psi)));
+  M1_LAUNCH_CHECK(ctx);
+  M1_DISPATCH_T(dtype, T, (attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
+/* dtype: VALUE type of theta / phi / x; dy, dx and dtheta are stored as M1_GRAD_DTYPE(dtype) */
 extern "C" int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const void* phi, const float* w_psi,
                            const float* psi, const void* x, int dtype, int batch, const int32_t* tg,
                            const int32_t* gg, const int32_t* xg, int F, int Cx, void* dx, int acc_dx,
@@ -660,37 +624,21 @@ extern "C" int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const
   if (vec) {
     const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
     const size_t sm = (F + 1) * sizeof(float);
-    if (dtype == M1_BF16) {
-      using T = __nv_bfloat16;
-      attn_bwd_psi_vec_kernel<T><<<pb, TB, sm, st>>>((const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi,
-                                                   (const T*)x, tv, T3, G3, X3, F, G, (T*)dtheta, dphi, dw_psi, db_psi);
-      M1_LAUNCH_CHECK(ctx);
-      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total / 8);
-    } else {
-      using T = float;
-      attn_bwd_psi_vec_kernel<T><<<pb, TB, sm, st>>>((const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi,
-                                                   (const T*)x, tv, T3, G3, X3, F, G, (T*)dtheta, dphi, dw_psi, db_psi);
-      M1_LAUNCH_CHECK(ctx);
-      attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total / 8);
-    }
+    M1_DISPATCH_VG(dtype, T, TG, (attn_bwd_psi_vec_kernel<T, TG><<<pb, TB, sm, st>>>(
+                                    (const TG*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, tv, T3, G3, X3,
+                                    F, G, (TG*)dtheta, dphi, dw_psi, db_psi)));
+    M1_LAUNCH_CHECK(ctx);
+    M1_DISPATCH_VG(dtype, T, TG, (attn_scale_vec_kernel<TG><<<sb, TB, 0, st>>>((const TG*)dy, psi, X3, T3, Cx, (TG*)dx,
+                                                                              acc_dx, total / 8)));
     M1_LAUNCH_CHECK(ctx);
     return 0;
   }
-  if (dtype == M1_BF16) {
-    using T = __nv_bfloat16;
-    attn_bwd_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(
-        (const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, batch, T3, G3, X3, F, Cx, (T*)dtheta,
-        dphi, dw_psi, db_psi);
-    M1_LAUNCH_CHECK(ctx);
-    attn_bwd_x_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total);
-  } else {
-    using T = float;
-    attn_bwd_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(
-        (const T*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, batch, T3, G3, X3, F, Cx, (T*)dtheta,
-        dphi, dw_psi, db_psi);
-    M1_LAUNCH_CHECK(ctx);
-    attn_bwd_x_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)dy, psi, X3, T3, Cx, (T*)dx, acc_dx, total);
-  }
+  M1_DISPATCH_VG(dtype, T, TG, (attn_bwd_psi_kernel<T, TG><<<nblocks(ctx, tv, TB / 32), TB, (F + 1) * sizeof(float), st>>>(
+                                  (const TG*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, batch, T3, G3, X3,
+                                  F, Cx, (TG*)dtheta, dphi, dw_psi, db_psi)));
+  M1_LAUNCH_CHECK(ctx);
+  M1_DISPATCH_VG(dtype, T, TG, (attn_bwd_x_kernel<TG><<<nblocks(ctx, total), TB, 0, st>>>((const TG*)dy, psi, X3, T3, Cx,
+                                                                                         (TG*)dx, acc_dx, total)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -700,25 +648,18 @@ extern "C" int m1_latent_fwd(m1_ctx* ctx, const float* ml, const float* eps, int
   M1_CHECK(mode == 1 || eps != nullptr, "m1_latent_fwd: sampling mode needs eps");
   M1_CHECK(zc >= L, "m1_latent_fwd: zc < L");
   const int64_t rows = (int64_t)batch * voxels;
-  if (zdtype == M1_BF16)
-    latent_fwd_kernel<__nv_bfloat16><<<nblocks(ctx, rows * zc), TB, 0, (cudaStream_t)stream>>>(
-        ml, eps, mode, L, zc, (__nv_bfloat16*)z, rows);
-  else
-    latent_fwd_kernel<float><<<nblocks(ctx, rows * zc), TB, 0, (cudaStream_t)stream>>>(ml, eps, mode, L, zc,
-                                                                                       (float*)z, rows);
+  M1_DISPATCH_T(zdtype, T, (latent_fwd_kernel<T><<<nblocks(ctx, rows * zc), TB, 0, (cudaStream_t)stream>>>(
+                               ml, eps, mode, L, zc, (T*)z, rows)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
+/* zdtype: VALUE type of z; dz is stored as M1_GRAD_DTYPE(zdtype) */
 extern "C" int m1_latent_bwd(m1_ctx* ctx, const void* dz, const float* ml, const float* eps, int mode, int batch,
                              int64_t voxels, int L, int zdtype, int zc, float* dml, void* stream) {
   const int64_t rows = (int64_t)batch * voxels;
-  if (zdtype == M1_BF16)
-    latent_bwd_kernel<__nv_bfloat16><<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dz, ml, eps, mode, L, zc, dml, rows);
-  else
-    latent_bwd_kernel<float><<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>((const float*)dz, ml, eps,
-                                                                                      mode, L, zc, dml, rows);
+  M1_DISPATCH_VG(zdtype, T, TG, (latent_bwd_kernel<TG><<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(
+                                   (const TG*)dz, ml, eps, mode, L, zc, dml, rows)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -727,7 +668,7 @@ extern "C" int m1_kl_fwd(m1_ctx* ctx, const float* ml_q, const float* ml_p, int 
                          float* kl_out, void* stream) {
   const int64_t rows = (int64_t)batch * voxels;
   kl_fwd_kernel<<<nblocks(ctx, rows * L), TB, 0, (cudaStream_t)stream>>>(ml_q, ml_p, L, rows, 1.f / (float)batch,
-                                                                         kl_out);
+                                                                         kl_out, m1_grid_sum(ctx));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -745,8 +686,9 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
                                 const float* alpha, float gamma, int batch, const int32_t* lg, const int32_t* up,
                                 int nc, float* prob, int prob_c, int head_off, float head_weight, float* loss_out,
                                 void* dlogits, float grad_scale, void* stream) {
-  M1_CHECK(ldtype == M1_F32 || ldtype == 2, "m1_softmax_focal: logits must be fp32 (ldtype 2: fp32 probabilities)");
-  M1_CHECK(ldtype != 2 || dlogits == nullptr, "m1_softmax_focal: no gradient in probability mode");
+  M1_CHECK(ldtype == M1_F32 || ldtype == M1_PROBS,
+           "m1_softmax_focal: logits must be fp32 (ldtype M1_PROBS: fp32 probabilities)");
+  M1_CHECK(ldtype != M1_PROBS || dlogits == nullptr, "m1_softmax_focal: no gradient in probability mode");
   M1_CHECK(nc >= 1 && nc <= MAXC, "m1_softmax_focal: nc %d out of range", nc);
   FocalArgs a;
   for (int c = 0; c < MAXC; ++c) a.alpha[c] = (alpha && c < nc) ? alpha[c] : 0.f;   // alpha is a HOST array
@@ -757,7 +699,7 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
   a.batch = batch;
   a.prob_c = prob_c;
   a.head_off = head_off;
-  a.from_probs = ldtype == 2;
+  a.from_probs = ldtype == M1_PROBS;
   a.loss_scale = head_weight / (float)batch;
   a.grad_scale = grad_scale * head_weight / (float)batch;
   const int64_t total = (int64_t)batch * a.lg.d * a.up.d * a.lg.h * a.up.h * a.lg.w * a.up.w;
@@ -766,29 +708,28 @@ extern "C" int m1_softmax_focal(m1_ctx* ctx, const void* logits, int ldtype, con
     // inference: softmax only (labels absent) - reuse the kernel with zero weights
     M1_CHECK(prob != nullptr, "m1_softmax_focal: nothing to do");
   }
-  if (ydtype == M1_BF16)
-    softmax_focal_kernel<__nv_bfloat16><<<nblocks(ctx, total), TB, 0, st>>>(
-        (const float*)logits, (const __nv_bfloat16*)y_true, a, prob, loss_out, (float*)dlogits);
-  else
-    softmax_focal_kernel<float><<<nblocks(ctx, total), TB, 0, st>>>((const float*)logits, (const float*)y_true, a,
-                                                                    prob, loss_out, (float*)dlogits);
+  M1_DISPATCH_T(ydtype, TY, (softmax_focal_kernel<TY><<<nblocks(ctx, total), TB, 0, st>>>(
+                                (const float*)logits, (const TY*)y_true, a, prob, loss_out, (float*)dlogits,
+                                m1_grid_sum(ctx))));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
-template <typename T, typename TY, int C, int NC>
+template <typename T, typename TG, typename TY, int C, int NC>
 static void launch_logits_focal(m1_ctx* ctx, const void* feat, const float* w, const float* bias, const void* y,
                                 const FocalArgs& a, int64_t total, float* prob, float* loss_out, void* dfeat,
                                 int acc_dfeat, float* dw, float* db, cudaStream_t st) {
-  logits_focal_kernel<T, TY, C, NC><<<nblocks(ctx, total), TB, 0, st>>>(
-      (const T*)feat, w, bias, (const TY*)y, a, total, prob, loss_out, (T*)dfeat, acc_dfeat, dw, db);
+  logits_focal_kernel<T, TG, TY, C, NC><<<nblocks(ctx, total), TB, 0, st>>>(
+      (const T*)feat, w, bias, (const TY*)y, a, total, prob, loss_out, (TG*)dfeat, acc_dfeat, dw, db, m1_grid_sum(ctx));
 }
 
+/* fdtype: VALUE type of feat; dfeat is stored as M1_GRAD_DTYPE(fdtype). y_true: fp32 or bf16. */
 extern "C" int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype, const float* w, const float* bias,
                                        const void* y_true, int ydtype, const float* alpha, float gamma, int batch,
                                        int64_t voxels, int C, int nc, float* prob, int prob_c, int head_off,
                                        float head_weight, float* loss_out, void* dfeat, int acc_dfeat, float* dw,
                                        float* db, float grad_scale, void* stream) {
+  M1_CHECK(ydtype == M1_F32 || ydtype == M1_BF16, "m1_logits_softmax_focal: labels must be fp32 or bf16");
   FocalArgs a;
   for (int c = 0; c < MAXC; ++c) a.alpha[c] = (alpha && c < nc) ? alpha[c] : 0.f;
   a.gamma = gamma; a.nc = nc; a.batch = batch; a.prob_c = prob_c; a.head_off = head_off;
@@ -798,13 +739,13 @@ extern "C" int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype
   a.grad_scale = grad_scale * head_weight / (float)batch;
   const int64_t total = (int64_t)batch * voxels;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fb = fdtype == M1_BF16, yb = ydtype == M1_BF16;
+  const bool yb = ydtype == M1_BF16;
 #define M1_LF(CC, NN)                                                                                              \
   if (C == CC && nc == NN) {                                                                                       \
-    if (fb && yb) launch_logits_focal<__nv_bfloat16, __nv_bfloat16, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st); \
-    else if (fb) launch_logits_focal<__nv_bfloat16, float, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);          \
-    else if (yb) launch_logits_focal<float, __nv_bfloat16, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);          \
-    else launch_logits_focal<float, float, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);                          \
+    M1_DISPATCH_VG(fdtype, T, TG, {                                                                                \
+      if (yb) launch_logits_focal<T, TG, __nv_bfloat16, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st); \
+      else launch_logits_focal<T, TG, float, CC, NN>(ctx, feat, w, bias, y_true, a, total, prob, loss_out, dfeat, acc_dfeat, dw, db, st);            \
+    });                                                                                                            \
     M1_LAUNCH_CHECK(ctx);                                                                                          \
     return 0;                                                                                                      \
   }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -15,8 +16,14 @@ struct m1_ctx {
   int num_sms;
   int64_t launches;
   void* encode_tiled;   // cuTensorMapEncodeTiled entry point (driver API, fetched at runtime)
-  float* scratch;       // small fp32 scratch (reductions)
+  float* scratch;       // small fp32 scratch (per-(sample, channel) reduction results)
   size_t scratch_bytes;
+  // deterministic reductions (norm_se.cu, attn_latent_loss.cu): per-block partial sums + ticket counters that
+  // the last block resets to zero - one reduction kernel at a time per context (one stream per context)
+  float* partial;
+  size_t partial_bytes;
+  unsigned int* counters;
+  size_t counter_bytes;
 };
 
 void m1_set_error(const char* fmt, ...);
@@ -50,45 +57,103 @@ void m1_set_error(const char* fmt, ...);
     (ctx)->launches++;                                                                  \
   } while (0)
 
-// ---- typed element access (activations are fp32 or bf16) -------------------------------
+// ---- typed element access (activations are fp32, bf16 or fp16) ---------------------------
+// 16-bit element types share one code path: cvt2<T> unpacks / pack2<T> packs two elements of a 32-bit word.
+template <typename T> __device__ __forceinline__ float2 cvt2(uint32_t w);
+template <> __device__ __forceinline__ float2 cvt2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));   // bf16 = high half of fp32
+}
+template <> __device__ __forceinline__ float2 cvt2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
 }
+template <> __device__ __forceinline__ float ld_f<__half>(const __half* p) { return __half2float(*p); }
 template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
 template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16_rn(v);
 }
+template <> __device__ __forceinline__ void st_f<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-// 4-wide vector access: fp32 -> float4 (16 B), bf16 -> 8 B
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-    float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+// 8-wide vector access: fp32 -> 2 x float4, 16-bit types -> one 16-byte access
+template <typename T> __device__ __forceinline__ void ld8v(const T* p, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = cvt2<T>(w[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
   }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+}
+template <typename T> __device__ __forceinline__ void st8v(T* p, const float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]),
+                                              pack2<T>(v[6], v[7]));
+  }
+}
+
+// 4-wide vector access: fp32 -> float4 (16 B), 16-bit types -> 8 B
+template <typename T> struct Vec4 {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(p);
+      const float2 a = cvt2<T>(t.x), b = cvt2<T>(t.y);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+  }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      *reinterpret_cast<uint2*>(p) = make_uint2(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]));
+    }
   }
 };
-template <> struct Vec4<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
-    uint2 t = *reinterpret_cast<const uint2*>(p);
-    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
-    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
-    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 t;
-    t.x = *reinterpret_cast<uint32_t*>(&a);
-    t.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = t;
-  }
-};
+
+// ---- dtype dispatch ---------------------------------------------------------------------
+// M1_DISPATCH_T(code, T, ...): runs the statement with `using T` = float / __nv_bfloat16 / __half.
+// M1_DISPATCH_VG(code, TV, TG, ...): value type TV of `code` and the type TG its GRADIENTS are stored in
+// (m1_grad_dtype: fp32 -> fp32, bf16 -> bf16, fp16 -> bf16 - fp16 has too little range for gradients).
+#define M1_DISPATCH_T(code, T, ...)                                                   \
+  do {                                                                                \
+    if ((code) == M1_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }                  \
+    else if ((code) == M1_F16) { using T = __half; __VA_ARGS__; }                     \
+    else { using T = float; __VA_ARGS__; }                                            \
+  } while (0)
+#define M1_DISPATCH_VG(code, TV, TG, ...)                                             \
+  do {                                                                                \
+    if ((code) == M1_BF16) { using TV = __nv_bfloat16; using TG = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((code) == M1_F16) { using TV = __half; using TG = __nv_bfloat16; __VA_ARGS__; }    \
+    else { using TV = float; using TG = float; __VA_ARGS__; }                         \
+  } while (0)
+#define M1_DISPATCH_T2(code_a, code_b, TA, TB_, ...) \
+  M1_DISPATCH_T(code_a, TA, M1_DISPATCH_T(code_b, TB_, __VA_ARGS__))
+static inline bool m1_is16(int code) { return code == M1_BF16 || code == M1_F16; }
+static inline int m1_grad_dtype_of(int code) { return code == M1_F16 ? M1_BF16 : code; }
+// element type of the packed tensor-core weight operand of a convolution launch
+static inline int m1_conv_w_dtype(const m1_conv_desc* d) { return d->w_dtype ? d->w_dtype : d->act_dtype; }
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
@@ -117,6 +182,31 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* NV * BL
     }
   }
   __syncthreads();
+}
+
+// Deterministic grid-wide sum of one value per block, added to *out (scaled) by the LAST block to finish:
+// block partials go to `part[blockIdx.x]`, a self-resetting ticket counter elects the last block, which sums the
+// partials in a fixed order. `v` must hold the block's value in thread 0. All threads of the block must call.
+struct GridSum {
+  float* part;            // >= gridDim.x floats (m1_ctx::partial)
+  unsigned int* counter;  // zero between launches (m1_ctx::counters + kGridSumCounter)
+};
+constexpr int kGridSumCounter = 8192;     // counters [0, 8192) belong to the per-sample reductions
+template <int BLOCK>
+__device__ __forceinline__ void grid_sum_add(float v, float scale, float* out, GridSum gs, float* smem /* BLOCK/32 */) {
+  __shared__ unsigned int s_ticket_gs;
+  if (threadIdx.x == 0) {
+    gs.part[blockIdx.x] = v;
+    __threadfence();
+    s_ticket_gs = atomicInc(gs.counter, gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_ticket_gs != gridDim.x - 1) return;
+  __threadfence();
+  float t[1] = {0.f};
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += BLOCK) t[0] += __ldcg(gs.part + i);
+  block_sum<1, BLOCK>(t, smem);
+  if (threadIdx.x == 0) *out += t[0] * scale;
 }
 
 // ---- Philox4x32-10 counter-based RNG (dropout masks regenerated in backward) -------------
@@ -159,6 +249,10 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream_i
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // entry points implemented per translation unit
+static inline GridSum m1_grid_sum(const m1_ctx* ctx) {
+  return GridSum{ctx->partial, ctx->counters + kGridSumCounter};
+}
+
 int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                    const float* const* w, const float* const* bias, void* const* outs,
                    cudaStream_t st);

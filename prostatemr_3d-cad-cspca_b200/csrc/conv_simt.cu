@@ -267,35 +267,8 @@ __global__ void __launch_bounds__(128) conv_thin_kernel(const __grid_constant__ 
 //   pw_head_fwd   : out[v][n]  = b[n] + sum_r x[v][r] W[r][n]                 (N <= 8)
 //   pw_head_dgrad : dx[v][r] (+)= sum_n dy[v][n] W[r][n]                      (N <= 8 gathered)
 //   pw_head_wgrad : dW[r][n]  += sum_v x[v][r] dy[v][n]
-template <typename T>
-__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
-template <>
-__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 t = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(b[i]); v[2 * i + 1] = __high2float(b[i]); }
-}
-template <>
-__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <typename T>
-__device__ __forceinline__ void st8(T* p, const float (&v)[8]);
-template <>
-__device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
-  uint4 t;
-  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = t;
-}
-template <>
-__device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]) { ld8v<T>(p, v); }
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]) { st8v<T>(p, v); }
 
 struct HeadParams {
   const void* x;      // [vox][C] features (fwd, wgrad)
@@ -730,7 +703,7 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   }
   const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
   for (int i = 0; i < nw; ++i) p.w[i] = w[i];
-  const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
+  const bool ib = d->act_dtype != M1_F32, ob = d->out_dtype != M1_F32;
   int k_total = 0;
   for (int s = 0; s < d->nsrc; ++s) k_total += d->src_c[s];
   const int taps = p.kd * p.kh * p.kw;
@@ -745,29 +718,23 @@ int m1_conv3d_simt(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
       // features -> few fp32 channels
       h.x = srcs[0]; h.out = outs[0]; h.bias = bias ? bias[0] : nullptr;
       h.C = k_total; h.N = p.n_total; h.sr = d->w_stride_red[0]; h.so = d->w_stride_out[0];
-      return ib ? launch_head<__nv_bfloat16>(ctx, 0, h, st) : launch_head<float>(ctx, 0, h, st);
+      M1_DISPATCH_T(d->act_dtype, T, return launch_head<T>(ctx, 0, h, st));
     }
     if (!ib && k_total <= 8 && head_shape_ok(p.n_total, k_total) && !(bias && bias[0])) {
       // few fp32 gradient channels -> gradient of the features (roles of the weight strides swapped)
       h.dy = reinterpret_cast<const float*>(srcs[0]); h.out = outs[0];
       h.C = p.n_total; h.N = k_total; h.sr = d->w_stride_out[0]; h.so = d->w_stride_red[0];
-      return ob ? launch_head<__nv_bfloat16>(ctx, 1, h, st) : launch_head<float>(ctx, 1, h, st);
+      M1_DISPATCH_T(d->out_dtype, T, return launch_head<T>(ctx, 1, h, st));
     }
   }
   if ((k_total <= 16 || p.n_total <= 16) && thin_smem <= 48 * 1024) {
     dim3 tgrid((unsigned)cdiv64(p.out_vox, TV), (unsigned)((p.n_total + TN - 1) / TN));
-    if (ib && ob) conv_thin_kernel<__nv_bfloat16, __nv_bfloat16><<<tgrid, 128, thin_smem, st>>>(p, k_total);
-    else if (ib) conv_thin_kernel<__nv_bfloat16, float><<<tgrid, 128, thin_smem, st>>>(p, k_total);
-    else if (ob) conv_thin_kernel<float, __nv_bfloat16><<<tgrid, 128, thin_smem, st>>>(p, k_total);
-    else conv_thin_kernel<float, float><<<tgrid, 128, thin_smem, st>>>(p, k_total);
+    M1_DISPATCH_T2(d->act_dtype, d->out_dtype, T, TO, (conv_thin_kernel<T, TO><<<tgrid, 128, thin_smem, st>>>(p, k_total)));
     M1_LAUNCH_CHECK(ctx);
     return 0;
   }
   dim3 grid((unsigned)cdiv64(p.out_vox, BM), (unsigned)((p.n_total + BN - 1) / BN));
-  if (ib && ob) conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
-  else if (ib) conv_simt_kernel<__nv_bfloat16, float><<<grid, TH, 0, st>>>(p);
-  else if (ob) conv_simt_kernel<float, __nv_bfloat16><<<grid, TH, 0, st>>>(p);
-  else conv_simt_kernel<float, float><<<grid, TH, 0, st>>>(p);
+  M1_DISPATCH_T2(d->act_dtype, d->out_dtype, T, TO, (conv_simt_kernel<T, TO><<<grid, TH, 0, st>>>(p)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -813,8 +780,9 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
         h.x = srcs[s]; h.dy = reinterpret_cast<const float*>(douts[j]);
         h.dw = q.dw + (int64_t)r_base * q.sr;
         h.C = C; h.N = q.Cn; h.sr = q.sr; h.so = q.so;
-        if (d->act_dtype == M1_BF16 ? launch_head<__nv_bfloat16>(ctx, 2, h, st) : launch_head<float>(ctx, 2, h, st))
-          return 1;
+        int rc = 0;
+        M1_DISPATCH_T(d->act_dtype, T, rc = launch_head<T>(ctx, 2, h, st));
+        if (rc) return 1;
         r_base += C;
         continue;
       }
@@ -831,11 +799,7 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
             q.vox_per_block = vpb;
             dim3 grid((unsigned)cdiv64(out_vox, vpb), (unsigned)taps);
             const size_t smem = (size_t)vch * (Rp + Np) * sizeof(float);
-            const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
-            if (ib && ob) wgrad_small_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>(q, vch);
-            else if (ib) wgrad_small_kernel<__nv_bfloat16, float><<<grid, 256, smem, st>>>(q, vch);
-            else if (ob) wgrad_small_kernel<float, __nv_bfloat16><<<grid, 256, smem, st>>>(q, vch);
-            else wgrad_small_kernel<float, float><<<grid, 256, smem, st>>>(q, vch);
+            M1_DISPATCH_T2(d->act_dtype, d->out_dtype, T, TO, (wgrad_small_kernel<T, TO><<<grid, 256, smem, st>>>(q, vch)));
             M1_LAUNCH_CHECK(ctx);
             r_base += C;
             continue;
@@ -849,11 +813,7 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       vpb = std::max<int64_t>(256, cdiv64(vpb, WV) * WV);
       q.vox_per_block = vpb;
       dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)cdiv64(out_vox, vpb));
-      const bool ib = d->act_dtype == M1_BF16, ob = d->out_dtype == M1_BF16;
-      if (ib && ob) wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, TH, 0, st>>>(q);
-      else if (ib) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, TH, 0, st>>>(q);
-      else if (ob) wgrad_simt_kernel<float, __nv_bfloat16><<<grid, TH, 0, st>>>(q);
-      else wgrad_simt_kernel<float, float><<<grid, TH, 0, st>>>(q);
+      M1_DISPATCH_T2(d->act_dtype, d->out_dtype, T, TO, (wgrad_simt_kernel<T, TO><<<grid, TH, 0, st>>>(q)));
       M1_LAUNCH_CHECK(ctx);
       r_base += C;
     }
@@ -861,12 +821,8 @@ extern "C" int m1_conv3d_wgrad(m1_ctx* ctx, const m1_conv_desc* d, const void* c
       const int C = q.Cn;
       const int64_t rpb = std::max<int64_t>(64, cdiv64(out_vox, (int64_t)ctx->num_sms * 4));
       const unsigned blocks = (unsigned)cdiv64(out_vox, rpb);
-      if (d->out_dtype == M1_BF16)
-        colsum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>(
-            reinterpret_cast<const __nv_bfloat16*>(douts[j]), out_vox, C, rpb, dbias[j]);
-      else
-        colsum_kernel<float><<<blocks, 256, C * sizeof(float), st>>>(
-            reinterpret_cast<const float*>(douts[j]), out_vox, C, rpb, dbias[j]);
+      M1_DISPATCH_T(d->out_dtype, T, (colsum_kernel<T><<<blocks, 256, C * sizeof(float), st>>>(
+                                         reinterpret_cast<const T*>(douts[j]), out_vox, C, rpb, dbias[j])));
       M1_LAUNCH_CHECK(ctx);
     }
   }
@@ -878,12 +834,8 @@ extern "C" int m1_bias_grad(m1_ctx* ctx, const void* dout, int dtype, int64_t ro
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rpb = std::max<int64_t>(64, cdiv64(rows, (int64_t)ctx->num_sms * 4));
   const unsigned blocks = (unsigned)cdiv64(rows, rpb);
-  if (dtype == M1_BF16)
-    colsum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dout), rows, C, rpb, dbias);
-  else
-    colsum_kernel<float><<<blocks, 256, C * sizeof(float), st>>>(reinterpret_cast<const float*>(dout), rows, C,
-                                                                  rpb, dbias);
+  M1_DISPATCH_T(dtype, T, (colsum_kernel<T><<<blocks, 256, C * sizeof(float), st>>>(reinterpret_cast<const T*>(dout),
+                                                                                     rows, C, rpb, dbias)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

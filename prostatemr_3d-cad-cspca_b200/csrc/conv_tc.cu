@@ -161,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           const uint64_t b_lo = (uint64_t)(((slot + p.a_alloc) >> 4) & 0x3FFFu);
           for (int k = 0; k < k16s; ++k) {
             // 16 channels = 32 bytes further along the swizzled row: +2 in 16-byte units
-            umma_bf16(tmem_base, hi | (a_lo + 2u * k), hi | (b_lo + 2u * k), p.idesc, acc);
+            umma_f16(tmem_base, hi | (a_lo + 2u * k), hi | (b_lo + 2u * k), p.idesc, acc);
             acc = 1;
           }
         }
@@ -321,7 +321,7 @@ conv_tc_multi_kernel(const __grid_constant__ TcParams p, int tiles_per_cta, int 
             const uint32_t slot = (tiles + (stage * p.group + j) * p.slot_bytes) >> 4;
             const uint32_t slot_b = slot + (p.a_alloc >> 4);
             for (int k = 0; k < k16s; ++k) {
-              umma_bf16(d_tmem, hi | (uint64_t)(slot + 2u * k), hi | (uint64_t)(slot_b + 2u * k), p.idesc, acc);
+              umma_f16(d_tmem, hi | (uint64_t)(slot + 2u * k), hi | (uint64_t)(slot_b + 2u * k), p.idesc, acc);
               acc = 1;
             }
           }
@@ -379,8 +379,9 @@ struct PackArgs {
   int src_start[M1_MAX_SRC + 1];
   int nout, nsrc, w_by_src;
 };
+template <typename TW>
 __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, int n_real, int n_total, int k_total,
-                                    int taps, __nv_bfloat16* __restrict__ out) {
+                                    int taps, TW* __restrict__ out) {
   const int64_t total = (int64_t)taps * n_total * k_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -401,7 +402,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, int n_re
         v = a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
       }
     }
-    out[i] = __float2bfloat16_rn(v);
+    st_f<TW>(out + i, v);
   }
 }
 
@@ -416,7 +417,8 @@ struct Plan {
 };
 
 bool make_plan(const m1_conv_desc* d, Plan* pl) {
-  if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
+  if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
+  if (d->w_dtype != 0 && !m1_is16(d->w_dtype)) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
   const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
   if (taps > 32) return false;
@@ -547,8 +549,12 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   }
   const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
   for (int i = 0; i < nw; ++i) a.w[i] = w[i];
-  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pl.n_real, pl.n_total, pl.k_total, taps,
-                                                              reinterpret_cast<__nv_bfloat16*>(w_packed));
+  if (m1_conv_w_dtype(d) == M1_F16)
+    pack_weights_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pl.n_real, pl.n_total, pl.k_total, taps,
+                                                                        reinterpret_cast<__half*>(w_packed));
+  else
+    pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        a, pl.n_real, pl.n_total, pl.k_total, taps, reinterpret_cast<__nv_bfloat16*>(w_packed));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -598,7 +604,7 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
                          (cuuint32_t)(pl.bd * is[0]), 1};
     cuuint32_t es[5] = {1, (cuuint32_t)is[2], (cuuint32_t)is[1], (cuuint32_t)is[0], 1};
     M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d: gathered tensor %d not 16-byte aligned", s);
-    CUresult r = encode(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]),
+    CUresult r = encode(&p.tmA[s], tm_dtype(d->act_dtype), 5, const_cast<void*>(srcs[s]),
                         dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, src %d) failed: %d", s, (int)r);
@@ -612,7 +618,7 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
     cuuint64_t strides[2] = {(cuuint64_t)pl.k_total * 2, (cuuint64_t)pl.k_total * 2 * pl.n_total};
     cuuint32_t box[3] = {(cuuint32_t)pl.ck, (cuuint32_t)pl.n_tile, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed),
+    CUresult r = encode(&p.tmB, tm_dtype(m1_conv_w_dtype(d)), 3, const_cast<void*>(w_packed),
                         dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
@@ -669,9 +675,10 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   p.slot_bytes = pl.slot_bytes;
   p.tx_per_kstep = (uint32_t)(pl.bd * pl.bh * pl.bw) * pl.ck * 2u + (uint32_t)pl.n_tile * pl.ck * 2u;
   p.tmem_cols = pl.tmem_cols;
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.n_tile >> 3) << 17) |
-            ((128u >> 4) << 24);
+  // instruction descriptor: D=f32, A / B format (f16 or bf16, independently), both K-major, N>>3 at [17,23),
+  // M>>4 at [24,29)
+  p.idesc = (1u << 4) | (idesc_fmt(d->act_dtype) << 7) | (idesc_fmt(m1_conv_w_dtype(d)) << 10) |
+            ((uint32_t)(pl.n_tile >> 3) << 17) | ((128u >> 4) << 24);
   // smem descriptor high word: SBO = 8 rows * ck*2 bytes (>>4) at [32,46), version 1 at [46,48),
   // layout type at [61,64): 2 = SW128, 4 = SW64, 6 = SW32; LBO (unused for swizzled K-major) = 1
   const uint32_t sbo = (8u * pl.ck * 2u) >> 4;
@@ -688,7 +695,7 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
       epi_fill_chunks(&p.epi, d, pl.n_tile)) {
     p.epi_tma = 1;
     for (int j = 0; j < d->nout; ++j) {
-      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_c[j], d->out_dhw[2], d->out_dhw[1],
+      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_dtype, d->out_c[j], d->out_dhw[2], d->out_dhw[1],
                                  d->out_dhw[0], d->batch, p.epi.cs[j], pl.bw, pl.bh, pl.bd);
       M1_CHECK(r == 0, "cuTensorMapEncodeTiled(store %d) failed: %d", j, r);
     }

@@ -152,11 +152,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
             for (int g = 0; g < 4; ++g) {
               if (g < g_live) {
                 const uint32_t ag = at + g_off[g];
-                umma_bf16(g_tmem[g], hi | ag, hi | bt, p.idesc, first);
-                if (k16s > 1) umma_bf16(g_tmem[g], hi | (ag + 2u), hi | (bt + 2u), p.idesc, 1u);
+                umma_f16(g_tmem[g], hi | ag, hi | bt, p.idesc, first);
+                if (k16s > 1) umma_f16(g_tmem[g], hi | (ag + 2u), hi | (bt + 2u), p.idesc, 1u);
                 if (k16s > 2) {
-                  umma_bf16(g_tmem[g], hi | (ag + 4u), hi | (bt + 4u), p.idesc, 1u);
-                  umma_bf16(g_tmem[g], hi | (ag + 6u), hi | (bt + 6u), p.idesc, 1u);
+                  umma_f16(g_tmem[g], hi | (ag + 4u), hi | (bt + 4u), p.idesc, 1u);
+                  umma_f16(g_tmem[g], hi | (ag + 6u), hi | (bt + 6u), p.idesc, 1u);
                 }
               }
             }
@@ -234,7 +234,8 @@ struct HaloPlan {
 bool make_halo_plan(const m1_conv_desc* d, HaloPlan* pl) {
   static const int enabled = getenv("M1_HALO") ? atoi(getenv("M1_HALO")) : 1;
   if (!enabled) return false;
-  if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
+  if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
+  if (d->w_dtype != 0 && !m1_is16(d->w_dtype)) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
   for (int i = 0; i < 3; ++i) {
     if (d->stride[i] != 1) return false;
@@ -367,7 +368,7 @@ int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, 
   int koff = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d: gathered tensor %d not 16-byte aligned", s);
-    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], W, H, D, d->batch, pl.ck, pl.P, pl.L, 1);
+    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->act_dtype, d->src_c[s], W, H, D, d->batch, pl.ck, pl.P, pl.L, 1);
     M1_CHECK(r == 0, "cuTensorMapEncodeTiled(halo A %d) failed: %d", s, r);
     p.src_chunks[s] = d->src_c[s] / pl.ck;
     p.src_koff[s] = koff;
@@ -379,7 +380,7 @@ int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, 
     cuuint64_t strides[2] = {(cuuint64_t)pl.k_total * 2, (cuuint64_t)pl.k_total * 2 * pl.n_total};
     cuuint32_t box[3] = {(cuuint32_t)pl.ck, (cuuint32_t)pl.n_tile, (cuuint32_t)(kh * kw)};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides,
+    CUresult r = encode(&p.tmB, tm_dtype(m1_conv_w_dtype(d)), 3, const_cast<void*>(w_packed), dims, strides,
                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.ck), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M1_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo B) failed: %d", (int)r);
@@ -404,7 +405,8 @@ int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, 
   p.a_alloc = pl.a_alloc; p.b_tile_bytes = pl.b_tile_bytes; p.stage_bytes = pl.stage_bytes;
   p.tx_bytes = (uint32_t)(pl.L * pl.P) * pl.ck * 2u + (uint32_t)(kh * kw) * pl.b_tile_bytes;
   p.tmem_cols = pl.tmem_cols;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (idesc_fmt(d->act_dtype) << 7) | (idesc_fmt(m1_conv_w_dtype(d)) << 10) |
+            ((uint32_t)(pl.n_tile >> 3) << 17) | ((128u >> 4) << 24);
   p.desc_hi = ((8u * pl.ck * 2u) >> 4) | (1u << 14) | (layout_for(pl.ck) << 29);
   M1_CHECK(epi_fill(&p.epi, d, bias, outs), "m1_conv3d: too many produced channels for the tcgen05 epilogue table");
   for (int j = 0; j < d->nout; ++j)
@@ -421,7 +423,8 @@ int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, 
   if (g_epi_tma && epi_fill_chunks(&p.epi, d, pl.n_tile)) {
     p.epi_tma = 1;
     for (int j = 0; j < d->nout; ++j) {
-      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_c[j], W, H, D, d->batch, p.epi.cs[j], pl.bw, 1, 1);
+      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_dtype, d->out_c[j], W, H, D, d->batch, p.epi.cs[j],
+                                 pl.bw, 1, 1);
       M1_CHECK(r == 0, "cuTensorMapEncodeTiled(halo store %d) failed: %d", j, r);
     }
     smem_bytes = std::max(smem_bytes, 2048u + 128u * (uint32_t)pl.n_tile * 2u);

@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
             uint32_t a_t = a_m;
             for (int tp = 0; tp < p.tpg; ++tp) {   // accumulator = (M sub-tile, tap)
               uint32_t a_k = a_t, b_k = b0;
-              umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, it ? 1u : 0u);
+              umma_f16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, it ? 1u : 0u);
               for (int k = 1; k < k16s; ++k) {
                 a_k += a_kstep; b_k += b_kstep;
-                umma_bf16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, 1u);
+                umma_f16(d_t, a_hi | a_k, b_hi | b_k, p.idesc, 1u);
               }
               a_t += p.shift ? a_row16 : a_tap16;
               d_t += (uint32_t)p.n_tile;
@@ -288,7 +288,7 @@ struct WgPlan {
 
 bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
   if (d->mode != M1_CONV_FWD) return false;
-  if (d->act_dtype != M1_BF16 || d->out_dtype != M1_BF16) return false;
+  if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
   for (int i = 0; i < 3; ++i)
     if (d->stride[i] < 1 || d->stride[i] > 2) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC) return false;
@@ -462,7 +462,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   int blk = 0, goff = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     M1_CHECK(((uintptr_t)srcs[s] & 15) == 0, "m1_conv3d_wgrad: gathered tensor %d not 16-byte aligned", s);
-    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->src_c[s], d->in_dhw[2], d->in_dhw[1], d->in_dhw[0],
+    int r = encode_ndhwc(encode, &p.tmA[s], srcs[s], d->act_dtype, d->src_c[s], d->in_dhw[2], d->in_dhw[1], d->in_dhw[0],
                          d->batch, pl.ck, pl.bw, pl.bh, pl.bd, d->stride[2], d->stride[1], d->stride[0]);
     M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad A %d) failed: %d", s, r);
     if (!pl.taps_in_m) {
@@ -490,7 +490,8 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
     int nb = 0, acc = 0;
     for (int o = 0; o < jn; ++o) {
       const int j = j0 + o;
-      int r = encode_ndhwc(encode, &p.tmB[o], douts[j], d->out_c[j], W, H, D, d->batch, pl.cb, pl.bw, pl.bh, pl.bd);
+      int r = encode_ndhwc(encode, &p.tmB[o], douts[j], d->out_dtype, d->out_c[j], W, H, D, d->batch, pl.cb, pl.bw, pl.bh,
+                           pl.bd);
       M1_CHECK(r == 0, "cuTensorMapEncodeTiled(wgrad B %d) failed: %d", j, r);
       for (int c0 = 0; c0 < d->out_c[j]; c0 += pl.cb) {
         p.nb_out[nb] = (uint8_t)o;
@@ -526,9 +527,10 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.a_tap_bytes = pl.a_tap_bytes; p.b_off = pl.b_off; p.stage_bytes = pl.stage_bytes;
   p.a_blk_bytes = pl.a_blk_bytes; p.b_blk_bytes = pl.b_blk_bytes;
   p.tmem_cols = pl.tmem_cols;
-  // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(pl.n_tile >> 3) << 17) |
-            ((128u >> 4) << 24);
+  // D = f32, A = activations (f16 or bf16), B = output gradients (bf16, or f16), both MN-major (bits 15, 16),
+  // N >> 3 at [17,23), M >> 4 at [24,29)
+  p.idesc = (1u << 4) | (idesc_fmt(d->act_dtype) << 7) | (idesc_fmt(d->out_dtype) << 10) | (1u << 15) | (1u << 16) |
+            ((uint32_t)(pl.n_tile >> 3) << 17) | ((128u >> 4) << 24);
   // MN-major descriptors: SBO = 8 voxel rows of a block, LBO = one block (next channel block)
   p.a_desc_hi = ((8u * pl.ck * 2u) >> 4) | (1u << 14) | (layout_for(pl.ck) << 29);
   p.b_desc_hi = ((8u * pl.cb * 2u) >> 4) | (1u << 14) | (layout_for(pl.cb) << 29);

@@ -3,10 +3,12 @@
 //       R:networks.py:473,576; R:network_blocks.py:38-44,55,58,104
 //   K5  squeeze (GAP), excite (conv6 -> lrelu -> conv7 -> sigmoid), gate * residual -> lrelu
 //       -> dropout, R:network_blocks.py:68-78 + R:network_blocks.py:137-143 (tf.nn.dropout)
-// All tensors are [batch][voxels][C] (NDHWC flattened); statistics/parameters are fp32.
-// Vectorised 8 channels per thread (16-byte bf16 / 2 x 16-byte fp32 accesses), per-(sample,channel)
-// reductions go warp-shuffle-free through shared-memory accumulators and one global atomic per
-// (block, channel).
+// All tensors are [batch][voxels][C] (NDHWC flattened); statistics/parameters are fp32. Forward VALUES are
+// fp32 / bf16 / fp16 (TV), activation GRADIENTS fp32 / bf16 / bf16 (TG, m1_grad_dtype).
+// Vectorised 8 channels per thread (16-byte 16-bit / 2 x 16-byte fp32 accesses). Every per-(sample, channel)
+// reduction is DETERMINISTIC: fixed-order shuffles inside a warp, per-warp slots in shared memory summed in
+// slot order, per-block partial sums in a scratch buffer summed in block order by the last block to finish
+// (ticket counter) - no floating-point atomics, so two runs of the forward pass are bit-identical.
 #include "common.cuh"
 #include <algorithm>
 
@@ -14,20 +16,12 @@ namespace {
 
 constexpr int TB = 256;
 
-// ---- generic loaders: VW = 8 / 4 channels per thread (16-byte bf16 / 2x16-byte fp32 accesses) or 1
-// (scalar fallback for odd channel counts); value arrays always have 8 slots --------------------
+// ---- generic loaders: VW = 8 / 4 channels per thread or 1 (scalar fallback for odd channel counts); value
+// arrays always have 8 slots --------------------
 template <typename T, int VW>
 __device__ __forceinline__ void ldv(const T* p, float (&v)[8]) {
   if constexpr (VW == 8) {
-    if constexpr (sizeof(T) == 2) {
-      const uint4 u = *reinterpret_cast<const uint4*>(p);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-    } else {
-      const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
+    ld8v<T>(p, v);
   } else if constexpr (VW == 4) {
     float t[4];
     Vec4<T>::load(p, t);
@@ -39,16 +33,7 @@ __device__ __forceinline__ void ldv(const T* p, float (&v)[8]) {
 template <typename T, int VW>
 __device__ __forceinline__ void stv(T* p, const float (&v)[8]) {
   if constexpr (VW == 8) {
-    if constexpr (sizeof(T) == 2) {
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      *reinterpret_cast<uint4*>(p) = u;
-    } else {
-      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
+    st8v<T>(p, v);
   } else if constexpr (VW == 4) {
     const float t[4] = {v[0], v[1], v[2], v[3]};
     Vec4<T>::store(p, t);
@@ -76,41 +61,46 @@ __device__ __forceinline__ void ld_stats(const float* st, float (&mean)[8], floa
   for (int i = 0; i < VW; ++i) { mean[i] = st[2 * i]; rstd[i] = st[2 * i + 1]; }
 }
 
-// Raw (unconverted) vector of VW channels: what a load returns before anything depends on it. The skeletons
-// below first issue the loads of UNR rows x NT tensors into RawVec registers and only then start converting
-// and computing - explicit memory-level parallelism (these kernels are latency bound on long-scoreboard
-// stalls otherwise: ~50 KB must be in flight per SM to saturate HBM3e).
-template <typename T, int VW>
+// Raw (unconverted) vector of VW channels of ES-byte elements: what a load returns before anything depends on
+// it. The skeletons below first issue the loads of UNR rows x NT tensors into RawVec registers and only then
+// start converting and computing - explicit memory-level parallelism (these kernels are latency bound on
+// long-scoreboard stalls otherwise: ~50 KB must be in flight per SM to saturate HBM3e). The element TYPE is
+// only needed by unpack<T>: the streamed tensors of one kernel may mix fp16 values and bf16 gradients.
+template <int ES, int VW>
 struct RawVec {
-  static constexpr int kWords = (int)(sizeof(T) * VW + 3) / 4;
+  static constexpr int kWords = (ES * VW + 3) / 4;
   uint32_t w[kWords];
-  __device__ __forceinline__ void load(const T* p) {
-    if constexpr (sizeof(T) * VW == 32) {
+  __device__ __forceinline__ void load(const void* base, int64_t elem) {
+    const char* p = reinterpret_cast<const char*>(base) + elem * ES;
+    if constexpr (ES * VW == 32) {
       const uint4 a = *reinterpret_cast<const uint4*>(p), b = *(reinterpret_cast<const uint4*>(p) + 1);
       w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    } else if constexpr (sizeof(T) * VW == 16) {
+    } else if constexpr (ES * VW == 16) {
       const uint4 a = *reinterpret_cast<const uint4*>(p);
       w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    } else if constexpr (sizeof(T) * VW == 8) {
+    } else if constexpr (ES * VW == 8) {
       const uint2 a = *reinterpret_cast<const uint2*>(p);
       w[0] = a.x; w[1] = a.y;
-    } else if constexpr (sizeof(T) == 4) {
+    } else if constexpr (ES == 4) {
       w[0] = *reinterpret_cast<const uint32_t*>(p);
     } else {
       w[0] = *reinterpret_cast<const uint16_t*>(p);
     }
   }
+  template <typename T>
   __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    if constexpr (sizeof(T) == 4) {
+    static_assert(sizeof(T) == ES, "element type does not match the raw vector");
+    if constexpr (ES == 4) {
 #pragma unroll
       for (int i = 0; i < VW; ++i) v[i] = __uint_as_float(w[i]);
     } else if constexpr (VW == 1) {
-      v[0] = __uint_as_float(w[0] << 16);
+      v[0] = cvt2<T>(w[0]).x;
     } else {
 #pragma unroll
       for (int i = 0; i < VW / 2; ++i) {
-        v[2 * i] = __uint_as_float(w[i] << 16);            // bf16 -> fp32: the bits are the high half
-        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        const float2 f = cvt2<T>(w[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
       }
     }
   }
@@ -121,20 +111,29 @@ struct RawVec {
 // into registers by `prep(cbase)`, then the thread streams rows [slab*rows_per_slab, ...) with stride
 // `lanes` - one vector access per tensor and row, no index arithmetic, no parameter traffic in the loop.
 // Consecutive threads cover consecutive channel groups of a row, then the next row: fully coalesced.
-// src[t]: the NT streamed tensors of this sample; F gets the raw vectors of one row.
+// src[t]: the NT streamed tensors of this sample (ES-byte elements); F gets the raw vectors of one row.
 //
-// reduce_rows: F(row, cbase, regs, raw[NT], acc[K][8]) accumulates; the block folds its partial sums through
-// warp shuffles + shared memory and issues one global atomic per (block, channel, k).
-template <int K, int VW, int UNR, int NT, typename T, typename P, typename F>
-__device__ __forceinline__ void reduce_rows(const T* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
-                                            float* smem, float* gout /* [C][K] of this sample */, float scale,
-                                            P prep, F f) {
+// reduce_rows: F(row, cbase, regs, raw[NT], acc[K][8]) accumulates. Deterministic fold (see the file header):
+// warp shuffles -> shared-memory slots -> `part` [(sample, slab)][K*C] in the scratch of the context -> the last
+// block of the sample (ticket in counter[sample], self-resetting) sums the slabs in order and calls
+// FIN(c, totals[K]) once per channel.
+struct ReduceScratch {
+  float* part;            // [batch * slabs][K * C]
+  unsigned int* counter;  // [batch], zero between launches
+};
+
+template <int K, int VW, int UNR, int NT, int ES, typename P, typename F, typename FIN>
+__device__ __forceinline__ void reduce_rows(const void* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
+                                            float* smem, ReduceScratch rs, P prep, F f, FIN fin) {
   const int CG = C / VW;
   const int cgs = min(CG, TB);
   const int lanes = TB / cgs;
   const int my_lane = threadIdx.x / cgs;
-  for (int i = threadIdx.x; i < K * C; i += TB) smem[i] = 0.f;
-  __syncthreads();
+  // lanes of a warp that own the same channel group (cgs < 32: lane ids congruent mod cgs) fold their partial
+  // sums with shuffles first (power of two: every thread of the block is active); slot = warp, else slot = lane
+  const bool fold = cgs < 32 && (cgs & (cgs - 1)) == 0;
+  const int nslots = fold ? TB / 32 : lanes;
+  const int slot = fold ? (int)(threadIdx.x >> 5) : my_lane;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_slab;
   const int64_t r1 = min(r0 + rows_per_slab, voxels);
   if (my_lane < lanes) {
@@ -150,23 +149,20 @@ __device__ __forceinline__ void reduce_rows(const T* const (&src)[NT], int64_t v
       int64_t r = r0 + my_lane;
       int64_t off = r * C + cbase;
       for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
-        RawVec<T, VW> raw[UNR][NT];
+        RawVec<ES, VW> raw[UNR][NT];
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
 #pragma unroll
-          for (int t = 0; t < NT; ++t) raw[u][t].load(src[t] + off + u * step);
+          for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, cbase, regs, raw[u], acc);
       }
       for (; r < r1; r += lanes, off += step) {
-        RawVec<T, VW> raw[NT];
+        RawVec<ES, VW> raw[NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) raw[t].load(src[t] + off);
+        for (int t = 0; t < NT; ++t) raw[t].load(src[t], off);
         f(r, cbase, regs, raw, acc);
       }
-      // lanes of a warp that own the same channel group (cgs < 32: lane ids congruent mod cgs) fold their
-      // partial sums with shuffles first: one shared-memory atomic per (warp, channel, k) instead of per thread
-      const bool fold = cgs < 32 && (cgs & (cgs - 1)) == 0;     // power of two: every thread of the block is active
       if (fold) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -178,21 +174,47 @@ __device__ __forceinline__ void reduce_rows(const T* const (&src)[NT], int64_t v
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-          for (int i = 0; i < VW; ++i) atomicAdd(&smem[k * C + cbase + i], acc[k][i]);
+          for (int i = 0; i < VW; ++i) smem[(slot * K + k) * C + cbase + i] = acc[k][i];
       }
     }
   }
   __syncthreads();
+  const int n = blockIdx.y, slabs = gridDim.x;
+  float* mine = rs.part + ((int64_t)n * slabs + blockIdx.x) * (K * C);
   for (int i = threadIdx.x; i < K * C; i += TB) {
-    const int k = i / C, c = i % C;
-    atomicAdd(&gout[c * K + k], smem[i] * scale);
+    float t = 0.f;
+    for (int sl = 0; sl < nslots; ++sl) t += smem[sl * K * C + i];
+    mine[i] = t;
   }
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicInc(rs.counter + n, (unsigned)(slabs - 1));   // wraps to 0: self-resetting
+  __syncthreads();
+  if (s_ticket != (unsigned)(slabs - 1)) return;
+  __threadfence();
+  const float* all = rs.part + (int64_t)n * slabs * (K * C);
+  for (int c = threadIdx.x; c < C; c += TB) {
+    float tot[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) tot[k] = 0.f;
+    for (int sl = 0; sl < slabs; ++sl)
+#pragma unroll
+      for (int k = 0; k < K; ++k) tot[k] += __ldcg(all + (int64_t)sl * (K * C) + k * C + c);
+    fin(c, tot);
+  }
+}
+// shared-memory floats of reduce_rows<K> for C channels of VW-wide groups
+inline size_t reduce_smem(int K, int C, int VW) {
+  const int CG = C / VW, cgs = std::min(CG, TB), lanes = TB / cgs;
+  const bool fold = cgs < 32 && (cgs & (cgs - 1)) == 0;
+  return (size_t)(fold ? TB / 32 : lanes) * K * C * sizeof(float);
 }
 
 // stream_rows: pure elementwise pass, F(row, element offset, cbase, regs, raw[NT]) computes and stores one row's
 // channel group (element offset = row * C + cbase inside the sample)
-template <int VW, int UNR, int NT, typename T, typename P, typename F>
-__device__ __forceinline__ void stream_rows(const T* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
+template <int VW, int UNR, int NT, int ES, typename P, typename F>
+__device__ __forceinline__ void stream_rows(const void* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
                                             P prep, F f) {
   const int CG = C / VW;
   const int cgs = min(CG, TB);
@@ -208,18 +230,18 @@ __device__ __forceinline__ void stream_rows(const T* const (&src)[NT], int64_t v
     int64_t r = r0 + my_lane;
     int64_t off = r * C + cbase;
     for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
-      RawVec<T, VW> raw[UNR][NT];
+      RawVec<ES, VW> raw[UNR][NT];
 #pragma unroll
       for (int u = 0; u < UNR; ++u)
 #pragma unroll
-        for (int t = 0; t < NT; ++t) raw[u][t].load(src[t] + off + u * step);
+        for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
 #pragma unroll
       for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, off + u * step, cbase, regs, raw[u]);
     }
     for (; r < r1; r += lanes, off += step) {
-      RawVec<T, VW> raw[NT];
+      RawVec<ES, VW> raw[NT];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) raw[t].load(src[t] + off);
+      for (int t = 0; t < NT; ++t) raw[t].load(src[t], off);
       f(r, off, cbase, regs, raw);
     }
   }
@@ -249,29 +271,29 @@ __device__ __forceinline__ NormRegs norm_regs(const float* st /* [C][2] of the s
 // ---------------------------------------------------------------------------------------------
 // K4 forward
 // ---------------------------------------------------------------------------------------------
+// stats[n][c] = (mean, rstd) over the voxels of sample n; the last block of a sample finalises
 template <typename T, int VW>
-__global__ void __launch_bounds__(TB) inorm_sums_kernel(const T* __restrict__ x, int64_t voxels, int C,
-                                                       int64_t rows_per_slab, float* __restrict__ sums) {
+__global__ void __launch_bounds__(TB) inorm_stats_kernel(const T* __restrict__ x, int64_t voxels, int C,
+                                                        int64_t rows_per_slab, float inv_v, float eps,
+                                                        ReduceScratch rs, float* __restrict__ stats) {
   extern __shared__ float smem[];
   const int n = blockIdx.y;
-  const T* const src[1] = {x + (int64_t)n * voxels * C};
-  reduce_rows<2, VW, 8, 1>(src, voxels, C, rows_per_slab, smem, sums + (int64_t)n * C * 2, 1.f, [](int) { return 0; },
-                     [&](int64_t, int, int, const RawVec<T, VW> (&raw)[1], float (&acc)[2][8]) {
-                       float v[8];
-                       raw[0].unpack(v);
+  const void* const src[1] = {x + (int64_t)n * voxels * C};
+  float* st = stats + (int64_t)n * C * 2;
+  reduce_rows<2, VW, 8, 1, sizeof(T)>(
+      src, voxels, C, rows_per_slab, smem, rs, [](int) { return 0; },
+      [&](int64_t, int, int, const RawVec<sizeof(T), VW> (&raw)[1], float (&acc)[2][8]) {
+        float v[8];
+        raw[0].template unpack<T>(v);
 #pragma unroll
-                       for (int i = 0; i < VW; ++i) { acc[0][i] += v[i]; acc[1][i] = fmaf(v[i], v[i], acc[1][i]); }
-                     });
-}
-
-__global__ void inorm_finalize_kernel(float* __restrict__ stats, int total, float inv_v, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const float s1 = stats[2 * i], s2 = stats[2 * i + 1];
-  const float mean = s1 * inv_v;
-  const float var = fmaxf(s2 * inv_v - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
+        for (int i = 0; i < VW; ++i) { acc[0][i] += v[i]; acc[1][i] = fmaf(v[i], v[i], acc[1][i]); }
+      },
+      [&](int c, const float (&t)[2]) {
+        const float mean = t[0] * inv_v;
+        const float var = fmaxf(t[1] * inv_v - mean * mean, 0.f);
+        st[2 * c] = mean;
+        st[2 * c + 1] = rsqrtf(var + eps);
+      });
 }
 
 template <typename T, int VW>
@@ -280,13 +302,13 @@ __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__
                                                           const float* __restrict__ beta, int64_t voxels, int C,
                                                           float slope, T* __restrict__ y, int64_t rows_per_slab) {
   const int n = blockIdx.y;
-  const T* const src[1] = {x + (int64_t)n * voxels * C};
+  const void* const src[1] = {x + (int64_t)n * voxels * C};
   T* yb = y + (int64_t)n * voxels * C;
-  stream_rows<VW, 8, 1>(src, voxels, C, rows_per_slab,
+  stream_rows<VW, 8, 1, sizeof(T)>(src, voxels, C, rows_per_slab,
                   [&](int cbase) { return norm_regs<VW>(stats + (int64_t)n * C * 2, gamma, beta, cbase); },
-                  [&](int64_t, int64_t off, int, const NormRegs& q, const RawVec<T, VW> (&raw)[1]) {
+                  [&](int64_t, int64_t off, int, const NormRegs& q, const RawVec<sizeof(T), VW> (&raw)[1]) {
                     float v[8];
-                    raw[0].unpack(v);
+                    raw[0].template unpack<T>(v);
 #pragma unroll
                     for (int k = 0; k < VW; ++k) v[k] = lrelu(fmaf(v[k], q.a[k], q.b[k]), slope);
                     stv<T, VW>(yb + off, v);
@@ -296,30 +318,34 @@ __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__
 // ---------------------------------------------------------------------------------------------
 // K4 backward: red[n][c] = (sum g, sum g*xhat), g = dy * act'(y)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VW>
-__global__ void __launch_bounds__(TB) inorm_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, typename TG, int VW>
+__global__ void __launch_bounds__(TB) inorm_bwd_reduce_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int64_t voxels,
                                                              int C, float slope, int64_t rows_per_slab,
-                                                             float* __restrict__ red) {
+                                                             ReduceScratch rs, float* __restrict__ red) {
+  static_assert(sizeof(T) == sizeof(TG), "value and gradient storage must have the same width");
   extern __shared__ float smem[];
   const int n = blockIdx.y;
-  const T* const src[2] = {x + (int64_t)n * voxels * C, dy + (int64_t)n * voxels * C};
-  reduce_rows<2, VW, 4, 2>(src, voxels, C, rows_per_slab, smem, red + (int64_t)n * C * 2, 1.f,
-                     [&](int cbase) { return norm_regs<VW>(stats + (int64_t)n * C * 2, gamma, beta, cbase); },
-                     [&](int64_t, int, const NormRegs& q, const RawVec<T, VW> (&raw)[2], float (&acc)[2][8]) {
-                       float v[8], d[8];
-                       raw[0].unpack(v);
-                       raw[1].unpack(d);
+  const void* const src[2] = {x + (int64_t)n * voxels * C, dy + (int64_t)n * voxels * C};
+  float* out = red + (int64_t)n * C * 2;
+  reduce_rows<2, VW, 4, 2, sizeof(T)>(
+      src, voxels, C, rows_per_slab, smem, rs,
+      [&](int cbase) { return norm_regs<VW>(stats + (int64_t)n * C * 2, gamma, beta, cbase); },
+      [&](int64_t, int, const NormRegs& q, const RawVec<sizeof(T), VW> (&raw)[2], float (&acc)[2][8]) {
+        float v[8], d[8];
+        raw[0].template unpack<T>(v);
+        raw[1].template unpack<TG>(d);
 #pragma unroll
-                       for (int i = 0; i < VW; ++i) {
-                         const float xh = (v[i] - q.mean[i]) * q.rstd[i];
-                         const float gg = d[i] * (fmaf(v[i], q.a[i], q.b[i]) > 0.f ? 1.f : slope);
-                         acc[0][i] += gg;
-                         acc[1][i] = fmaf(gg, xh, acc[1][i]);
-                       }
-                     });
+        for (int i = 0; i < VW; ++i) {
+          const float xh = (v[i] - q.mean[i]) * q.rstd[i];
+          const float gg = d[i] * (fmaf(v[i], q.a[i], q.b[i]) > 0.f ? 1.f : slope);
+          acc[0][i] += gg;
+          acc[1][i] = fmaf(gg, xh, acc[1][i]);
+        }
+      },
+      [&](int c, const float (&t)[2]) { out[2 * c] = t[0]; out[2 * c + 1] = t[1]; });
 }
 
 struct NormBwdRegs {
@@ -327,19 +353,19 @@ struct NormBwdRegs {
   float c1[8], c2[8];      // (sum g) / V, (sum g * xhat) / V
 };
 
-template <typename T, int VW>
-__global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, typename TG, int VW>
+__global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ red, int64_t voxels, int C,
-                                                            float slope, float inv_v, T* __restrict__ dx,
+                                                            float slope, float inv_v, TG* __restrict__ dx,
                                                             int accumulate, int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
-  const T* const src[2] = {x + base, dy + base};
-  T* dxb = dx + base;
-  stream_rows<VW, 4, 2>(src, voxels, C, rows_per_slab,
+  const void* const src[2] = {x + base, dy + base};
+  TG* dxb = dx + base;
+  stream_rows<VW, 4, 2, sizeof(T)>(src, voxels, C, rows_per_slab,
                   [&](int cbase) {
                     NormBwdRegs w;
                     w.q = norm_regs<VW>(stats + (int64_t)n * C * 2, gamma, beta, cbase);
@@ -348,11 +374,11 @@ __global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const T* __restrict
                     for (int k = 0; k < VW; ++k) { w.c1[k] = rd[2 * k] * inv_v; w.c2[k] = rd[2 * k + 1] * inv_v; }
                     return w;
                   },
-                  [&](int64_t, int64_t off, int, const NormBwdRegs& w, const RawVec<T, VW> (&raw)[2]) {
+                  [&](int64_t, int64_t off, int, const NormBwdRegs& w, const RawVec<sizeof(T), VW> (&raw)[2]) {
                     float v[8], d[8], o[8];
-                    raw[0].unpack(v);
-                    raw[1].unpack(d);
-                    if (accumulate) ldv<T, VW>(dxb + off, o);
+                    raw[0].template unpack<T>(v);
+                    raw[1].template unpack<TG>(d);
+                    if (accumulate) ldv<TG, VW>(dxb + off, o);
 #pragma unroll
                     for (int k = 0; k < VW; ++k) {
                       const float xh = (v[k] - w.q.mean[k]) * w.q.rstd[k];
@@ -360,7 +386,7 @@ __global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const T* __restrict
                       const float t = w.q.a[k] * (gg - w.c1[k] - xh * w.c2[k]);
                       o[k] = accumulate ? o[k] + t : t;
                     }
-                    stv<T, VW>(dxb + off, o);
+                    stv<TG, VW>(dxb + off, o);
                   });
 }
 
@@ -383,23 +409,16 @@ __global__ void param_grad_kernel(const float* __restrict__ red, int K, int ig, 
 // ---------------------------------------------------------------------------------------------
 // K5: squeeze / excite / gate
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VW>
-__global__ void __launch_bounds__(TB) se_squeeze_kernel(const T* __restrict__ raw3, const float* __restrict__ stats3,
-                                                       const float* __restrict__ gamma3,
-                                                       const float* __restrict__ beta3, int64_t voxels, int C,
-                                                       int64_t rows_per_slab, float inv_v,
-                                                       float* __restrict__ pool) {
-  extern __shared__ float smem[];
-  const int n = blockIdx.y;
-  const T* const src[1] = {raw3 + (int64_t)n * voxels * C};
-  reduce_rows<1, VW, 8, 1>(src, voxels, C, rows_per_slab, smem, pool + (int64_t)n * C, inv_v,
-                     [&](int cbase) { return norm_regs<VW>(stats3 + (int64_t)n * C * 2, gamma3, beta3, cbase); },
-                     [&](int64_t, int, const NormRegs& q, const RawVec<T, VW> (&raw)[1], float (&acc)[1][8]) {
-                       float v[8];
-                       raw[0].unpack(v);
-#pragma unroll
-                       for (int i = 0; i < VW; ++i) acc[0][i] += fmaf(v[i], q.a[i], q.b[i]);
-                     });
+// pool = GAP(norm3(raw3)) = a * mean(raw3) + b with a = rstd * gamma, b = beta - mean * a (Q6: == beta up to
+// rounding). The mean IS the reduction of the statistics pass over raw3, so the squeeze needs no second read of
+// the tensor: one thread per (sample, channel).
+__global__ void se_squeeze_kernel(const float* __restrict__ stats3, const float* __restrict__ gamma3,
+                                  const float* __restrict__ beta3, int batch, int C, float* __restrict__ pool) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * C) return;
+  const int c = i % C;
+  const float mean = stats3[2 * i], a = stats3[2 * i + 1] * gamma3[c];
+  pool[i] = fmaf(mean, a, beta3[c] - mean * a);
 }
 
 // one block per sample; C <= 2048, Cr <= 256
@@ -560,13 +579,13 @@ __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ r
                                                         T* __restrict__ out, int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
-  const T* const src[2] = {raw3 + base, raw4 + base};
-  stream_rows<VW, 4, 2>(src, voxels, C, rows_per_slab, [&](int cbase) { return gate_regs<VW>(a, n, C, cbase); },
-                  [&](int64_t, int64_t off, int, const GateRegs& w, const RawVec<T, VW> (&raw)[2]) {
+  const void* const src[2] = {raw3 + base, raw4 + base};
+  stream_rows<VW, 4, 2, sizeof(T)>(src, voxels, C, rows_per_slab, [&](int cbase) { return gate_regs<VW>(a, n, C, cbase); },
+                  [&](int64_t, int64_t off, int, const GateRegs& w, const RawVec<sizeof(T), VW> (&raw)[2]) {
                     const int64_t e = base + off;
                     float x3[8], x4[8], f[8], o[8];
-                    raw[0].unpack(x3);
-                    raw[1].unpack(x4);
+                    raw[0].template unpack<T>(x3);
+                    raw[1].template unpack<T>(x4);
                     drop_factors<VW>(dr, e, f);
 #pragma unroll
                     for (int k = 0; k < VW; ++k) {
@@ -578,45 +597,49 @@ __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ r
                   });
 }
 
-// red[n][c] = { sum dx_, sum dx_*xh3, sum dr, sum dr*xh4 } ; dgate[n][c] = sum dz*x_*r
-template <typename T, int VW>
-__global__ void __launch_bounds__(TB) se_gate_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ raw3,
+// red[n][c] = { sum dx_, sum dx_*xh3, sum dr, sum dr*xh4, sum dz*x_*r } ; dgate[n][c] = the last one
+template <typename T, typename TG, int VW>
+__global__ void __launch_bounds__(TB) se_gate_bwd_reduce_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
                                                                const T* __restrict__ raw4, GateArgs a, DropArgs dr,
                                                                int64_t voxels, int C, int64_t rows_per_slab,
-                                                               float* __restrict__ red5) {
+                                                               ReduceScratch rs, float* __restrict__ red5,
+                                                               float* __restrict__ dgate) {
+  static_assert(sizeof(T) == sizeof(TG), "value and gradient storage must have the same width");
   extern __shared__ float smem[];
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
-  const T* const src[3] = {raw3 + base, raw4 + base, dout + base};
-  reduce_rows<5, VW, 4, 3>(src, voxels, C, rows_per_slab, smem, red5 + (int64_t)n * C * 5, 1.f,
-                     [&](int cbase) { return gate_regs<VW>(a, n, C, cbase); },
-                     [&](int64_t r, int cbase, const GateRegs& w, const RawVec<T, VW> (&raw)[3], float (&acc)[5][8]) {
-                       const int64_t e = base + r * C + cbase;
-                       float x3[8], x4[8], d[8], f[8];
-                       raw[0].unpack(x3);
-                       raw[1].unpack(x4);
-                       raw[2].unpack(d);
-                       drop_factors<VW, true>(dr, e, f);
+  const void* const src[3] = {raw3 + base, raw4 + base, dout + base};
+  float* out = red5 + (int64_t)n * C * 5;
+  float* dg = dgate + (int64_t)n * C;
+  reduce_rows<5, VW, 4, 3, sizeof(T)>(
+      src, voxels, C, rows_per_slab, smem, rs, [&](int cbase) { return gate_regs<VW>(a, n, C, cbase); },
+      [&](int64_t r, int cbase, const GateRegs& w, const RawVec<sizeof(T), VW> (&raw)[3], float (&acc)[5][8]) {
+        const int64_t e = base + r * C + cbase;
+        float x3[8], x4[8], d[8], f[8];
+        raw[0].template unpack<T>(x3);
+        raw[1].template unpack<T>(x4);
+        raw[2].template unpack<TG>(d);
+        drop_factors<VW, true>(dr, e, f);
 #pragma unroll
-                       for (int k = 0; k < VW; ++k) {
-                         const float xh3 = (x3[k] - w.q3.mean[k]) * w.q3.rstd[k];
-                         const float xh4 = (x4[k] - w.q4.mean[k]) * w.q4.rstd[k];
-                         const float x_ = fmaf(x3[k], w.q3.a[k], w.q3.b[k]), res = fmaf(x4[k], w.q4.a[k], w.q4.b[k]);
-                         const float z = x_ * w.gt[k] * res;
-                         const float dz = d[k] * f[k] * (z > 0.f ? 1.f : M1_LRELU_SLOPE);
-                         const float dx_ = dz * w.gt[k] * res, dres = dz * x_ * w.gt[k];
-                         acc[0][k] += dx_;
-                         acc[1][k] = fmaf(dx_, xh3, acc[1][k]);
-                         acc[2][k] += dres;
-                         acc[3][k] = fmaf(dres, xh4, acc[3][k]);
-                         acc[4][k] = fmaf(dz * x_, res, acc[4][k]);
-                       }
-                     });
-}
-
-__global__ void extract_dgate_kernel(const float* __restrict__ red5, int total, float* __restrict__ dgate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) dgate[i] = red5[(int64_t)i * 5 + 4];
+        for (int k = 0; k < VW; ++k) {
+          const float xh3 = (x3[k] - w.q3.mean[k]) * w.q3.rstd[k];
+          const float xh4 = (x4[k] - w.q4.mean[k]) * w.q4.rstd[k];
+          const float x_ = fmaf(x3[k], w.q3.a[k], w.q3.b[k]), res = fmaf(x4[k], w.q4.a[k], w.q4.b[k]);
+          const float z = x_ * w.gt[k] * res;
+          const float dz = d[k] * f[k] * (z > 0.f ? 1.f : M1_LRELU_SLOPE);
+          const float dx_ = dz * w.gt[k] * res, dres = dz * x_ * w.gt[k];
+          acc[0][k] += dx_;
+          acc[1][k] = fmaf(dx_, xh3, acc[1][k]);
+          acc[2][k] += dres;
+          acc[3][k] = fmaf(dres, xh4, acc[3][k]);
+          acc[4][k] = fmaf(dz * x_, res, acc[4][k]);
+        }
+      },
+      [&](int c, const float (&t)[5]) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out[5 * c + k] = t[k];
+        dg[c] = t[4];
+      });
 }
 
 struct GateBwdRegs {
@@ -624,16 +647,16 @@ struct GateBwdRegs {
   float c[4][8];      // the four reduction results / V
 };
 
-template <typename T, int VW>
-__global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ raw3,
+template <typename T, typename TG, int VW>
+__global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
                                                               const T* __restrict__ raw4, GateArgs a, DropArgs dr,
                                                               const float* __restrict__ red5, int64_t voxels, int C,
-                                                              float inv_v, T* __restrict__ draw3,
-                                                              T* __restrict__ draw4, int64_t rows_per_slab) {
+                                                              float inv_v, TG* __restrict__ draw3,
+                                                              TG* __restrict__ draw4, int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
-  const T* const src[3] = {raw3 + base, raw4 + base, dout + base};
-  stream_rows<VW, 4, 3>(src, voxels, C, rows_per_slab,
+  const void* const src[3] = {raw3 + base, raw4 + base, dout + base};
+  stream_rows<VW, 4, 3, sizeof(T)>(src, voxels, C, rows_per_slab,
                   [&](int cbase) {
                     GateBwdRegs g;
                     g.w = gate_regs<VW>(a, n, C, cbase);
@@ -644,13 +667,13 @@ __global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const T* __restri
                       for (int j = 0; j < 4; ++j) g.c[j][k] = rd[5 * k + j] * inv_v;
                     return g;
                   },
-                  [&](int64_t, int64_t off, int, const GateBwdRegs& g, const RawVec<T, VW> (&raw)[3]) {
+                  [&](int64_t, int64_t off, int, const GateBwdRegs& g, const RawVec<sizeof(T), VW> (&raw)[3]) {
                     const GateRegs& w = g.w;
                     const int64_t e = base + off;
                     float x3[8], x4[8], d[8], f[8], o3[8], o4[8];
-                    raw[0].unpack(x3);
-                    raw[1].unpack(x4);
-                    raw[2].unpack(d);
+                    raw[0].template unpack<T>(x3);
+                    raw[1].template unpack<T>(x4);
+                    raw[2].template unpack<TG>(d);
                     drop_factors<VW, true>(dr, e, f);
 #pragma unroll
                     for (int k = 0; k < VW; ++k) {
@@ -664,8 +687,8 @@ __global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const T* __restri
                       o3[k] = w.q3.a[k] * (dx_ - g.c[0][k] - xh3 * g.c[1][k]);
                       o4[k] = w.q4.a[k] * (dres - g.c[2][k] - xh4 * g.c[3][k]);
                     }
-                    stv<T, VW>(draw3 + e, o3);
-                    stv<T, VW>(draw4 + e, o4);
+                    stv<TG, VW>(draw3 + e, o3);
+                    stv<TG, VW>(draw4 + e, o4);
                   });
 }
 
@@ -687,26 +710,11 @@ inline int64_t slab_rows(const m1_ctx* ctx, int batch, int64_t voxels, int per_s
     if ((C) % 4 == 0) { constexpr int VW = 4; __VA_ARGS__; }             \
     else { constexpr int VW = 1; __VA_ARGS__; }                          \
   } while (0)
-#define DISPATCH_T_VW4(dtype, C, ...)                                    \
-  do {                                                                   \
-    if ((dtype) == M1_BF16) {                                            \
-      using T = __nv_bfloat16;                                           \
-      DISPATCH_VW4_(C, __VA_ARGS__);                                     \
-    } else {                                                             \
-      using T = float;                                                   \
-      DISPATCH_VW4_(C, __VA_ARGS__);                                     \
-    }                                                                    \
-  } while (0)
-#define DISPATCH_T_VW(dtype, C, ...)                                     \
-  do {                                                                   \
-    if ((dtype) == M1_BF16) {                                            \
-      using T = __nv_bfloat16;                                           \
-      DISPATCH_VW_(C, __VA_ARGS__);                                      \
-    } else {                                                             \
-      using T = float;                                                   \
-      DISPATCH_VW_(C, __VA_ARGS__);                                      \
-    }                                                                    \
-  } while (0)
+// value type T (+ its gradient type TG) x vector width
+#define DISPATCH_T_VW(dtype, C, ...) M1_DISPATCH_VG(dtype, T, TG, DISPATCH_VW_(C, __VA_ARGS__))
+#define DISPATCH_T_VW4(dtype, C, ...) M1_DISPATCH_VG(dtype, T, TG, DISPATCH_VW4_(C, __VA_ARGS__))
+inline int vw_of(int C) { return C % 8 == 0 ? 8 : C % 4 == 0 ? 4 : 1; }
+inline int vw4_of(int C) { return C % 4 == 0 ? 4 : 1; }
 
 DropArgs make_drop(const m1_dropout* d) {
   DropArgs a;
@@ -720,19 +728,27 @@ DropArgs make_drop(const m1_dropout* d) {
   return a;
 }
 
+// scratch of the deterministic reductions for a (slabs x batch) grid of K*C partial sums per block
+int reduce_scratch(m1_ctx* ctx, int64_t slabs, int batch, int K, int C, ReduceScratch* rs) {
+  M1_CHECK(batch <= kGridSumCounter, "reduction: batch %d exceeds the ticket counters", batch);
+  M1_CHECK((size_t)slabs * batch * K * C * sizeof(float) <= ctx->partial_bytes,
+           "reduction: partial sums (%lld blocks x %d) exceed the context scratch", (long long)slabs * batch, K * C);
+  rs->part = ctx->partial;
+  rs->counter = ctx->counters;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int m1_inorm_stats(m1_ctx* ctx, const void* x, int dtype, int batch, int64_t voxels, int C,
                               float eps, float* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  M1_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * C * 2 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (inorm_sums_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
-                              reinterpret_cast<const T*>(x), voxels, C, rows, stats)));
-  M1_LAUNCH_CHECK(ctx);
-  const int total = batch * C;
-  inorm_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(stats, total, 1.f / (float)voxels, eps);
+  ReduceScratch rs;
+  if (reduce_scratch(ctx, grid.x, batch, 2, C, &rs)) return 1;
+  DISPATCH_T_VW(dtype, C, (inorm_stats_kernel<T, VW><<<grid, TB, reduce_smem(2, C, VW), st>>>(
+                              reinterpret_cast<const T*>(x), voxels, C, rows, 1.f / (float)voxels, eps, rs, stats)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -757,19 +773,20 @@ extern "C" int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, cons
   cudaStream_t st = (cudaStream_t)stream;
   M1_CHECK((size_t)batch * C * 2 * sizeof(float) <= ctx->scratch_bytes, "inorm_act_bwd: scratch too small");
   float* red = ctx->scratch;
-  M1_CUDA(cudaMemsetAsync(red, 0, (size_t)batch * C * 2 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW4(dtype, C, (inorm_bwd_reduce_kernel<T, VW><<<grid, TB, 2 * C * sizeof(float), st>>>(
-                              reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta,
-                              voxels, C, slope, rows, red)));
+  ReduceScratch rs;
+  if (reduce_scratch(ctx, grid.x, batch, 2, C, &rs)) return 1;
+  DISPATCH_T_VW4(dtype, C, (inorm_bwd_reduce_kernel<T, TG, VW><<<grid, TB, reduce_smem(2, C, VW), st>>>(
+                              reinterpret_cast<const TG*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta,
+                              voxels, C, slope, rows, rs, red)));
   M1_LAUNCH_CHECK(ctx);
   {
     const int64_t rows8 = slab_rows(ctx, batch, voxels, 8);
     dim3 grid8((unsigned)cdiv64(voxels, rows8), (unsigned)batch);
-    DISPATCH_T_VW4(dtype, C, (inorm_bwd_apply_kernel<T, VW><<<grid8, TB, 0, st>>>(
-                               reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta, red,
-                               voxels, C, slope, 1.f / (float)voxels, reinterpret_cast<T*>(dx), accumulate, rows8)));
+    DISPATCH_T_VW4(dtype, C, (inorm_bwd_apply_kernel<T, TG, VW><<<grid8, TB, 0, st>>>(
+                               reinterpret_cast<const TG*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta, red,
+                               voxels, C, slope, 1.f / (float)voxels, reinterpret_cast<TG*>(dx), accumulate, rows8)));
   }
   M1_LAUNCH_CHECK(ctx);
   if (dgamma || dbeta) {
@@ -782,13 +799,9 @@ extern "C" int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, cons
 extern "C" int m1_se_squeeze(m1_ctx* ctx, const void* raw3, const float* stats3, const float* gamma3,
                              const float* beta3, int dtype, int batch, int64_t voxels, int C, float* pool,
                              void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  M1_CUDA(cudaMemsetAsync(pool, 0, (size_t)batch * C * sizeof(float), st));
-  const int64_t rows = slab_rows(ctx, batch, voxels);
-  dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW(dtype, C, (se_squeeze_kernel<T, VW><<<grid, TB, C * sizeof(float), st>>>(
-                              reinterpret_cast<const T*>(raw3), stats3, gamma3, beta3, voxels, C, rows,
-                              1.f / (float)voxels, pool)));
+  (void)raw3; (void)dtype; (void)voxels;      // the statistics of raw3 already hold its mean (see the kernel)
+  const int total = batch * C;
+  se_squeeze_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats3, gamma3, beta3, batch, C, pool);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -835,15 +848,13 @@ extern "C" int m1_se_gate_bwd_reduce(m1_ctx* ctx, const void* dout, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   GateArgs a{stats3, stats4, gamma3, beta3, gamma4, beta4, gate};
   DropArgs dr = make_drop(drop);
-  M1_CUDA(cudaMemsetAsync(red, 0, (size_t)batch * C * 5 * sizeof(float), st));
   const int64_t rows = slab_rows(ctx, batch, voxels);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-  DISPATCH_T_VW4(dtype, C, (se_gate_bwd_reduce_kernel<T, VW><<<grid, TB, 5 * C * sizeof(float), st>>>(
-                              reinterpret_cast<const T*>(dout), reinterpret_cast<const T*>(raw3),
-                              reinterpret_cast<const T*>(raw4), a, dr, voxels, C, rows, red)));
-  M1_LAUNCH_CHECK(ctx);
-  const int total = batch * C;
-  extract_dgate_kernel<<<(total + 255) / 256, 256, 0, st>>>(red, total, dgate);
+  ReduceScratch rs;
+  if (reduce_scratch(ctx, grid.x, batch, 5, C, &rs)) return 1;
+  DISPATCH_T_VW4(dtype, C, (se_gate_bwd_reduce_kernel<T, TG, VW><<<grid, TB, reduce_smem(5, C, VW), st>>>(
+                              reinterpret_cast<const TG*>(dout), reinterpret_cast<const T*>(raw3),
+                              reinterpret_cast<const T*>(raw4), a, dr, voxels, C, rows, rs, red, dgate)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -861,10 +872,10 @@ extern "C" int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* r
   {
     const int64_t rows = slab_rows(ctx, batch, voxels, 8);
     dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
-    DISPATCH_T_VW4(dtype, C, (se_gate_bwd_apply_kernel<T, VW><<<grid, TB, 0, st>>>(
-                               reinterpret_cast<const T*>(dout), reinterpret_cast<const T*>(raw3),
+    DISPATCH_T_VW4(dtype, C, (se_gate_bwd_apply_kernel<T, TG, VW><<<grid, TB, 0, st>>>(
+                               reinterpret_cast<const TG*>(dout), reinterpret_cast<const T*>(raw3),
                                reinterpret_cast<const T*>(raw4), a, dr, red, voxels, C, 1.f / (float)voxels,
-                               reinterpret_cast<T*>(draw3), reinterpret_cast<T*>(draw4), rows)));
+                               reinterpret_cast<TG*>(draw3), reinterpret_cast<TG*>(draw4), rows)));
   }
   M1_LAUNCH_CHECK(ctx);
   // norm3: dgamma += sum_n A2, dbeta += sum_n (A1 + dpool) ; norm4: dgamma += sum_n B2, dbeta += sum_n B1

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const f
                                                  float* __restrict__ vhat, int64_t n, float lr_t,
                                                  const float* __restrict__ lr_dev, float b1,
                                                  float b2, float eps, float l2, float gscale,
-                                                 float* __restrict__ l2_out) {
+                                                 float* __restrict__ l2_out, GridSum gs) {
   __shared__ float sm[TB / 32];
   if (lr_dev != nullptr) lr_t = *lr_dev;      // graph replay: the step size lives in device memory
   float acc[1] = {0.f};
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const f
   }
   if (l2_out) {
     block_sum<1, TB>(acc, sm);
-    if (threadIdx.x == 0) atomicAdd(l2_out, acc[0] * l2);
+    grid_sum_add<TB>(acc[0], l2, l2_out, gs, sm);
   }
 }
 
@@ -122,7 +122,7 @@ extern "C" int m1_adam_amsgrad(m1_ctx* ctx, float* w, const float* g, float* m, 
   M1_CHECK((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vhat) & 15) == 0,
            "m1_adam_amsgrad: buffers must be 16-byte aligned");
   adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, lr_t, nullptr, beta1, beta2,
-                                                                   eps, l2, gscale, l2_sq_out);
+                                                                   eps, l2, gscale, l2_sq_out, m1_grid_sum(ctx));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -134,18 +134,14 @@ extern "C" int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float*
            "m1_adam_amsgrad_dev: buffers must be 16-byte aligned");
   M1_CHECK(lr_t_dev != nullptr, "m1_adam_amsgrad_dev: lr_t_dev is NULL");
   adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, 0.f, lr_t_dev, beta1, beta2,
-                                                                   eps, l2, gscale, l2_sq_out);
+                                                                   eps, l2, gscale, l2_sq_out, m1_grid_sum(ctx));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 extern "C" int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int ddtype, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  using B = __nv_bfloat16;
-  if (sdtype == M1_F32 && ddtype == M1_BF16) cast_kernel<float, B><<<nb(ctx, n), TB, 0, st>>>((const float*)src, (B*)dst, n);
-  else if (sdtype == M1_BF16 && ddtype == M1_F32) cast_kernel<B, float><<<nb(ctx, n), TB, 0, st>>>((const B*)src, (float*)dst, n);
-  else if (sdtype == M1_F32) cast_kernel<float, float><<<nb(ctx, n), TB, 0, st>>>((const float*)src, (float*)dst, n);
-  else cast_kernel<B, B><<<nb(ctx, n), TB, 0, st>>>((const B*)src, (B*)dst, n);
+  M1_DISPATCH_T2(sdtype, ddtype, S, D, (cast_kernel<S, D><<<nb(ctx, n), TB, 0, st>>>((const S*)src, (D*)dst, n)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -153,25 +149,17 @@ extern "C" int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int 
 extern "C" int m1_copy_channels(m1_ctx* ctx, const void* src, int sdtype, int src_c, int src_off, void* dst,
                                 int ddtype, int dst_c, int dst_off, int c, int64_t rows, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  using B = __nv_bfloat16;
   const int64_t n = rows * c;
   M1_CHECK(src_off + c <= src_c && dst_off + c <= dst_c, "m1_copy_channels: slice out of range");
-  if (sdtype == M1_F32 && ddtype == M1_BF16)
-    copy_channels_kernel<float, B><<<nb(ctx, n), TB, 0, st>>>((const float*)src, src_c, src_off, (B*)dst, dst_c, dst_off, c, rows);
-  else if (sdtype == M1_BF16 && ddtype == M1_F32)
-    copy_channels_kernel<B, float><<<nb(ctx, n), TB, 0, st>>>((const B*)src, src_c, src_off, (float*)dst, dst_c, dst_off, c, rows);
-  else if (sdtype == M1_F32)
-    copy_channels_kernel<float, float><<<nb(ctx, n), TB, 0, st>>>((const float*)src, src_c, src_off, (float*)dst, dst_c, dst_off, c, rows);
-  else
-    copy_channels_kernel<B, B><<<nb(ctx, n), TB, 0, st>>>((const B*)src, src_c, src_off, (B*)dst, dst_c, dst_off, c, rows);
+  M1_DISPATCH_T2(sdtype, ddtype, S, D, (copy_channels_kernel<S, D><<<nb(ctx, n), TB, 0, st>>>(
+                                           (const S*)src, src_c, src_off, (D*)dst, dst_c, dst_off, c, rows)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 extern "C" int m1_axpy(m1_ctx* ctx, const void* x, int dtype, float a, void* y, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == M1_BF16) axpy_kernel<__nv_bfloat16><<<nb(ctx, n), TB, 0, st>>>((const __nv_bfloat16*)x, a, (__nv_bfloat16*)y, n);
-  else axpy_kernel<float><<<nb(ctx, n), TB, 0, st>>>((const float*)x, a, (float*)y, n);
+  M1_DISPATCH_T(dtype, T, (axpy_kernel<T><<<nb(ctx, n), TB, 0, st>>>((const T*)x, a, (T*)y, n)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

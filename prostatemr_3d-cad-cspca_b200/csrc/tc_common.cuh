@@ -60,7 +60,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -91,35 +91,43 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// tensor-map element type of a 16-bit activation / weight tensor (m1_dtype); the idesc operand format field
+inline CUtensorMapDataType tm_dtype(int dt) {
+  return dt == M1_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+// tcgen05 instruction-descriptor operand format of kind::f16: 0 = f16, 1 = bf16 (A at bits [7,10), B at [10,13))
+inline uint32_t idesc_fmt(int dt) { return dt == M1_F16 ? 0u : 1u; }
+
 inline CUtensorMapSwizzle swizzle_for(int ck) {
   return ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 // UMMA shared-memory descriptor layout_type field for rows of ck bf16 elements
 inline uint32_t layout_for(int ck) { return ck == 64 ? 2u : ck == 32 ? 4u : 6u; }
 
-// 5-D map over an NDHWC bf16 tensor: a box of (ck channels, bw, bh, bd voxels, 1 volume) where voxels
+// 5-D map over an NDHWC 16-bit tensor: a box of (ck channels, bw, bh, bd voxels, 1 volume) where voxels
 // are taken every (sw, sh, sd)-th position (TMA element strides; box extent = count * stride)
-inline int encode_ndhwc(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int C, int W, int H, int D, int N,
+inline int encode_ndhwc(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int dt, int C, int W, int H, int D, int N,
                         int ck, int bw, int bh, int bd, int sw = 1, int sh = 1, int sd = 1) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t c2 = (cuuint64_t)C * 2;
   cuuint64_t strides[4] = {c2, c2 * W, c2 * W * H, c2 * W * H * D};
   cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh), (cuuint32_t)(bd * sd), 1};
   cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
-  return (int)encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+  return (int)encode(tm, tm_dtype(dt), 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ck), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-// un-swizzled 5-D map for TMA STORES of a (cs channels, bw, bh, bd, 1) brick of an NDHWC bf16 tensor
-inline int encode_ndhwc_store(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int C, int W, int H, int D, int N,
-                              int cs, int bw, int bh, int bd) {
+// un-swizzled 5-D map for TMA STORES of a (cs channels, bw, bh, bd, 1) brick of an NDHWC 16-bit tensor (the
+// element type matters here: cp.reduce.async.bulk.tensor adds in it)
+inline int encode_ndhwc_store(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int dt, int C, int W, int H, int D,
+                              int N, int cs, int bw, int bh, int bd) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t c2 = (cuuint64_t)C * 2;
   cuuint64_t strides[4] = {c2, c2 * W, c2 * W * H, c2 * W * H * D};
   cuuint32_t box[5] = {(cuuint32_t)cs, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  return (int)encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+  return (int)encode(tm, tm_dtype(dt), 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }

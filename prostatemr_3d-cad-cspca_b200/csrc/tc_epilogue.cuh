@@ -18,6 +18,7 @@ struct EpiOut {
   int out_c[M1_MAX_OUT];
   int accumulate;                 // bitmask over produced tensors
   int n_total;                    // real produced channels (multiple of 8)
+  int out_f16;                    // produced tensors are fp16 (else bf16)
   uint8_t grp_out[kMaxGroups];    // 8-column group -> produced tensor
   uint16_t grp_c[kMaxGroups];     // 8-column group -> first channel inside that tensor
   uint8_t cs[M1_MAX_OUT];         // TMA-store epilogue: channels per store box of each produced tensor
@@ -41,6 +42,7 @@ inline bool epi_fill(EpiOut* e, const m1_conv_desc* d, const float* const* bias,
   }
   e->n_total = total;
   e->accumulate = d->accumulate;
+  e->out_f16 = d->out_dtype == M1_F16;
   return true;
 }
 
@@ -60,7 +62,7 @@ __device__ __forceinline__ void epilogue_row(const EpiOut& e, uint32_t taddr, in
                                              bool valid, int64_t vox, bool zero_acc) {
   for (int j = col_begin; j < col_end; j += 16) {
     uint4 old[2];
-    __nv_bfloat16* dst[2];
+    uint16_t* dst[2];
     const float* bias[2];
     bool live[2];
 #pragma unroll
@@ -69,7 +71,7 @@ __device__ __forceinline__ void epilogue_row(const EpiOut& e, uint32_t taddr, in
       live[h] = valid && gcol < e.n_total;
       const int grp = min(gcol >> 3, kMaxGroups - 1);
       const int o = e.grp_out[grp], c = e.grp_c[grp];
-      dst[h] = reinterpret_cast<__nv_bfloat16*>(e.out[o]) + vox * e.out_c[o] + c;
+      dst[h] = reinterpret_cast<uint16_t*>(e.out[o]) + vox * e.out_c[o] + c;
       bias[h] = e.bias[o] ? e.bias[o] + c : nullptr;
       old[h] = make_uint4(0u, 0u, 0u, 0u);
       if (live[h] && ((e.accumulate >> o) & 1)) old[h] = *reinterpret_cast<const uint4*>(dst[h]);
@@ -89,17 +91,22 @@ __device__ __forceinline__ void epilogue_row(const EpiOut& e, uint32_t taddr, in
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       }
-      const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old[h]);   // zeros unless accumulating
+      const uint32_t ow[4] = {old[h].x, old[h].y, old[h].z, old[h].w};               // zeros unless accumulating
+      uint32_t pk[4];
+      if (e.out_f16) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        f[2 * i] += __low2float(ob[i]);
-        f[2 * i + 1] += __high2float(ob[i]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 o2 = cvt2<__half>(ow[i]);
+          pk[i] = pack2<__half>(f[2 * i] + o2.x, f[2 * i + 1] + o2.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 o2 = cvt2<__nv_bfloat16>(ow[i]);
+          pk[i] = pack2<__nv_bfloat16>(f[2 * i] + o2.x, f[2 * i + 1] + o2.y);
+        }
       }
-      uint4 pk;
-      __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pb[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      *reinterpret_cast<uint4*>(dst[h]) = pk;
+      *reinterpret_cast<uint4*>(dst[h]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -133,10 +140,8 @@ __device__ __forceinline__ void epilogue_row_smem(const EpiOut& e, uint32_t tadd
       }
       uint32_t pk[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&t);
-      }
+      for (int i = 0; i < 4; ++i)
+        pk[i] = e.out_f16 ? pack2<__half>(f[2 * i], f[2 * i + 1]) : pack2<__nv_bfloat16>(f[2 * i], f[2 * i + 1]);
       const int within = c % cs;                                   // channel inside its chunk
       const uint32_t addr = c_base + (uint32_t)(lc - within) * 256u + (uint32_t)row * (uint32_t)(cs * 2) +
                             (uint32_t)within * 2u;

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from ... import _lib, ops
-from ..._lib import BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, F32
+from ..._lib import BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, F16, F32, grad_dtype
 
 LRELU = 0.1
 IN_EPS = 1e-3
@@ -38,8 +38,9 @@ class Act:
         return self.shape[-1]
 
 
-def _code(dtype):
-    return BF16 if dtype == torch.bfloat16 else F32
+_code = _lib.code_of
+
+PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
 class InjectedNoise:
@@ -116,11 +117,20 @@ class LazyHead:
 
 
 class Engine:
-    def __init__(self, params, precision="bf16", device=None, use_tcgen05=True):
-        assert precision in ("bf16", "fp32")
+    def __init__(self, params, precision="fp16", device=None, use_tcgen05=True):
+        """precision: storage type of the activation VALUES - 'fp16' (tcgen05 convolutions on fp16 values and
+        weights, bf16 activation gradients: the mode that meets the 2e-2 / 1e-3 parity bounds at tensor-core
+        speed), 'bf16' (values, gradients and tensor-core weights all bf16) or 'fp32' (CUDA-core convolutions,
+        the 1e-4 parity mode). Accumulation, statistics, parameters and parameter gradients are always fp32."""
+        assert precision in PRECISIONS, precision
         self.params = params
-        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.use_tc = use_tcgen05 and precision == "bf16"
+        self.precision = precision
+        self.act_dtype = PRECISIONS[precision]
+        self.use_tc = use_tcgen05 and precision != "fp32"
+        # packed tensor-core weights of the DATA-GRADIENT launches in fp16 mode: fp16 like the forward pack
+        # (tcgen05.mma.kind::f16 multiplies the bf16 gradients with them directly); M1_DGRAD_W_BF16=1: bf16 pack
+        import os
+        self.dgrad_w = F16 if (precision == "fp16" and os.environ.get("M1_DGRAD_W_BF16", "0") != "1") else 0
         self.tracing = device is None
         self.device = device
         self.ctx = None if self.tracing else _lib.Context.get(torch.device(device).index or 0)
@@ -160,9 +170,13 @@ class Engine:
     def grad_buffer(self, act, zero=False):
         """(tensor, accumulate): allocates act.g on first use."""
         if act.g is None:
-            act.g = (torch.zeros if zero else torch.empty)(act.shape, dtype=act.dtype, device=self.device)
+            act.g = (torch.zeros if zero else torch.empty)(act.shape, dtype=grad_dtype(act.dtype), device=self.device)
             return act.g, False
         return act.g, True
+
+    def new_grad(self, act):
+        """uninitialised gradient tensor of an activation (bf16 for fp16 values, else the value type)"""
+        return self.new(act.shape, grad_dtype(act.dtype))
 
     def _timed(self, cat, flops, fn, label=None):
         if self.prof is None:
@@ -195,7 +209,7 @@ class Engine:
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
     def _gather(self, cat, mode, batch, in_dhw, out_dhw, k, s, pad, src_t, src_c, ws, wstr, bias, out_t, out_c,
-                acc, key, w_by_src=False):
+                acc, key, w_by_src=False, w_dtype=0):
         """One convolution-shaped launch family: outs[j] (+)= gather(concat(src)) * ws[j] (+ bias[j]).
         The tcgen05 engine takes it when every gathered tensor has a multiple of 16 channels; a
         concatenation that mixes such tensors with odd ones (the 1-3 channel latents, R:networks.py:653)
@@ -204,7 +218,7 @@ class Engine:
         vox = batch * int(np.prod(in_dhw if mode == CONV_TRANSPOSED else out_dhw))
         act_code, out_code = _code(src_t[0].dtype), _code(out_t[0].dtype)
         runs = [(0, len(src_t))]
-        if self.use_tc and act_code == BF16 and out_code == BF16 and not w_by_src:
+        if self.use_tc and act_code != F32 and out_code != F32 and not w_by_src:
             ok = [c % 16 == 0 for c in src_c]
             if any(ok) and not all(ok):
                 runs, i = [], 0
@@ -221,7 +235,7 @@ class Engine:
             a_flags = list(acc) if first else [True] * len(out_t)
             d = ops.conv_desc(mode, batch, in_dhw, out_dhw, k, s, pad, list(src_c[i0:i1]), list(out_c), list(wstr),
                               accumulate=a_flags, act_dtype=act_code, out_dtype=out_code,
-                              engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT, w_by_src=w_by_src)
+                              engine=ENGINE_AUTO if self.use_tc else ENGINE_SIMT, w_by_src=w_by_src, w_dtype=w_dtype)
             packed = None
             if self.use_tc and ops.conv3d_tc_supported(d):
                 pk = key + (i0,)
@@ -234,7 +248,7 @@ class Engine:
             b = bias if first else None
             if packed is not None and self.autotune:
                 tk = ("conv", mode, batch, tuple(in_dhw), tuple(out_dhw), k, s, tuple(src_c[i0:i1]), tuple(out_c),
-                      bool(w_by_src))
+                      bool(w_by_src), act_code, out_code, w_dtype)
                 var = self.tuned.get(tk)
                 if var is None:
                     var = self._tune_conv(d, list(src_t[i0:i1]), sub_w, list(out_t), packed)
@@ -403,7 +417,7 @@ class Engine:
             cos = [layers[j][1] for j in live]
             d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], cos,
                               [wstr[j] for j in live], act_dtype=_code(srcs[0].dtype),
-                              out_dtype=_code(outs[live[0]].dtype), engine=auto)
+                              out_dtype=_code(outs[live[0]].g.dtype), engine=auto)
             self._wgrad(d, [a.t for a in srcs], [outs[j].g for j in live],
                         [self.pg(layers[j][0] + "/kernel") for j in live],
                         [self.pg(layers[j][0] + "/bias") for j in live] if bias_grad else None,
@@ -420,7 +434,7 @@ class Engine:
                     self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad,
                                  [outs[j].g for j in live], cos, wv, [(cin * c, 1, c) for c in cos], None,
                                  list(bufs), [a.c for a in srcs], list(accs),
-                                 ("dgrad",) + tuple(layers[j][0] for j in live), w_by_src=True)
+                                 ("dgrad",) + tuple(layers[j][0] for j in live), w_by_src=True, w_dtype=self.dgrad_w)
                 else:
                     for i, j in enumerate(live):
                         co = layers[j][1]
@@ -428,7 +442,7 @@ class Engine:
                         self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [outs[j].g],
                                      [co], wv, [(cin * co, 1, co)] * len(srcs), None, list(bufs),
                                      [a.c for a in srcs], list(accs) if i == 0 else [True] * len(srcs),
-                                     ("dgrad", layers[j][0]))
+                                     ("dgrad", layers[j][0]), w_dtype=self.dgrad_w if outs[j].g.dtype != torch.float32 else 0)
         else:
             co = layers[0][1]
             dy = outs[0].g
@@ -437,7 +451,7 @@ class Engine:
             off = 0
             for a in srcs:
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
-                                  act_dtype=_code(outs[0].dtype), out_dtype=_code(a.dtype), engine=auto)
+                                  act_dtype=_code(dy.dtype), out_dtype=_code(a.dtype), engine=auto)
                 self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
                             layers[0][0] + "(T)")
                 off += a.c
@@ -451,7 +465,7 @@ class Engine:
                     gbuf, acc = self.grad_buffer(a)
                     self._gather("conv_dgrad", CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [dy], [co],
                                  [ws[0].view(-1)[off:]], [(co * cin, cin, 1)], None, [gbuf], [a.c], [acc],
-                                 ("dgradT", layers[0][0], idx))
+                                 ("dgradT", layers[0][0], idx), w_dtype=self.dgrad_w)
                     off += a.c
         for o in outs:
             o.g = None
@@ -523,8 +537,8 @@ class Engine:
             red = self.new((n, c, 5), f32)
             dgate, dpool = self.new((n, c), f32), self.new((n, c), f32)
             assert raw3.g is None and raw4.g is None
-            raw3.g = self.new(raw3.shape, raw3.dtype)
-            raw4.g = self.new(raw4.shape, raw4.dtype)
+            raw3.g = self.new_grad(raw3)
+            raw4.g = self.new_grad(raw4)
 
             def run():
                 ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
@@ -558,20 +572,20 @@ class Engine:
             if y.g is None:
                 return
             assert theta.g is None
-            theta.g = self.new(theta.shape, theta.dtype)
+            theta.g = self.new_grad(theta)
             dphi = self.new(phi.shape, torch.float32, zero=True)
             if x.needs_grad:
                 gx, acc = self.grad_buffer(x)
             else:
-                gx, acc = self.new(x.shape, x.dtype), False
+                gx, acc = self.new_grad(x), False
             self._timed("attn_bwd", 0, lambda: ops.attn_bwd(
                 self.ctx, y.g, theta.t, phi.t, wpsi, psi, x.t, gx, acc, theta.g, dphi,
                 self.pg(name + "/conv3/kernel"), self.pg(name + "/conv3/bias")))
             if phi.g is None:
-                phi.g = self.new(phi.shape, phi.dtype)
+                phi.g = self.new_grad(phi)
                 ops.cast(self.ctx, dphi, phi.g)
             else:
-                tmp = self.new(phi.shape, phi.dtype)
+                tmp = self.new_grad(phi)
                 ops.cast(self.ctx, dphi, tmp)
                 ops.axpy(self.ctx, tmp, 1.0, phi.g)
             y.g = None
@@ -593,7 +607,7 @@ class Engine:
             if z.g is None:
                 return
             gbuf, _ = self.grad_buffer(ml, zero=True)
-            ops.latent_bwd(self.ctx, z.g, ml.t, eps, mode, gbuf)
+            ops.latent_bwd(self.ctx, z.g, ml.t, eps, mode, gbuf, z.dtype)
             z.g = None
         if self.record:
             self._rec(bwd, [])

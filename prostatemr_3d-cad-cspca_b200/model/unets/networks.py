@@ -225,7 +225,10 @@ class M1(LoadableModel):
 
     Constructor arguments up to `name` are the reference's (R:networks.py:34-55), same names, order,
     defaults and assertions. The keyword-only arguments after it are additions of this implementation:
-      precision   'bf16' (tcgen05 tensor-core convolutions, bf16 activations) | 'fp32' (CUDA-core fp32)
+      precision   'fp16' (default: tcgen05 tensor-core convolutions on fp16 activations and weights, bf16
+                  activation gradients, fp32 accumulation - meets the 2e-2 softmax / 1e-3 loss parity bounds)
+                  | 'bf16' (everything the tensor cores see is bf16: same speed, 8-bit mantissa, misses the bounds)
+                  | 'fp32' (CUDA-core fp32 convolutions: the 1e-4 parity mode)
       ds_in_prob  'reference': probabilistic + deep_supervision == no deep supervision (Q3, 2 output channels)
                   'intended' : wires the dead ds_ops branch (R:networks.py:743-747), 4 heads
       seed        parameter-initialisation and Philox seed;   device: CUDA device (None: current)
@@ -255,12 +258,13 @@ class M1(LoadableModel):
                  prob_latent_dims=(3, 2, 1),
                  summary=True,
                  name='UNET-TYPE-M1',
-                 *, precision='bf16', ds_in_prob='reference', seed=0, device=None, build=None,
+                 *, precision='fp16', ds_in_prob='reference', seed=0, device=None, build=None,
                  use_tcgen05=True, compute_dead_branches=False):
         ndims = len(input_spatial_dims)
         assert ndims in [1, 2, 3], 'Variable (ndims) should be  1, 2 or 3. Found: %d.' % ndims
         assert ndims == 3, 'the sm_100a kernels implement the 3-D model (the only one M1Core can build)'
         assert ds_in_prob in ('reference', 'intended')
+        assert precision in ('fp16', 'bf16', 'fp32'), "precision must be 'fp16', 'bf16' or 'fp32'"
         if cascaded is not False:
             raise NotImplementedError(
                 "cascaded two-stage M1 (R:networks.py:109-193) is not wired yet: the m1_decision_fusion kernel and "

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, F32,
+from ._lib import (BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, F16, F32, PROBS,
                    ConvDesc, Dropout, check, current_stream, dtype_code, lib, ptr, ptr_array)
 
 
@@ -21,8 +21,9 @@ def same_pads(size, k, s):
 
 
 def conv_desc(mode, batch, in_dhw, out_dhw, kernel, stride, pad, src_c, out_c, w_strides,
-              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO, out_dtype=None, w_by_src=False):
+              accumulate=False, act_dtype=F32, engine=ENGINE_AUTO, out_dtype=None, w_by_src=False, w_dtype=0):
     d = ConvDesc()
+    d.w_dtype = w_dtype
     d.w_by_src = 1 if w_by_src else 0
     d.mode = mode
     d.batch = batch
@@ -84,7 +85,8 @@ def conv3d_pack_weights(ctx, d, ws):
     nbytes = lib().m1_conv3d_packed_bytes(C.byref(d))
     if nbytes == 0:
         raise _lib.M1Error("conv launch not supported by the tcgen05 engine")
-    packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=ws[0].device)
+    wd = d.w_dtype or d.act_dtype
+    packed = torch.empty(nbytes // 2, dtype=torch.float16 if wd == F16 else torch.bfloat16, device=ws[0].device)
     check(lib().m1_conv3d_pack_weights(ctx.handle, C.byref(d), ptr_array([ptr(w) for w in ws]),
                                        ptr(packed), current_stream()))
     return packed
@@ -208,9 +210,11 @@ def latent_fwd(ctx, ml, eps, mode, z):
                               ptr(z), current_stream()))
 
 
-def latent_bwd(ctx, dz, ml, eps, mode, dml):
+def latent_bwd(ctx, dz, ml, eps, mode, dml, z_dtype=None):
+    """z_dtype: torch dtype of the latent VALUE z (dz is stored as grad_dtype(z_dtype)); None: that of dz"""
     n, v, c2 = _nvc(ml)
-    check(lib().m1_latent_bwd(ctx.handle, ptr(dz), ptr(ml), ptr(eps), mode, n, v, c2 // 2, dtype_code(dz),
+    code = dtype_code(dz) if z_dtype is None else _lib.code_of(z_dtype)
+    check(lib().m1_latent_bwd(ctx.handle, ptr(dz), ptr(ml), ptr(eps), mode, n, v, c2 // 2, code,
                               dz.shape[-1], ptr(dml), current_stream()))
 
 
@@ -231,7 +235,7 @@ def softmax_focal(ctx, logits, y_true, alpha, gamma, up, prob, head_off, head_we
     nc = logits.shape[-1]
     al = (C.c_float * nc)(*[float(a) for a in alpha]) if alpha is not None else None
     check(lib().m1_softmax_focal(
-        ctx.handle, ptr(logits), 2 if from_probs else F32, ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
+        ctx.handle, ptr(logits), PROBS if from_probs else F32, ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
         C.cast(al, C.c_void_p) if al is not None else None, gamma, logits.shape[0], _grid(logits),
         (C.c_int32 * 3)(*up), nc, ptr(prob), prob.shape[-1] if prob is not None else 0, head_off, head_weight,
         ptr(loss_out), ptr(dlogits), grad_scale, current_stream()))

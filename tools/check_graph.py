@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """CUDA-graph replay of the training step vs the eager launch sequence, same model state and Philox step:
-captures at step 2, then re-runs the same steps eagerly from a snapshot and compares losses and weights
-(differences: fp32 atomic summation order only)."""
+captures at step 2, then re-runs the same steps eagerly from a snapshot and compares losses and weights.
+The forward pass is deterministic (fixed-order reductions, no floating-point atomics on forward values), so the
+FIRST compared step - same weights, same Philox step - must agree BIT FOR BIT between graph and eager and between
+two eager runs. Later steps start from weights that carry the split-K fp32 atomics of the weight gradients and
+are compared with a tolerance."""
 import os
 import sys
 
@@ -20,7 +23,8 @@ def main():
     m = unets.networks.M1((8, 32, 32), 4, 2, dropout_mode='monte-carlo', filters=(32, 64, 128, 192, 256),
                           strides=strides, kernel_sizes=kernels, se_reduction=(8,) * 5,
                           att_sub_samp=((1, 1, 1),) * 4, dense_skip=True, deep_supervision=True, probabilistic=True,
-                          prob_latent_dims=(3, 2, 1, 0), summary=False, precision='bf16', device='cuda:0', seed=0)
+                          prob_latent_dims=(3, 2, 1, 0), summary=False, precision=os.environ.get('M1_PRECISION', 'fp16'),
+                          device='cuda:0', seed=0)
     sched = optimizers.CosineDecayRestarts(1e-3, 5, t_mul=2.0, m_mul=1.0, alpha=1e-3)
     m.compile(optimizer=optimizers.Adam(sched, amsgrad=True),
               loss=[losses.Focal(alpha=[0.75, 0.25], gamma=2.0).loss, losses.EvidenceLowerBound().loss],
@@ -61,9 +65,10 @@ def main():
           % (rel[0].max(), rel.max(), floor[0].max(), floor.max()))
     print("worst mean |dw| graph-vs-eager %.3e | eager-vs-eager %.3e | launches per replayed step %d"
           % (wd, wf, m.launches_per_graph_step))
-    # first compared step: same weights, same Philox step -> at the run-to-run floor; later steps diverge
-    # chaotically (bf16 + Adam) in both comparisons
-    assert rel[0].max() < max(3.0 * floor[0].max(), 5e-4), (rel, floor)
+    # first compared step: same weights, same Philox step, deterministic forward -> identical bits
+    assert np.array_equal(lg[0], le[0]), ("graph vs eager, first step", lg[0], le[0])
+    assert np.array_equal(le2[0], le[0]), ("eager vs eager, first step", le2[0], le[0])
+    # later steps: the weights carry fp32 atomic summation-order noise of the weight gradients, amplified by Adam
     assert rel.max() < 5e-2, (rel, floor)
     print("GRAPH OK")
 
