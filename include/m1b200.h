@@ -75,9 +75,9 @@ typedef struct {
   int32_t out_dtype;                  /* m1_dtype of the produced tensors (wgrad: of dout) */
   int32_t engine;                     /* m1_engine */
   /* tcgen05 engine: element type of the packed weight operand (m1_conv3d_pack_weights), M1_BF16 or M1_F16;
-   * 0 = the type of the gathered tensors. tcgen05.mma.kind::f16 takes the two operand formats independently:
-   * the fp16 mode multiplies bf16 gradients with fp16 weights (data gradient) and fp16 activations with bf16
-   * gradients (weight gradient). */
+   * 0 = the type of the gathered tensors, which is the only combination the hardware executes: an instruction
+   * descriptor with different A and B formats traps with "illegal instruction" (measured on B200, both ways).
+   * fp16 mode therefore packs fp16 weights for the forward launches and bf16 weights for the data gradients. */
   int32_t w_dtype;
   /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
    * conv:  tune[0] = engine variant: 1 = one TMA box per filter tap (conv_tc.cu), 2 = halo tile shared by
@@ -146,9 +146,13 @@ int m1_bias_grad(m1_ctx* ctx, const void* dout, int dtype, int64_t rows, int C, 
  * R:networks.py:473,576; R:network_blocks.py:38-44,55,58,104.  stats = [batch][C][2] = mean,rstd */
 int m1_inorm_stats(m1_ctx* ctx, const void* x, int dtype, int batch, int64_t voxels, int C,
                    float eps, float* stats, void* stream);
+/* y_bf16 (here and in m1_se_gate_fwd / m1_attn_fwd): optional second copy of the output rounded to bf16, or NULL.
+ * fp16 mode only: tcgen05.mma.kind::f16 traps (illegal instruction, measured on B200) when its two operands
+ * have different formats, so the tensor-core WEIGHT GRADIENT - activations x bf16 output gradients - reads this
+ * bf16 twin of every activation that feeds a convolution, while the forward pass reads the fp16 tensor. */
 int m1_inorm_act_fwd(m1_ctx* ctx, const void* x, const float* stats, const float* gamma,
                      const float* beta, int dtype, int batch, int64_t voxels, int C,
-                     float slope /* 1 = no activation */, void* y, void* stream);
+                     float slope /* 1 = no activation */, void* y, void* y_bf16, void* stream);
 /* dy: gradient w.r.t. y; x: the raw (pre-norm) tensor; dx written (or accumulated);
  * dgamma/dbeta accumulate. */
 int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, const float* stats,
@@ -193,7 +197,7 @@ int m1_se_gate_fwd(m1_ctx* ctx, const void* raw3, const void* raw4, const float*
                    const float* stats4, const float* gamma3, const float* beta3,
                    const float* gamma4, const float* beta4, const float* gate,
                    const m1_dropout* drop, int dtype, int batch, int64_t voxels, int C,
-                   void* out, void* stream);
+                   void* out, void* out_bf16, void* stream);
 /* Backward of the fused gate INCLUDING the two instance norms: produces draw3/draw4 (gradients
  * w.r.t. the raw conv outputs), dgate [batch][C] (to feed m1_se_excite_bwd) in phase 1, then,
  * after the excite backward produced dpool, phase 2 writes draw3/draw4 and accumulates
@@ -218,7 +222,7 @@ int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* raw3, const 
 int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, const float* w_psi,
                 const float* b_psi, const void* x, int dtype, int batch, const int32_t* tg,
                 const int32_t* gg, const int32_t* xg, int F, int Cx, float* psi, void* y,
-                void* stream);
+                void* y_bf16, void* stream);
 /* dy -> dx (accumulated if acc_dx), dtheta (written), dphi (fp32, accumulated), dw_psi/db_psi acc */
 int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const void* phi,
                 const float* w_psi, const float* psi, const void* x, int dtype, int batch,
@@ -266,18 +270,19 @@ int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype, const flo
                             float head_weight, float* loss_out, void* dfeat, int acc_dfeat, float* dw,
                             float* db, float grad_scale, void* stream);
 
-/* ---- K9: Keras Adam(amsgrad=True) + L2 regulariser gradient, train_model.py:113-120 ---------
- * g' = g*gscale + 2*l2*w ; m,v,vhat update; w -= lr_t * m / (sqrt(vhat) + eps)
+/* ---- K9: Keras Adam (amsgrad=True: train_model.py:113-120; amsgrad=0: the Keras default) + L2 regulariser
+ * gradient.  g' = g*gscale + 2*l2*w ; m,v update; vhat = max(vhat, v) (amsgrad) or v;
+ * w -= lr_t * m / (sqrt(vhat) + eps)
  * l2_sq_out[0] += l2 * sum w^2 (regularisation loss term, R:networks.py:259-263) if non-NULL. */
 int m1_adam_amsgrad(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat,
                     int64_t n, float lr_t, float beta1, float beta2, float eps, float l2,
-                    float gscale, float* l2_sq_out, void* stream);
+                    float gscale, float* l2_sq_out, int amsgrad, void* stream);
 
 /* Same update with the step size read from DEVICE memory (lr_t_dev[0]): the form that can be captured in a
  * CUDA graph and replayed while the learning-rate schedule advances on the host. */
 int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat,
                         int64_t n, const float* lr_t_dev, float beta1, float beta2, float eps, float l2,
-                        float gscale, float* l2_sq_out, void* stream);
+                        float gscale, float* l2_sq_out, int amsgrad, void* stream);
 
 /* ---- small utilities used by the host ------------------------------------------------------- */
 int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int ddtype, int64_t n,

@@ -56,11 +56,13 @@ __device__ __forceinline__ int64_t psi_index(int64_t xv, int n_unused, Grid3 xg,
 template <typename T>
 __global__ void __launch_bounds__(TB) attn_apply_kernel(const T* __restrict__ x, const float* __restrict__ psi,
                                                        Grid3 xg, Grid3 tg, int Cx, T* __restrict__ y,
-                                                       int64_t total) {
+                                                       __nv_bfloat16* __restrict__ y2, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
     int64_t n;
     const int64_t pv = psi_index(i / Cx, 0, xg, tg, &n);
-    st_f<T>(y + i, ld_f<T>(x + i) * psi[pv]);
+    const float v = ld_f<T>(x + i) * psi[pv];
+    st_f<T>(y + i, v);
+    if (y2) st_f<__nv_bfloat16>(y2 + i, v);
   }
 }
 
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(TB) attn_psi_vec_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(TB) attn_scale_vec_kernel(const T* __restrict__ x, const float* __restrict__ psi,
                                                            Grid3 xg, Grid3 tg, int Cx, T* __restrict__ y, int acc,
-                                                           int64_t total8) {
+                                                           int64_t total8, __nv_bfloat16* __restrict__ y2 = nullptr) {
   const int c8 = Cx / 8;
   for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total8; i += (int64_t)gridDim.x * TB) {
     const int64_t xv = i / c8;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(TB) attn_scale_vec_kernel(const T* __restrict_
       for (int k = 0; k < 8; ++k) v[k] *= p;
     }
     store8<T>(y + i * 8, v);
+    if (y2) store8<__nv_bfloat16>(y2 + i * 8, v);
   }
 }
 
@@ -583,9 +586,10 @@ inline Grid3 g3(const int32_t* p) { return Grid3{p[0], p[1], p[2]}; }
 extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, const float* w_psi,
                            const float* b_psi, const void* x, int dtype, int batch, const int32_t* tg,
                            const int32_t* gg, const int32_t* xg, int F, int Cx, float* psi, void* y,
-                           void* stream) {
+                           void* y_bf16, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const Grid3 T3 = g3(tg), G3 = g3(gg), X3 = g3(xg);
+  __nv_bfloat16* y2 = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   M1_CHECK(T3.d % G3.d == 0 && T3.h % G3.h == 0 && T3.w % G3.w == 0 && X3.d % T3.d == 0 && X3.h % T3.h == 0 &&
                X3.w % T3.w == 0,
            "m1_attn_fwd: grids must nest by integer factors");
@@ -598,14 +602,14 @@ extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, cons
     M1_DISPATCH_T(dtype, T, (attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv,
                                                                       T3, G3, F, G, psi)));
     M1_LAUNCH_CHECK(ctx);
-    M1_DISPATCH_T(dtype, T, (attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8)));
+    M1_DISPATCH_T(dtype, T, (attn_scale_vec_kernel<T><<<sb, TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, 0, total / 8, y2)));
     M1_LAUNCH_CHECK(ctx);
     return 0;
   }
   M1_DISPATCH_T(dtype, T, (attn_psi_kernel<T><<<nblocks(ctx, tv, TB / 32), TB, 0, st>>>((const T*)theta, (const T*)phi,
                                                                                        w_psi, b_psi, batch, T3, G3, F, psi)));
   M1_LAUNCH_CHECK(ctx);
-  M1_DISPATCH_T(dtype, T, (attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, total)));
+  M1_DISPATCH_T(dtype, T, (attn_apply_kernel<T><<<nblocks(ctx, total), TB, 0, st>>>((const T*)x, psi, X3, T3, Cx, (T*)y, y2, total)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -418,7 +418,8 @@ struct Plan {
 
 bool make_plan(const m1_conv_desc* d, Plan* pl) {
   if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
-  if (d->w_dtype != 0 && !m1_is16(d->w_dtype)) return false;
+  // one operand format per MMA: kind::f16 with different A / B formats is an illegal instruction on sm_100
+  if (d->w_dtype != 0 && d->w_dtype != d->act_dtype) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
   const int taps = d->kernel[0] * d->kernel[1] * d->kernel[2];
   if (taps > 32) return false;

@@ -235,7 +235,8 @@ bool make_halo_plan(const m1_conv_desc* d, HaloPlan* pl) {
   static const int enabled = getenv("M1_HALO") ? atoi(getenv("M1_HALO")) : 1;
   if (!enabled) return false;
   if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
-  if (d->w_dtype != 0 && !m1_is16(d->w_dtype)) return false;
+  // one operand format per MMA: kind::f16 with different A / B formats is an illegal instruction on sm_100
+  if (d->w_dtype != 0 && d->w_dtype != d->act_dtype) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC || d->nout < 1 || d->nout > M1_MAX_OUT) return false;
   for (int i = 0; i < 3; ++i) {
     if (d->stride[i] != 1) return false;

@@ -288,7 +288,8 @@ struct WgPlan {
 
 bool make_wg_plan(const m1_conv_desc* d, int j0, int jn, WgPlan* pl) {
   if (d->mode != M1_CONV_FWD) return false;
-  if (!m1_is16(d->act_dtype) || !m1_is16(d->out_dtype)) return false;
+  // activations and output gradients must share one 16-bit format (kind::f16 with mixed operand formats traps)
+  if (!m1_is16(d->act_dtype) || d->out_dtype != d->act_dtype) return false;
   for (int i = 0; i < 3; ++i)
     if (d->stride[i] < 1 || d->stride[i] > 2) return false;
   if (d->nsrc < 1 || d->nsrc > M1_MAX_SRC) return false;
@@ -527,7 +528,7 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   p.a_tap_bytes = pl.a_tap_bytes; p.b_off = pl.b_off; p.stage_bytes = pl.stage_bytes;
   p.a_blk_bytes = pl.a_blk_bytes; p.b_blk_bytes = pl.b_blk_bytes;
   p.tmem_cols = pl.tmem_cols;
-  // D = f32, A = activations (f16 or bf16), B = output gradients (bf16, or f16), both MN-major (bits 15, 16),
+  // D = f32, A = activations, B = output gradients (one common format: bf16, or f16), both MN-major (bits 15, 16),
   // N >> 3 at [17,23), M >> 4 at [24,29)
   p.idesc = (1u << 4) | (idesc_fmt(d->act_dtype) << 7) | (idesc_fmt(d->out_dtype) << 10) | (1u << 15) | (1u << 16) |
             ((uint32_t)(pl.n_tile >> 3) << 17) | ((128u >> 4) << 24);

@@ -300,10 +300,12 @@ template <typename T, int VW>
 __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int64_t voxels, int C,
-                                                          float slope, T* __restrict__ y, int64_t rows_per_slab) {
+                                                          float slope, T* __restrict__ y,
+                                                          __nv_bfloat16* __restrict__ y2, int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const void* const src[1] = {x + (int64_t)n * voxels * C};
   T* yb = y + (int64_t)n * voxels * C;
+  __nv_bfloat16* y2b = y2 ? y2 + (int64_t)n * voxels * C : nullptr;      // optional bf16 twin of the output
   stream_rows<VW, 8, 1, sizeof(T)>(src, voxels, C, rows_per_slab,
                   [&](int cbase) { return norm_regs<VW>(stats + (int64_t)n * C * 2, gamma, beta, cbase); },
                   [&](int64_t, int64_t off, int, const NormRegs& q, const RawVec<sizeof(T), VW> (&raw)[1]) {
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__
 #pragma unroll
                     for (int k = 0; k < VW; ++k) v[k] = lrelu(fmaf(v[k], q.a[k], q.b[k]), slope);
                     stv<T, VW>(yb + off, v);
+                    if (y2b) stv<__nv_bfloat16, VW>(y2b + off, v);
                   });
 }
 
@@ -576,7 +579,8 @@ __device__ __forceinline__ GateRegs gate_regs(const GateArgs& a, int n, int C, i
 template <typename T, int VW>
 __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ raw3, const T* __restrict__ raw4,
                                                         GateArgs a, DropArgs dr, int64_t voxels, int C,
-                                                        T* __restrict__ out, int64_t rows_per_slab) {
+                                                        T* __restrict__ out, __nv_bfloat16* __restrict__ out2,
+                                                        int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
   const void* const src[2] = {raw3 + base, raw4 + base};
@@ -594,6 +598,7 @@ __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ r
                       o[k] = lrelu(x_ * w.gt[k] * res, M1_LRELU_SLOPE) * f[k];
                     }
                     stv<T, VW>(out + e, o);
+                    if (out2) stv<__nv_bfloat16, VW>(out2 + e, o);
                   });
 }
 
@@ -755,13 +760,13 @@ extern "C" int m1_inorm_stats(m1_ctx* ctx, const void* x, int dtype, int batch, 
 
 extern "C" int m1_inorm_act_fwd(m1_ctx* ctx, const void* x, const float* stats, const float* gamma,
                                 const float* beta, int dtype, int batch, int64_t voxels, int C, float slope,
-                                void* y, void* stream) {
+                                void* y, void* y_bf16, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = slab_rows(ctx, batch, voxels, 8);
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
   DISPATCH_T_VW(dtype, C, (inorm_act_fwd_kernel<T, VW><<<grid, TB, 0, st>>>(
                              reinterpret_cast<const T*>(x), stats, gamma, beta, voxels, C, slope,
-                             reinterpret_cast<T*>(y), rows)));
+                             reinterpret_cast<T*>(y), reinterpret_cast<__nv_bfloat16*>(y_bf16), rows)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -827,7 +832,7 @@ extern "C" int m1_se_excite_bwd(m1_ctx* ctx, const float* dgate, const float* po
 extern "C" int m1_se_gate_fwd(m1_ctx* ctx, const void* raw3, const void* raw4, const float* stats3,
                               const float* stats4, const float* gamma3, const float* beta3, const float* gamma4,
                               const float* beta4, const float* gate, const m1_dropout* drop, int dtype, int batch,
-                              int64_t voxels, int C, void* out, void* stream) {
+                              int64_t voxels, int C, void* out, void* out_bf16, void* stream) {
   GateArgs a{stats3, stats4, gamma3, beta3, gamma4, beta4, gate};
   DropArgs dr = make_drop(drop);
   M1_CHECK(dr.mask == nullptr || C % 8 == 0, "m1_se_gate_fwd: the dropout keep-mask needs C %% 8 == 0 (C = %d)", C);
@@ -835,7 +840,7 @@ extern "C" int m1_se_gate_fwd(m1_ctx* ctx, const void* raw3, const void* raw4, c
   dim3 grid((unsigned)cdiv64(voxels, rows), (unsigned)batch);
   DISPATCH_T_VW(dtype, C, (se_gate_fwd_kernel<T, VW><<<grid, TB, 0, (cudaStream_t)stream>>>(
                              reinterpret_cast<const T*>(raw3), reinterpret_cast<const T*>(raw4), a, dr, voxels, C,
-                             reinterpret_cast<T*>(out), rows)));
+                             reinterpret_cast<T*>(out), reinterpret_cast<__nv_bfloat16*>(out_bf16), rows)));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

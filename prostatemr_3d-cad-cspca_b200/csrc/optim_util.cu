@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const f
                                                  float* __restrict__ m, float* __restrict__ v,
                                                  float* __restrict__ vhat, int64_t n, float lr_t,
                                                  const float* __restrict__ lr_dev, float b1,
-                                                 float b2, float eps, float l2, float gscale,
+                                                 float b2, float eps, float l2, float gscale, int amsgrad,
                                                  float* __restrict__ l2_out, GridSum gs) {
   __shared__ float sm[TB / 32];
   if (lr_dev != nullptr) lr_t = *lr_dev;      // graph replay: the step size lives in device memory
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const f
       const float gg = fmaf(2.f * l2, pw[k], pg[k] * gscale);
       pm[k] = b1 * pm[k] + (1.f - b1) * gg;
       pv[k] = b2 * pv[k] + (1.f - b2) * gg * gg;
-      ph[k] = fmaxf(ph[k], pv[k]);
+      ph[k] = amsgrad ? fmaxf(ph[k], pv[k]) : pv[k];      // plain Adam: the denominator is sqrt(v)
       pw[k] -= lr_t * pm[k] / (sqrtf(ph[k]) + eps);
     }
     reinterpret_cast<float4*>(w)[i] = W;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(TB) adam_kernel(float* __restrict__ w, const f
     const float gg = fmaf(2.f * l2, w[i], g[i] * gscale);
     m[i] = b1 * m[i] + (1.f - b1) * gg;
     v[i] = b2 * v[i] + (1.f - b2) * gg * gg;
-    vhat[i] = fmaxf(vhat[i], v[i]);
+    vhat[i] = amsgrad ? fmaxf(vhat[i], v[i]) : v[i];
     w[i] -= lr_t * m[i] / (sqrtf(vhat[i]) + eps);
   }
   if (l2_out) {
@@ -118,23 +118,23 @@ inline unsigned nb(const m1_ctx* ctx, int64_t n) {
 
 extern "C" int m1_adam_amsgrad(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat, int64_t n,
                                float lr_t, float beta1, float beta2, float eps, float l2, float gscale,
-                               float* l2_sq_out, void* stream) {
+                               float* l2_sq_out, int amsgrad, void* stream) {
   M1_CHECK((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vhat) & 15) == 0,
            "m1_adam_amsgrad: buffers must be 16-byte aligned");
   adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, lr_t, nullptr, beta1, beta2,
-                                                                   eps, l2, gscale, l2_sq_out, m1_grid_sum(ctx));
+                                                                   eps, l2, gscale, amsgrad, l2_sq_out, m1_grid_sum(ctx));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 extern "C" int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float* m, float* v, float* vhat, int64_t n,
                                    const float* lr_t_dev, float beta1, float beta2, float eps, float l2,
-                                   float gscale, float* l2_sq_out, void* stream) {
+                                   float gscale, float* l2_sq_out, int amsgrad, void* stream) {
   M1_CHECK((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vhat) & 15) == 0,
            "m1_adam_amsgrad_dev: buffers must be 16-byte aligned");
   M1_CHECK(lr_t_dev != nullptr, "m1_adam_amsgrad_dev: lr_t_dev is NULL");
   adam_kernel<<<nb(ctx, n / 4 + 1), TB, 0, (cudaStream_t)stream>>>(w, g, m, v, vhat, n, 0.f, lr_t_dev, beta1, beta2,
-                                                                   eps, l2, gscale, l2_sq_out, m1_grid_sum(ctx));
+                                                                   eps, l2, gscale, amsgrad, l2_sq_out, m1_grid_sum(ctx));
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }

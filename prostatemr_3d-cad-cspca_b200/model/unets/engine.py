@@ -17,13 +17,14 @@ IN_EPS = 1e-3
 
 class Act:
     """An NDHWC activation: shape, device tensor (None while tracing) and its gradient."""
-    __slots__ = ("shape", "t", "g", "dtype", "needs_grad", "lc")
+    __slots__ = ("shape", "t", "g", "dtype", "needs_grad", "lc", "tw")
 
     def __init__(self, shape, dtype, t=None, needs_grad=True, lc=None):
         self.shape = tuple(int(s) for s in shape)
         self.dtype = dtype
         self.t = t
         self.g = None
+        self.tw = None      # fp16 mode, training: bf16 twin of t - the operand of the tensor-core weight gradients
         self.needs_grad = needs_grad
         # logical (reference) channel count; shape[-1] is the physical one, zero-padded to the tensor-core
         # granularity for the few-channel tensors (f/4 = 8 bottlenecks, 3-4 channel inputs, 1-3 channel latents)
@@ -127,10 +128,15 @@ class Engine:
         self.precision = precision
         self.act_dtype = PRECISIONS[precision]
         self.use_tc = use_tcgen05 and precision != "fp32"
-        # packed tensor-core weights of the DATA-GRADIENT launches in fp16 mode: fp16 like the forward pack
-        # (tcgen05.mma.kind::f16 multiplies the bf16 gradients with them directly); M1_DGRAD_W_BF16=1: bf16 pack
-        import os
-        self.dgrad_w = F16 if (precision == "fp16" and os.environ.get("M1_DGRAD_W_BF16", "0") != "1") else 0
+        # tcgen05.mma.kind::f16 traps when its two operands have different formats (measured on B200, both ways).
+        # fp16 mode therefore runs   forward        fp16 activations x fp16 weight pack
+        #                            data gradient  bf16 gradients   x bf16 weight pack (w_dtype 0 = as gathered)
+        #                            weight gradient bf16 TWIN of the activations x bf16 gradients
+        # The twin is written by the kernel that produces the activation (second store of the same registers)
+        # or, for tensors produced by a convolution epilogue / the input, by one cast the first time a weight
+        # gradient needs it.
+        self.twins = precision == "fp16" and self.use_tc
+        self.dgrad_w = 0
         self.tracing = device is None
         self.device = device
         self.ctx = None if self.tracing else _lib.Context.get(torch.device(device).index or 0)
@@ -142,6 +148,7 @@ class Engine:
         self.autotune = True       # one-off timing of candidate tcgen05 tilings per layer shape
         self.tuned = {}
         self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
+        self.bwd_flops = 0         # ... of the data-gradient and weight-gradient launches actually executed
         self.trace_log = []        # TRACE mode: one record per convolution launch (tools/list_launches.py, tests)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -174,6 +181,21 @@ class Engine:
             return act.g, False
         return act.g, True
 
+    def new_twin(self, act):
+        """bf16 twin buffer for an activation being produced (None unless fp16-mode training)"""
+        if self.twins and self.record and not self.tracing and act.dtype == torch.float16:
+            act.tw = self.new(act.shape, torch.bfloat16)
+        return act.tw
+
+    def x16(self, act):
+        """the tensor a tensor-core weight gradient reads for activation `act`: its bf16 twin in fp16 mode"""
+        if not self.twins or act.dtype != torch.float16:
+            return act.t
+        if act.tw is None:
+            act.tw = self.new(act.shape, torch.bfloat16)
+            ops.cast(self.ctx, act.t, act.tw)
+        return act.tw
+
     def new_grad(self, act):
         """uninitialised gradient tensor of an activation (bf16 for fp16 values, else the value type)"""
         return self.new(act.shape, grad_dtype(act.dtype))
@@ -191,6 +213,7 @@ class Engine:
         self.tape = []
         self.record = record
         self.conv_flops = 0
+        self.bwd_flops = 0
         self.param_uses = {}
 
     def _rec(self, fn, names):
@@ -411,14 +434,21 @@ class Engine:
         taps = int(np.prod(k))
         need = [a for a in srcs if a.needs_grad]
         assert not need or len(need) == len(srcs), "mixed needs_grad inside one concatenation"
+        # algorithmic (reference-channel) FLOPs of what runs below: one weight gradient, one data gradient if needed
+        lvox = batch * int(np.prod(in_dhw if transposed else out_dhw))
+        lfl = 2 * lvox * taps * sum(a.lc for a in srcs) * sum(outs[j].lc for j in live)
+        self.bwd_flops += lfl * (2 if need else 1)
         if not transposed:
             # ---- wgrad: dW_j[tap, r, n] += gathered(src)[r] * dout_j[n] for all layers j of the fused launch in
             # one call (the gathered operand is streamed once); BiasAddGrad per layer
             cos = [layers[j][1] for j in live]
+            # fp16 mode: 16-bit output gradients are bf16, so the activations are read through their bf16 twins
+            # (one operand format per MMA); fp32-gradient heads (CUDA cores) read the fp16 activations
+            xs = [self.x16(a) for a in srcs] if outs[live[0]].g.dtype != torch.float32 else [a.t for a in srcs]
             d = ops.conv_desc(CONV_FWD, batch, in_dhw, out_dhw, k, s, pad, [a.c for a in srcs], cos,
-                              [wstr[j] for j in live], act_dtype=_code(srcs[0].dtype),
+                              [wstr[j] for j in live], act_dtype=_code(xs[0].dtype),
                               out_dtype=_code(outs[live[0]].g.dtype), engine=auto)
-            self._wgrad(d, [a.t for a in srcs], [outs[j].g for j in live],
+            self._wgrad(d, xs, [outs[j].g for j in live],
                         [self.pg(layers[j][0] + "/kernel") for j in live],
                         [self.pg(layers[j][0] + "/bias") for j in live] if bias_grad else None,
                         2 * batch * int(np.prod(out_dhw)) * taps * cin * sum(cos), layers[live[0]][0])
@@ -450,9 +480,10 @@ class Engine:
             gk = self.pg(layers[0][0] + "/kernel").view(-1)
             off = 0
             for a in srcs:
+                xa = self.x16(a)
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
-                                  act_dtype=_code(dy.dtype), out_dtype=_code(a.dtype), engine=auto)
-                self._wgrad(d, [dy], [a.t], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
+                                  act_dtype=_code(dy.dtype), out_dtype=_code(xa.dtype), engine=auto)
+                self._wgrad(d, [dy], [xa], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
                             layers[0][0] + "(T)")
                 off += a.c
             if bias_grad:
@@ -480,9 +511,10 @@ class Engine:
         if self.tracing:
             return y
         stats = self.new((x.shape[0], c, 2), torch.float32)
+        self.new_twin(y)
         def fwd():
             ops.inorm_stats(self.ctx, x.t, stats, IN_EPS)
-            ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t)
+            ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t, y.tw)
         self._timed("inorm_fwd", 0, fwd)
 
         def bwd():
@@ -517,6 +549,7 @@ class Engine:
         f32 = torch.float32
         st3, st4 = self.new((n, c, 2), f32), self.new((n, c, 2), f32)
         pool, hidden, gate = self.new((n, c), f32), self.new((n, cr), f32), self.new((n, c), f32)
+        self.new_twin(out)
         if drop is not None and drop[2] > 0.0:
             dr, keep_alive = self.noise.dropout(self, drop[0], drop[1], raw3.shape, drop[2])
         else:
@@ -527,7 +560,7 @@ class Engine:
             ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
             ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
             ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
-            ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t)
+            ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t, out.tw)
         self._timed("se_tail_fwd", 0, fwd)
 
         def bwd():
@@ -566,7 +599,8 @@ class Engine:
         if self.tracing:
             return y
         psi = self.new((theta.shape[0],) + theta.grid, torch.float32)
-        self._timed("attn_fwd", 0, lambda: ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t))
+        self.new_twin(y)
+        self._timed("attn_fwd", 0, lambda: ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t, y.tw))
 
         def bwd():
             if y.g is None:

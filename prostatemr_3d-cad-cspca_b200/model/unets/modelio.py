@@ -44,6 +44,13 @@ class ModelConfig:
         self.params = params
 
 
+def _npz_path(path):
+    """np.savez appends '.npz' to a path that lacks it: save() and load() normalise the same way, so that
+    save('w.h5') / load('w.h5') round-trip (the archive is then 'w.h5.npz')."""
+    path = str(path)
+    return path if path.endswith(".npz") else path + ".npz"
+
+
 def _jsonable(v):
     if hasattr(v, "get_config"):
         return {"class": type(v).__name__, "config": v.get_config()}
@@ -53,7 +60,9 @@ def _jsonable(v):
         return int(v)
     if isinstance(v, (np.floating,)):
         return float(v)
-    return v
+    if v is None or isinstance(v, (bool, int, float, str)):
+        return v
+    return str(v)                      # e.g. a torch.device passed as `device`
 
 
 def _from_jsonable(v):
@@ -82,15 +91,18 @@ class LoadableModel:
     def save(self, path):
         """Weights + optimizer state (Adam m/v/v-hat and the step, which the reference loses on
         resume) + the constructor config, as one .npz archive."""
+        if getattr(self, "eng", None) is None:
+            raise RuntimeError("save(): the model holds no weights yet (built with build=False / no GPU)")
         arrays = {"w/" + k: v for k, v in self.get_weights().items()}
         arrays.update({"opt/" + k: v for k, v in self.get_optimizer_state().items()})
-        cfg = {k: _jsonable(v) for k, v in self.get_config().items()}
+        # `device` and `build` describe the process that saved, not the model: load() decides them afresh
+        cfg = {k: _jsonable(v) for k, v in self.get_config().items() if k not in ("device", "build")}
         arrays["model_config"] = np.frombuffer(json.dumps({"config": cfg}).encode("utf-8"), dtype=np.uint8)
-        np.savez(path, **arrays)
+        np.savez(_npz_path(path), **arrays)
 
     @classmethod
     def load(cls, path, by_name=False):
-        with np.load(path, allow_pickle=False) as f:
+        with np.load(_npz_path(path), allow_pickle=False) as f:
             config = json.loads(bytes(f["model_config"]).decode("utf-8"))["config"]
             config = {k: _from_jsonable(v) for k, v in config.items()}
             weights = {k[2:]: f[k] for k in f.files if k.startswith("w/")}

@@ -298,11 +298,20 @@ class M1(LoadableModel):
             self.heads = 4 if ds else 1
 
         # ---- parameter inventory: a shape-only trace of one training step (Keras builds on first call)
+        # Live parameters first; then the variables the reference creates but that no model output depends on (the
+        # prior net's sersd0 + logits in probabilistic mode, whose output only feeds an empty slice, Q3): they are
+        # declared 'frozen' - kept in the checkpoint inventory, never updated, never regularised - exactly what
+        # Keras does with layers that are not on the path between the functional model's inputs and outputs.
         self.params = ParamTable()
         tracer = Engine(self.params, precision, device=None, use_tcgen05=use_tcgen05)
-        self._graph(tracer, batch=1, training=True, trace=True)
+        self._graph(tracer, batch=1, training=True, trace=True, dead=self._dead_branches_live())
         if probabilistic:
             self._infer_graph(tracer, batch=1, trace=True)
+            if not self._dead_branches_live():
+                self.params.declare_frozen = True
+                self._graph(Engine(self.params, precision, device=None, use_tcgen05=use_tcgen05), batch=1,
+                            training=True, trace=True, dead=True)
+                self.params.declare_frozen = False
         self.params.finalize()
         self.train_flops_per_volume = None
 
@@ -389,7 +398,12 @@ class M1(LoadableModel):
         post = padded(ci + cl, [(0, 0, ci), (lab_lo, ci, cl)])
         return [img], [post]
 
-    def _graph(self, eng, batch, training, trace=False, x=None):
+    def _dead_branches_live(self):
+        """True if the prior net's sersd0 + logits are computed (and then trained): on request, or when the
+        intended deep-supervision wiring makes the prior core produce outputs of its own."""
+        return bool(self.compute_dead_branches or (self.probabilistic and self.prior.deep_supervision))
+
+    def _graph(self, eng, batch, training, trace=False, x=None, dead=None):
         """One training-graph forward. Returns dict(heads=[(logits Act, up)], kl_pairs=[(ml_q, ml_p)])."""
         img, lab = self._inputs(eng, batch, x, trace)
         if not self.probabilistic:
@@ -400,7 +414,8 @@ class M1(LoadableModel):
         q_sample = self.posterior(eng, post_in, False, None, 'q_sample', training, 'latents')
         q_mean = self.posterior(eng, post_in, True, None, 'q_mean', training, 'latents')
         p_zq = self.prior(eng, img, False, q_sample['prob_used_latents'], 'p_z_q', training, 'latents')
-        dead = trace or self.compute_dead_branches or self.prior.deep_supervision
+        if dead is None:
+            dead = self._dead_branches_live()
         p_zqm = self.prior(eng, img, False, q_mean['prob_used_latents'], 'p_z_qmean', training, 'full',
                            need_logits=dead)
         train_conv = self.final_decoder(eng, p_zqm['prob_decoder_features'])
@@ -421,12 +436,29 @@ class M1(LoadableModel):
     def compile(self, optimizer=None, loss=None, loss_weights=None, **_):
         """unet_model.compile(optimizer, loss=[Focal.loss, ELBO.loss], loss_weights=[1, 10])
         (train_model.py:231, README.md:60-61). `loss` entries are the bound .loss methods (or the objects)."""
+        prev = self.optimizer
         self.optimizer = optimizer if optimizer is not None else Adam(1e-3, amsgrad=True)
-        if not getattr(self.optimizer, 'amsgrad', True):
-            raise NotImplementedError("only Adam(amsgrad=True) (train_model.py:120) has a fused kernel")
-        losses = loss if isinstance(loss, (list, tuple)) else [loss]
+        if not isinstance(self.optimizer, Adam):
+            raise NotImplementedError("M1.compile: only model.optimizers.Adam (amsgrad True or False) has a fused "
+                                      "update kernel, got %r" % type(self.optimizer).__name__)
+        if prev is not None and prev is not self.optimizer and self.optimizer.iterations == 0:
+            # a checkpoint restored m / v / v-hat and the step: a fresh optimizer object continues from there
+            self.optimizer.iterations = prev.iterations
+        if isinstance(loss, dict):
+            loss = [loss.get('detection'), loss.get('KL')]
+        losses = list(loss) if isinstance(loss, (list, tuple)) else [loss]
         objs = [getattr(ls, '__self__', ls) for ls in losses if ls is not None]
-        self.focal = next((o for o in objs if isinstance(o, Focal)), Focal())
+        for o in objs:
+            if not isinstance(o, (Focal, EvidenceLowerBound)):
+                raise NotImplementedError(
+                    "M1.compile: loss %r has no fused kernel - the detection output is trained with losses.Focal "
+                    "(losses.py:20-49) and the KL output with losses.EvidenceLowerBound (losses.py:52-63); "
+                    "SoftDicePlusBoundarySurface (losses.py:66-128) and custom callables are not implemented"
+                    % (getattr(o, '__name__', None) or type(o).__name__))
+        focal = [o for o in objs if isinstance(o, Focal)]
+        if objs and not focal:
+            raise ValueError("M1.compile: no losses.Focal among the supplied losses - the detection output needs one")
+        self.focal = focal[0] if focal else Focal()                 # only loss=None falls back to the defaults
         self.elbo = next((o for o in objs if isinstance(o, EvidenceLowerBound)), EvidenceLowerBound())
         if len(self.focal.alpha) != self.num_classes:      # train_model.py:148-149
             raise Exception("Number of Class Weights Declared in Loss Function != Number of Classes in "
@@ -613,10 +645,11 @@ class M1(LoadableModel):
                 if graphed:      # step size from device memory: the captured launch is replayed every step
                     ops.adam_amsgrad_dev(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b],
                                          self._lr_dev, opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0,
-                                         l2_out if l2 > 0 else None)
+                                         l2_out if l2 > 0 else None, bool(opt.amsgrad))
                 else:
                     ops.adam_amsgrad(self.eng.ctx, P.w[a:b], P.g[a:b], P.m[a:b], P.v[a:b], P.vhat[a:b], lr_t,
-                                     opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0, l2_out if l2 > 0 else None)
+                                     opt.beta_1, opt.beta_2, opt.epsilon, l2, 1.0, l2_out if l2 > 0 else None,
+                                     bool(opt.amsgrad))
         if not graphed:
             opt.iterations += 1
         self.eng.refresh_packs()

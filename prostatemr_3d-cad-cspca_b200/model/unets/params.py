@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 ALIGN = 64
-GROUPS = ("kernel", "bias", "plain")
+GROUPS = ("kernel", "bias", "plain", "frozen")
 KIND_GROUP = {"kernel": "kernel", "bias": "bias", "se_kernel": "plain", "se_bias": "plain",
               "gamma": "plain", "beta": "plain"}
 
@@ -24,10 +24,13 @@ class ParamSpec:
     whose channel counts are zero-padded to the tensor-core granularity (16): `index` maps, per padded
     axis, logical position -> physical position. Padded entries are zero, receive exactly-zero
     gradients (their activations are identically zero) and therefore stay zero under Adam."""
-    __slots__ = ("name", "shape", "kind", "offset", "size", "pshape", "psize", "index")
+    __slots__ = ("name", "shape", "kind", "offset", "size", "pshape", "psize", "index", "frozen")
 
-    def __init__(self, name, shape, kind, pshape=None, index=None):
+    def __init__(self, name, shape, kind, pshape=None, index=None, frozen=False):
         self.name, self.shape, self.kind = name, tuple(int(s) for s in shape), kind
+        # frozen: a variable the reference creates but that is not reachable from the model outputs (the prior
+        # net's sersd0 + logits in probabilistic mode, Q3): Keras neither trains nor regularises it
+        self.frozen = frozen
         self.size = int(np.prod(self.shape))
         self.pshape = tuple(int(s) for s in (pshape if pshape is not None else shape))
         self.psize = int(np.prod(self.pshape))
@@ -57,6 +60,7 @@ class ParamTable:
         self.group_range = {}
         self.total = 0
         self.w = self.g = self.m = self.v = self.vhat = None
+        self.declare_frozen = False     # parameters declared while set are 'frozen' (see ParamSpec)
         self._views = {}
         self._gviews = {}
 
@@ -65,7 +69,7 @@ class ParamTable:
         sp = self.specs.get(name)
         if sp is None:
             assert not self.finalized, f"parameter {name} requested after the table was finalised"
-            sp = ParamSpec(name, shape, kind, pshape, index)
+            sp = ParamSpec(name, shape, kind, pshape, index, self.declare_frozen)
             self.specs[name] = sp
         assert sp.shape == tuple(shape), (name, sp.shape, tuple(shape))
         assert sp.pshape == tuple(pshape if pshape is not None else shape), (name, sp.pshape, pshape)
@@ -76,7 +80,7 @@ class ParamTable:
         for grp in GROUPS:
             start = off
             for sp in self.specs.values():
-                if KIND_GROUP[sp.kind] == grp:
+                if ("frozen" if sp.frozen else KIND_GROUP[sp.kind]) == grp:
                     sp.offset = off
                     off += -(-sp.psize // ALIGN) * ALIGN
             self.group_range[grp] = (start, off)

@@ -115,10 +115,11 @@ def inorm_stats(ctx, x, stats, eps=1e-3):
     check(lib().m1_inorm_stats(ctx.handle, ptr(x), dtype_code(x), n, v, c, eps, ptr(stats), current_stream()))
 
 
-def inorm_act_fwd(ctx, x, stats, gamma, beta, slope, y):
+def inorm_act_fwd(ctx, x, stats, gamma, beta, slope, y, y_bf16=None):
+    """y_bf16: optional bf16 twin of the output (fp16 mode: operand of the tensor-core weight gradients)"""
     n, v, c = _nvc(x)
     check(lib().m1_inorm_act_fwd(ctx.handle, ptr(x), ptr(stats), ptr(gamma), ptr(beta), dtype_code(x), n, v, c,
-                                 slope, ptr(y), current_stream()))
+                                 slope, ptr(y), ptr(y_bf16), current_stream()))
 
 
 def inorm_act_bwd(ctx, dy, x, stats, gamma, beta, slope, dx, accumulate, dgamma, dbeta):
@@ -162,10 +163,10 @@ def se_excite_bwd(ctx, dgate, pool, hidden, gate, w6, w7, dpool, dw6, db6, dw7, 
                                  n, c, cr, ptr(dpool), ptr(dw6), ptr(db6), ptr(dw7), ptr(db7), current_stream()))
 
 
-def se_gate_fwd(ctx, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, out):
+def se_gate_fwd(ctx, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, out, out_bf16=None):
     n, v, c = _nvc(raw3)
     check(lib().m1_se_gate_fwd(ctx.handle, ptr(raw3), ptr(raw4), ptr(st3), ptr(st4), ptr(g3), ptr(b3), ptr(g4),
-                               ptr(b4), ptr(gate), C.byref(drop), dtype_code(raw3), n, v, c, ptr(out),
+                               ptr(b4), ptr(gate), C.byref(drop), dtype_code(raw3), n, v, c, ptr(out), ptr(out_bf16),
                                current_stream()))
 
 
@@ -190,10 +191,10 @@ def _grid(t):
     return (C.c_int32 * 3)(*t.shape[1:4])
 
 
-def attn_fwd(ctx, theta, phi, w_psi, b_psi, x, psi, y):
+def attn_fwd(ctx, theta, phi, w_psi, b_psi, x, psi, y, y_bf16=None):
     check(lib().m1_attn_fwd(ctx.handle, ptr(theta), ptr(phi), ptr(w_psi), ptr(b_psi), ptr(x), dtype_code(x),
                             x.shape[0], _grid(theta), _grid(phi), _grid(x), theta.shape[-1], x.shape[-1],
-                            ptr(psi), ptr(y), current_stream()))
+                            ptr(psi), ptr(y), ptr(y_bf16), current_stream()))
 
 
 def attn_bwd(ctx, dy, theta, phi, w_psi, psi, x, dx, acc_dx, dtheta, dphi, dw_psi, db_psi):
@@ -242,14 +243,14 @@ def softmax_focal(ctx, logits, y_true, alpha, gamma, up, prob, head_off, head_we
 
 
 # ---- K9 optimizer + utilities ----------------------------------------------------------------
-def adam_amsgrad(ctx, w, g, m, v, vhat, lr_t, b1, b2, eps, l2, gscale, l2_out=None):
+def adam_amsgrad(ctx, w, g, m, v, vhat, lr_t, b1, b2, eps, l2, gscale, l2_out=None, amsgrad=True):
     check(lib().m1_adam_amsgrad(ctx.handle, ptr(w), ptr(g), ptr(m), ptr(v), ptr(vhat), w.numel(), lr_t, b1, b2,
-                                eps, l2, gscale, ptr(l2_out), current_stream()))
+                                eps, l2, gscale, ptr(l2_out), 1 if amsgrad else 0, current_stream()))
 
 
-def adam_amsgrad_dev(ctx, w, g, m, v, vhat, lr_t_dev, b1, b2, eps, l2, gscale, l2_out=None):
+def adam_amsgrad_dev(ctx, w, g, m, v, vhat, lr_t_dev, b1, b2, eps, l2, gscale, l2_out=None, amsgrad=True):
     check(lib().m1_adam_amsgrad_dev(ctx.handle, ptr(w), ptr(g), ptr(m), ptr(v), ptr(vhat), w.numel(), ptr(lr_t_dev),
-                                    b1, b2, eps, l2, gscale, ptr(l2_out), current_stream()))
+                                    b1, b2, eps, l2, gscale, ptr(l2_out), 1 if amsgrad else 0, current_stream()))
 
 
 def cast(ctx, src, dst):

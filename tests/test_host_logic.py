@@ -94,8 +94,16 @@ def test_param_inventory_matches_oracle_probabilistic(ds_mode):
     P = m.params
     for sp in P.specs.values():
         assert sp.offset % 64 == 0
-    (k0, k1), (b0, b1), (p0, p1) = (P.group_range[g] for g in ('kernel', 'bias', 'plain'))
-    assert k0 == 0 and k1 == b0 and b1 == p0 and p1 == P.total
+    (k0, k1), (b0, b1), (p0, p1), (f0, f1) = (P.group_range[g] for g in ('kernel', 'bias', 'plain', 'frozen'))
+    assert k0 == 0 and k1 == b0 and b1 == p0 and p1 == f0 and f1 == P.total
+    # variables the reference creates but no model output depends on (prior sersd0 + logits, Q3): Keras neither
+    # trains nor regularises them - they sit in the 'frozen' group, outside every Adam / L2 launch
+    frozen = sorted(n for n, sp in P.specs.items() if sp.frozen)
+    if ds_mode == 'reference':
+        assert frozen and all(n.startswith(('prior/sersd0/', 'prior/logits/')) for n in frozen), frozen[:5]
+        assert {n.split('/')[1] for n in frozen} == {'sersd0', 'logits'}
+    else:
+        assert not frozen
 
 
 def test_compile_reads_reference_loss_objects():

@@ -252,6 +252,7 @@ def test_adam_update_and_second_step(ctx):
             mask = (t.grad.abs() > 5e-2 * t.grad.abs().max()) & (t.grad.abs() > 1e-6 * gmax)
             if mask.any() and dw[mask].max().item() > worst:
                 worst, worst_name = dw[mask].max().item(), n
+        print('adam step %d: worst well-conditioned |dw| %.3e (%s), mean |dw| %.3e' % (step, worst, worst_name, tot / cnt))
         assert worst < 5e-4, (worst, worst_name, step)      # half an Adam step (lr = 1e-3)
         assert tot / cnt < 1e-4, tot / cnt
 
