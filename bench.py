@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — M1 training throughput (volumes/s) on N B200s, one JSON line on rank 0.
+"""bench.py — M1 throughput (volumes/s) on N B200s, one JSON line on rank 0.
 
   python bench.py --gpus 1 --steps K --warmup W                      our arm (sm_100a kernels via the C-ABI)
   torchrun ... bench.py --gpus N --steps K --warmup W                data parallel, one rank per GPU (NCCL)
   python bench.py --impl reference --gpus N --steps K --warmup W     the reference's CPU path (oracle port)
+  python bench.py --config c1|c2|c4|c5 ...                           the other rows of BASELINE.md section 4
 
-Workload (BASELINE.json configs[1]): full M1 — probabilistic + dense_skip + deep_supervision — training
-step (4-pass forward, focal + KL, backward, Adam-AMSGrad), bf16, batch 8 per GPU, synthetic 20x160x160
-volumes with 4 input channels (3 bpMRI + label channel). A "step" is one such training step.
+Default workload = the one BASELINE.json's metric is quoted on (configs[1], "c2"): full M1 — probabilistic +
+dense_skip + deep_supervision — training step (4-pass forward, focal + KL, backward, Adam-AMSGrad), batch 8 per
+GPU, synthetic 20x160x160 volumes with 4 input channels (3 bpMRI + label channel), 16-bit tensor-core arithmetic
+with fp32 accumulation (precision 'fp16': fp16 values and weights, bf16 gradients - the mode that meets the
+parity bounds; --precision bf16 is the all-bf16 mode). A "step" is one such training step.
+  c1  deterministic M1 (dense_skip=False, probabilistic=False), forward only, batch 1 (the reference's CPU case)
+  c4  Monte-Carlo dropout ensemble: 20 stochastic prior passes per volume (get_detect_model().predict_mc)
+  c5  24x256x256 volumes, att_sub_samp=(2,2,2), cascaded='identity' (Q8), training step, batch 2
 
 Timed regions (CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks):
-  value      K steps, inputs resident in HBM; after its warm-up the model replays the step from two CUDA graphs
-             ([forward, losses, backward] and [Adam, weight re-pack]; with N > 1 the NCCL all-reduce of the flat
-             gradient buffer runs between them)
-  e2e        K steps through the public API with pinned HOST inputs copied in and the loss read back every step
+  value      K steps, inputs resident in HBM; after its warm-up the model replays the step from CUDA graphs
+  e2e        K steps through the public API with pinned HOST inputs copied in and the result read back every step
   roofline   the same K steps launched eagerly with a CUDA-event pair around every kernel family (per position
-             in the step: median over the K steps), dominant conv family vs the measured bf16 peak
+             in the step: median over the K steps): dominant conv family vs the measured bf16 peak, dominant
+             bandwidth family vs the measured HBM copy bandwidth
   cpu_baseline / --impl reference   the oracle port of the reference on the host cores (TF 2.5 cannot run here)
 """
 import argparse
@@ -33,9 +38,21 @@ README_CFG = dict(filters=(32, 64, 128, 256, 512),
                   strides=((1, 1, 1), (1, 2, 2), (1, 2, 2), (2, 2, 2), (2, 2, 2)),
                   kernel_sizes=((1, 3, 3), (1, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
                   se_reduction=(8, 8, 8, 8, 8))
-METRIC = "M1 train volumes/sec (20x160x160x3)"
-# algorithmic conv FLOPs of one training volume (fwd 837.65 GMAC, fwd+bwd = 3x)
-FLOP_PER_VOLUME = 5025.9e9
+METRICS = {"c2": "M1 train volumes/sec (20x160x160x3)",
+           "c1": "M1 deterministic forward volumes/sec (20x160x160x3, batch 1)",
+           "c4": "M1 Monte-Carlo ensemble volumes/sec (20 stochastic passes per 20x160x160x3 volume)",
+           "c5": "M1 cascaded train volumes/sec (24x256x256x3, att_sub_samp 2x2x2)"}
+CONFIGS = {
+    "c2": dict(dims=(20, 160, 160), batch=8, mode="train", cascaded=False, sub=((1, 1, 1),) * 4, full=True),
+    "c1": dict(dims=(20, 160, 160), batch=1, mode="forward", cascaded=False, sub=((1, 1, 1),) * 4, full=False),
+    "c4": dict(dims=(20, 160, 160), batch=8, mode="mc", cascaded=False, sub=((1, 1, 1),) * 4, full=True, passes=20),
+    "c5": dict(dims=(24, 256, 256), batch=2, mode="train", cascaded='identity', sub=((2, 2, 2),) * 4, full=True),
+}
+# algorithmic conv FLOPs of one cfg-2 training volume INCLUDING the branches the reference builds
+# but whose output feeds an empty slice (Q3): fwd 837.65 GMAC, fwd+bwd = 3x. The product does not execute those
+# branches nor the data gradient of the stem; the roofline numerators below use the FLOPs actually executed
+# (counted by the engine with the reference's channel counts: 806.58 GMAC forward), not this figure.
+FLOP_PER_VOLUME_SURVEY = 5025.9e9
 
 
 def parse():
@@ -44,13 +61,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="volumes per GPU")
-    ap.add_argument("--dims", type=int, nargs=3, default=[20, 160, 160])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="volumes per GPU (default: the config's)")
+    ap.add_argument("--dims", type=int, nargs=3, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core convolutions only")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
                     help="storage type of the activation values (fp16: the mode that meets the parity bounds)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.batch is not None:
+        cfg['batch'] = a.batch
+    if a.dims is not None:
+        cfg['dims'] = tuple(a.dims)
+    a.cfg = cfg
+    a.dims, a.batch = tuple(cfg['dims']), cfg['batch']
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -100,24 +126,29 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (PyTorch/oneDNN fp32 port of the reference's arithmetic; TF 2.5 cannot run here)
 # ------------------------------------------------------------------------------------------------
-def oracle_step_fn(dims, threads):
-    """Returns f() running ONE full training step (fwd 4 passes, losses, bwd, Adam) on one volume."""
+def oracle_step_fn(cfgd, dims, threads):
+    """Returns f() running ONE step of the configuration's workload on ONE volume of size dims: a full training
+    step (forward passes, losses, backward, Adam), one deterministic forward, or the 20-pass ensemble."""
     import torch
     from oracle import m1_oracle as O
     torch.set_num_threads(threads)
-    cfg = O.default_config(dense_skip=True, deep_supervision=True, probabilistic=True, prob_latent_dims=(3, 2, 1, 0),
-                           dropout_mode='monte-carlo', **{k: README_CFG[k] for k in ('filters', 'strides', 'kernel_sizes')})
-    ps = O.ParamStore(dtype=torch.float32, seed=0, requires_grad=True)
-    x, y = O.synthetic_batch(1, tuple(dims), dtype=torch.float32)
-    state = {}
-    step = [0]
+    prob = cfgd['full']
+    cfg = O.default_config(dense_skip=cfgd['full'], deep_supervision=cfgd['full'], probabilistic=prob,
+                           prob_latent_dims=(3, 2, 1, 0), dropout_mode='monte-carlo', att_sub_samp=cfgd['sub'],
+                           **{k: README_CFG[k] for k in ('filters', 'strides', 'kernel_sizes')})
+    ps = O.ParamStore(dtype=torch.float32, seed=0, requires_grad=cfgd['mode'] == 'train')
+    x, y = O.synthetic_batch(1, tuple(dims), dtype=torch.float32, probabilistic=prob)
+    state, step = {}, [0]
 
-    def f():
+    def train():
         step[0] += 1
         noise = O.Noise(step[0], torch.float32)
         for t in ps.p.values():
             t.grad = None
-        r = O.train_loss(ps, cfg, x, y, noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0)
+        if cfgd['cascaded']:
+            r = O.cascade_train_loss(ps, cfg, x, x, y, noise, 'identity')
+        else:
+            r = O.train_loss(ps, cfg, x, y, noise, alpha=(0.75, 0.25), gamma=2.0, kl_weight=10.0)
         r['loss'].backward()
         with torch.no_grad():
             for n, t in ps.p.items():
@@ -128,36 +159,50 @@ def oracle_step_fn(dims, threads):
                 t.copy_(w)
                 state[n] = (m, v, vh)
         return float(r['loss'].detach())
-    return f
+
+    def forward():
+        step[0] += 1
+        with torch.no_grad():
+            o = O.m1_deterministic(ps, cfg, x, O.Noise(step[0], torch.float32), training=False)
+        return float(o['y_softmax'].sum())
+
+    def mc():
+        acc = 0.0
+        with torch.no_grad():
+            for _ in range(cfgd['passes']):
+                step[0] += 1
+                acc = acc + O.m1_infer(ps, cfg, x, O.Noise(step[0], torch.float32))
+        return float(acc.sum())
+    return {'train': train, 'forward': forward, 'mc': mc}[cfgd['mode']]
 
 
-def pick_cpu_sample(dims, budget_s, nsteps, threads):
-    """Largest crop (H, W multiples of 16 so that the four stride-2 levels nest) of the volume whose
-    nsteps training steps fit the budget; the conv cost is linear in the voxel count, so
-    volumes/s = voxel fraction / step time."""
+def pick_cpu_sample(cfgd, dims, budget_s, nsteps, threads):
+    """Largest crop (H, W multiples of 32 so that the stride-2 levels and the sub-sampled gates nest) of the volume
+    whose nsteps steps fit the budget; the conv cost is linear in the voxel count, so volumes/s = voxel fraction /
+    step time."""
     probe = (dims[0], 32, 32)
-    f = oracle_step_fn(probe, threads)
+    f = oracle_step_fn(cfgd, probe, threads)
     f()
     t0 = time.time(); f(); t_probe = time.time() - t0
     per_voxel = t_probe / (probe[0] * probe[1] * probe[2])
-    cands = [(dims[1], dims[2]), (dims[1], dims[2] // 2), (dims[1] // 2, dims[2] // 2), (80, 48), (48, 48), (32, 32)]
+    cands = [(dims[1], dims[2]), (dims[1], dims[2] // 2), (dims[1] // 2, dims[2] // 2), (96, 64), (64, 64), (64, 32),
+             (32, 32)]
     for h, w in cands:
-        if h % 16 == 0 and w % 16 == 0 and per_voxel * dims[0] * h * w * nsteps <= budget_s:
+        if h % 32 == 0 and w % 32 == 0 and per_voxel * dims[0] * h * w * nsteps <= budget_s:
             return (dims[0], h, w)
     return (dims[0], 32, 32)
 
 
-def cpu_baseline(dims, budget_s=30.0):
+def cpu_baseline(cfgd, dims, budget_s=30.0):
     threads = os.cpu_count() or 1
-    sample = pick_cpu_sample(dims, budget_s, 2, threads)
-    f = oracle_step_fn(sample, threads)
+    sample = pick_cpu_sample(cfgd, dims, budget_s, 2, threads)
+    f = oracle_step_fn(cfgd, sample, threads)
     f()                                             # warm-up (parameter creation, oneDNN primitives)
     t0 = time.time(); f(); dt = time.time() - t0
     frac = (sample[0] * sample[1] * sample[2]) / (dims[0] * dims[1] * dims[2])
     return {"value": frac / dt, "unit": "volumes/s", "cores": threads, "kind": "port",
-            "sample": "1 training step (4-pass fwd + bwd + Adam, fp32 oneDNN) on one %dx%dx%d volume (%.3g of a "
-                      "20x160x160 volume; cost is linear in voxels); TF 2.5 itself cannot run in this image"
-                      % (sample + (frac,))}
+            "sample": "1 step of the workload (fp32 oneDNN) on one %dx%dx%d volume (%.3g of a %dx%dx%d volume; cost "
+                      "is linear in voxels); TF 2.5 itself cannot run in this image" % (sample + (frac,) + tuple(dims))}
 
 
 def run_reference(args):
@@ -165,9 +210,9 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    dims = tuple(args.dims)
-    sample = pick_cpu_sample(dims, 150.0, args.steps + args.warmup, threads)
-    f = oracle_step_fn(sample, threads)
+    dims, cfgd = tuple(args.dims), args.cfg
+    sample = pick_cpu_sample(cfgd, dims, 120.0, args.steps + args.warmup, threads)
+    f = oracle_step_fn(cfgd, sample, threads)
     for _ in range(args.warmup):
         f()
     t0 = time.time()
@@ -176,31 +221,67 @@ def run_reference(args):
     dt = time.time() - t0
     frac = (sample[0] * sample[1] * sample[2]) / (dims[0] * dims[1] * dims[2])
     value = frac * args.steps / dt
-    desc = ("each step = 1 training step on one %dx%dx%d volume (%.3g of the 20x160x160 volume), PyTorch-CPU oracle "
-            "port of the reference (TF 2.5 is not installable here)" % (sample + (frac,)))
+    # one step on a FULL volume, so that the linear-in-voxels extrapolation of the line's value can be checked
+    full = None
+    if sample != dims and os.environ.get("M1_REF_FULL_VOLUME", "1") == "1":
+        ff = oracle_step_fn(cfgd, dims, threads)
+        ff()
+        t1 = time.time(); ff(); full = 1.0 / (time.time() - t1)
+    desc = ("each step = 1 step of the workload on one %dx%dx%d volume (%.3g of the %dx%dx%d volume), PyTorch-CPU "
+            "oracle port of the reference (TF 2.5 is not installable here)" % (sample + (frac,) + dims))
+    if full is not None:
+        desc += "; one full-volume step measured in the same run: %.4f volumes/s" % full
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[args.config], "value": value, "unit": "volumes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, 1), "full_volume_value": full,
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 def workload_config(args, world):
-    return {"workload": "cfg2: full M1 (probabilistic + dense_skip + deep_supervision, monte-carlo dropout) training "
-                        "step, %dx%dx%d volumes, 4 input channels (3 bpMRI + label ch), batch %d per GPU"
-                        % (tuple(args.dims) + (args.batch,)),
+    c = args.cfg
+    what = {"train": "training step (forward passes, focal + KL, backward, Adam-AMSGrad)",
+            "forward": "deterministic forward pass (get_detect_model)",
+            "mc": "Monte-Carlo dropout ensemble of %d stochastic prior passes (predict_mc)" % c.get('passes', 0)}[c['mode']]
+    arch = ("full M1 (probabilistic + dense_skip + deep_supervision, monte-carlo dropout)" if c['full']
+            else "deterministic M1 (dense_skip=False, probabilistic=False)")
+    if c['cascaded']:
+        arch = "cascaded (%s) two-stage " % c['cascaded'] + arch
+    return {"workload": "%s: %s, %s, %dx%dx%d volumes, %d input channels, batch %d per GPU"
+                        % ((args.config, arch, what) + tuple(args.dims) + (4 if c['full'] else 3, args.batch)),
             "global_batch": args.batch * world, "parallelism": "dp%d" % world,
-            "step_launch": "whole training step captured once into a CUDA graph and replayed (M1_CUDA_GRAPH=0: eager)",
+            "precision": "%s activation values and tensor-core weights, %s activation gradients, fp32 accumulation / "
+                         "statistics / parameters" % (args.precision, "bf16" if args.precision != "fp32" else "fp32"),
+            "step_launch": "whole step captured once into CUDA graphs and replayed (M1_CUDA_GRAPH=0: eager)",
             "l2_flush": "not needed: every step streams >10 GB of activations, far above the 126 MB L2",
-            "filters": list(README_CFG['filters']), "prob_latent_dims": [3, 2, 1, 0]}
+            "filters": list(README_CFG['filters']), "att_sub_samp": [list(s) for s in c['sub']],
+            "prob_latent_dims": [3, 2, 1, 0] if c['full'] else None}
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def synthetic(B, dims, rank, channels):
+    """whitened images N(0,1), ellipsoid lesion labels; label as the last channel if channels == 4"""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    D, H, W = dims
+    xh = torch.randn((B, D, H, W, channels), generator=g)
+    zz, yy, xx = torch.meshgrid(torch.arange(D), torch.arange(H), torch.arange(W), indexing='ij')
+    lab = torch.zeros((B, D, H, W))
+    for b in range(B):
+        c = [int(torch.randint(0, s, (1,), generator=g)) for s in dims]
+        r = float(torch.randint(4, 13, (1,), generator=g))
+        lab[b] = (((zz - c[0]) * 2.0) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2 <= r * r).float()
+    if channels == 4:
+        xh[..., 3] = lab
+    yh = torch.stack([1 - lab, lab], -1)
+    return xh.pin_memory(), yh.pin_memory()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -214,10 +295,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     dev = torch.device("cuda", local)
-    dims = tuple(args.dims)
-    B = args.batch
-    model = unets.networks.M1(dims, 4, 2, dropout_rate=0.5, dropout_mode='monte-carlo', att_sub_samp=((1, 1, 1),) * 4,
-                              dense_skip=True, deep_supervision=True, probabilistic=True,
+    dims, B, c = tuple(args.dims), args.batch, args.cfg
+    full, mode = c['full'], c['mode']
+    cin = 4 if full else 3
+    model = unets.networks.M1(dims, cin, 2, dropout_rate=0.5, dropout_mode='monte-carlo', att_sub_samp=c['sub'],
+                              dense_skip=full, deep_supervision=full, probabilistic=full, cascaded=c['cascaded'],
                               prob_latent_dims=(3, 2, 1, 0), summary=False, precision=args.precision, seed=0,
                               device=dev, use_tcgen05=not args.no_tc, **README_CFG)
     sched = optimizers.CosineDecayRestarts(1e-3, 1000, t_mul=2.0, m_mul=1.0, alpha=1e-3)
@@ -227,21 +309,10 @@ def run_ours(args):
     if world > 1:
         model.distribute()
     ctx = _lib.Context.get(local)
-
-    # synthetic batch: whitened images N(0,1), ellipsoid lesion labels, pinned on the host
-    g = torch.Generator().manual_seed(1234 + rank)
-    D, H, W = dims
-    xh = torch.randn((B, D, H, W, 4), generator=g)
-    zz, yy, xx = torch.meshgrid(torch.arange(D), torch.arange(H), torch.arange(W), indexing='ij')
-    lab = torch.zeros((B, D, H, W))
-    for b in range(B):
-        c = [int(torch.randint(0, s, (1,), generator=g)) for s in dims]
-        r = float(torch.randint(4, 13, (1,), generator=g))
-        lab[b] = (((zz - c[0]) * 2.0) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2 <= r * r).float()
-    xh[..., 3] = lab
-    yh = torch.stack([1 - lab, lab], -1)
-    xh, yh = xh.pin_memory(), yh.pin_memory()
+    xh, yh = synthetic(B, dims, rank, cin)
     xd, yd = xh.to(dev), yh.to(dev)
+    det = model.get_detect_model() if mode != "train" else None
+    engines = model.engines() if hasattr(model, "engines") else [model.eng]
 
     def barrier():
         if world > 1:
@@ -261,45 +332,69 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    def dev_step():
-        model.train_step(xd, yd)
-
     last = {}
+    cascade_in = (lambda x: [x, x]) if c['cascaded'] else (lambda x: x)
+    if mode == "train":
+        def dev_step():
+            model.train_step(cascade_in(xd), yd)
 
-    def e2e_step():
-        x = xh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
-        r = model.train_step(x, y)
-        last['loss'] = model.total_loss(r).cpu()       # device -> host read of the step's result
+        def e2e_step():
+            x = xh.to(dev, non_blocking=True)
+            y = yh.to(dev, non_blocking=True)
+            r = model.train_step(cascade_in(x), y)
+            last['result'] = model.total_loss(r).cpu()       # device -> host read of the step's result
+        d2h = 4
+    elif mode == "forward":
+        def dev_step():
+            det.predict(xd)
+
+        def e2e_step():
+            last['result'] = det.predict(xh.to(dev, non_blocking=True)).cpu()[..., 1].sum()
+        d2h = int(yh.numel() * 4)
+    else:
+        def dev_step():
+            det.predict_mc(xd, passes=c['passes'])
+
+        def e2e_step():
+            last['result'] = det.predict_mc(xh.to(dev, non_blocking=True), passes=c['passes']).cpu()[..., 1].sum()
+        d2h = int(yh.numel() * 4)
+
+    def graph_launches():
+        """kernels inside the replayed graphs of one step (counted at capture)"""
+        if mode == "train":
+            return model.launches_per_graph_step or 0, getattr(model, "graph_replays", 0)
+        return (det.launches_per_graph_pass or 0), getattr(det, "graph_replays", 0)
 
     for _ in range(args.warmup):
         dev_step()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    # ---- headline: K steps, inputs resident in HBM. After its warm-up the model replays the whole step from
-    # a CUDA graph (M1.train_step); kernels launched = replays x kernels captured per step + eager launches.
+    # ---- headline: K steps, inputs resident in HBM. kernels launched = replays x kernels captured + eager launches
     ctx.launch_count(reset=True)
-    replays0 = getattr(model, "graph_replays", 0)
+    _, replays0 = graph_launches()
     ms = timed(args.steps, dev_step)
     launches = ctx.launch_count(reset=True)
-    replays = getattr(model, "graph_replays", 0) - replays0
-    if replays:
-        launches += replays * model.launches_per_graph_step
+    per_replay, replays1 = graph_launches()
+    launches += (replays1 - replays0) * per_replay
     clk = clocks.stop() if rank == 0 else None
-    # ---- end to end: pinned host inputs copied in, loss read back, every step
+    # ---- end to end: pinned host inputs copied in, result read back, every step
     e2e_step()
     ms_e2e = timed(args.steps, e2e_step)
     # ---- per-kernel-family durations: the same K steps once more, launched eagerly with a CUDA-event pair
     # around every launch family (a replayed graph cannot carry per-launch events)
-    model.eng.prof = []
+    for e in engines:
+        e.prof = []
     ncu_range = os.environ.get("M1_CUDA_PROFILER_RANGE") == "1"     # ncu --profile-from-start off: only this pass
     if ncu_range:
         torch.cuda.profiler.start()
     ms_prof = timed(args.steps, dev_step)
     if ncu_range:
         torch.cuda.profiler.stop()
-    prof, model.eng.prof = model.eng.prof, None
+    prof = [p for e in engines for p in e.prof]
+    flops_step = sum(e.conv_flops + e.bwd_flops for e in engines) * (c.get('passes', 1) if mode == "mc" else 1)
+    for e in engines:
+        e.prof = None
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -309,68 +404,88 @@ def run_ours(args):
     if rank != 0:
         return
 
-    # ---- roofline of the dominant conv kernel family (CUDA-event durations inside the timed region)
-    cats = {}
     if os.environ.get("M1_DUMP_PROF"):
-        rows = sorted(((a.elapsed_time(b), cat, fl, str(lbl)) for cat, fl, a, b, lbl in prof), reverse=True)
+        rows = sorted(((p[2].elapsed_time(p[3]), p[0], p[1], p[5], str(p[4])) for p in prof), reverse=True)
         with open(os.environ["M1_DUMP_PROF"], "w") as fh:
-            for t_ms, cat, fl, lbl in rows:
-                fh.write("%9.3f ms  %-20s %8.2f TFLOP/s  %s\n" % (t_ms, cat, fl / 1e9 / max(t_ms, 1e-6), lbl))
+            for t_ms, cat, fl, nb, lbl in rows:
+                fh.write("%9.3f ms  %-20s %8.2f TFLOP/s %8.1f GB/s  %s\n" % (t_ms, cat, fl / 1e9 / max(t_ms, 1e-6),
+                                                                          nb / 1e6 / max(t_ms, 1e-6), lbl))
     # every step issues the same launch sequence: take, per position in the step, the MEDIAN duration over the
     # K profiled steps (the eager pass is host-bound; a Python GC pause or a late launch otherwise lands in
     # whichever event pair happens to bracket it), then scale back to K steps
-    times = [a.elapsed_time(b) for _, _, a, b, _ in prof]
-    per_step = len(prof) // max(1, args.steps)
-    if per_step and per_step * args.steps == len(prof) and args.steps > 1:
+    times = [p[2].elapsed_time(p[3]) for p in prof]
+    nprof = args.steps * (c.get('passes', 1) if mode == "mc" else 1)
+    per_step = len(prof) // max(1, nprof)
+    if per_step and per_step * nprof == len(prof) and nprof > 1:
         for i in range(per_step):
-            col = sorted(times[i + k * per_step] for k in range(args.steps))
+            col = sorted(times[i + k * per_step] for k in range(nprof))
             med = col[len(col) // 2]
-            for k in range(args.steps):
+            for k in range(nprof):
                 times[i + k * per_step] = med
-    for (cat, fl, a, b, _), t_ms in zip(prof, times):
-        c = cats.setdefault(cat, [0.0, 0.0, 0])
-        c[0] += fl; c[1] += t_ms; c[2] += 1
+    cats = {}
+    for p, t_ms in zip(prof, times):
+        cc = cats.setdefault(p[0], [0.0, 0.0, 0, 0.0])
+        cc[0] += p[1]; cc[1] += t_ms; cc[2] += 1; cc[3] += p[5]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    peak_bw = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = ("measured (MEASURED_PEAKS.json: bf16_tflops_sustained, hbm_gbs)" if peaks
+                else "fallback 1.4 PFLOP/s sustained / 6.65 TB/s (B200_PROFILING.md)")
     breakdown = {k: {"launches": v[2] // args.steps, "ms_per_step": v[1] / args.steps,
-                     "tflops": (v[0] / 1e12) / (v[1] / 1e3) if v[1] > 0 else None} for k, v in cats.items()}
-    conv_cats = {k: v for k, v in cats.items() if k.startswith("conv_")}
+                     "tflops": (v[0] / 1e12) / (v[1] / 1e3) if v[1] > 0 and v[0] > 0 else None,
+                     "gbs": (v[3] / 1e9) / (v[1] / 1e3) if v[1] > 0 and v[3] > 0 else None} for k, v in cats.items()}
+    total_ms = sum(v[1] for v in cats.values())
+    traffic = {}
+    try:      # per-launch DRAM bytes of the dominant kernels, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+    except (OSError, ValueError):
+        pass
+    conv_cats = {k: v for k, v in cats.items() if k.startswith("conv_") and v[0] > 0}
     dom = max(conv_cats, key=lambda k: conv_cats[k][1]) if conv_cats else None
     roofline = None
     if dom:
-        fl, t_ms, n = cats[dom]
+        fl, t_ms, n, _ = cats[dom]
         ach = (fl / 1e12) / (t_ms / 1e3)
+        tr = traffic.get(dom, {})
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None,
-                    "traffic_note": "per-launch DRAM bytes of the family's largest launches are in "
-                                    "profiles/r01_summary.md (ncu --set full): sersp2 wgrad 0.56 GB vs 0.35 GB "
-                                    "algorithmic; the family mixes 168 launch shapes, so no single figure applies",
-                    "peak_source": peak_src,
-                    "share_of_step": t_ms / sum(v[1] for v in cats.values()), "flop_per_launch_avg": fl / n,
+                    "frac": ach / peak_tf, "traffic": tr.get("dram_bytes_per_launch"),
+                    "traffic_note": tr.get("note"), "peak_source": peak_src,
+                    "share_of_step": t_ms / total_ms, "flop_per_launch_avg": fl / n,
+                    "flops": "algorithmic: reference channel counts, only the launches actually executed",
                     "timed_with": "CUDA events around every launch family in an eager re-run of the same %d steps "
                                   "(%.2f ms/step; the headline replays the step as a CUDA graph)"
                                   % (args.steps, ms_prof / args.steps),
-                    "conv_path_tflops_whole_step": (FLOP_PER_VOLUME * B * args.steps / 1e12) / (ms / 1e3),
-                    "conv_path_frac_whole_step": (FLOP_PER_VOLUME * B * args.steps / 1e12) / (ms / 1e3) / peak_tf,
+                    "conv_flop_per_step_executed": flops_step,
+                    "conv_path_tflops_whole_step": (flops_step * args.steps / 1e12) / (ms / 1e3),
+                    "conv_path_frac_whole_step": (flops_step * args.steps / 1e12) / (ms / 1e3) / peak_tf,
                     "breakdown": breakdown}
+        bw_cats = {k: v for k, v in cats.items() if v[3] > 0}
+        if bw_cats:
+            bdom = max(bw_cats, key=lambda k: bw_cats[k][1])
+            _, t_b, n_b, nb = cats[bdom]
+            trb = traffic.get(bdom, {})
+            roofline["bandwidth"] = {"bound": "hbm", "kernel": bdom, "achieved": (nb / 1e9) / (t_b / 1e3),
+                                     "peak": peak_bw, "unit": "GB/s", "frac": (nb / 1e9) / (t_b / 1e3) / peak_bw,
+                                     "traffic": trb.get("dram_bytes_per_launch"), "traffic_note": trb.get("note"),
+                                     "bytes_per_launch_avg": nb / n_b, "share_of_step": t_b / total_ms,
+                                     "bytes": "algorithmic tensor passes x elements x element size (SURVEY 8(d))"}
     out = {
-        "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRICS[args.config], "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
         "clocks": clk,
-        "e2e": {"value": e2e, "unit": "volumes/s", "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4),
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "volumes/s", "h2d_bytes_per_step": int(xh.numel() * 4 + (yh.numel() * 4
+                if mode == "train" else 0)), "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "loss": float(last['loss']),
+        "result": float(last['result']),
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(dims)
+        out["cpu_baseline"] = cpu_baseline(c, dims)
     print(json.dumps(out))
 
 

@@ -82,7 +82,8 @@ typedef struct {
   /* tcgen05 tiling overrides found by the host's one-off autotuning (0 = heuristic default):
    * conv:  tune[0] = engine variant: 1 = one TMA box per filter tap (conv_tc.cu), 2 = halo tile shared by
    *        the in-plane taps through row-shifted UMMA descriptors (conv_tc_halo.cu; stride-1 gathers only),
-   *        3 = EXPERIMENTAL multi-tile CTAs with double-buffered TMEM accumulators (never chosen automatically)
+   *        3 = multi-tile CTAs: the TMA ring streams across tile boundaries, double-buffered TMEM accumulators,
+   *        dedicated epilogue warps (short-K launches: 1x1x1 convolutions, phases of transposed convolutions)
    * wgrad: tune[0] = max voxels per K brick (16..128), tune[1] = taps sharing one dY tile (1 or kw; 2 = SHIFT
    *        mode: the kw taps also share one activation box through row-shifted descriptors, stride 1 only),
    *        tune[2] = pipeline stage cap, tune[3] = 128-row M tiles per CTA (they share the dY tile) */

@@ -495,29 +495,31 @@ def kl_mvn_diag(q, p):
     return (torch.log(sp / sq) + (sq ** 2 + (mq - mp) ** 2) / (2 * sp ** 2) - 0.5).sum(-1)
 
 
-def m1_deterministic(ps, cfg, inputs, noise=None, training=True, net='m1'):
+def m1_deterministic(ps, cfg, inputs, noise=None, training=True, net='m1', stage=''):
     """m1() deterministic branch (R:networks.py:266-294) with the intended prob_mean=False,
-    prob_z_q=None (Q1)."""
+    prob_z_q=None (Q1). stage: prefix of parameter names and noise keys (second stage of a cascade)."""
     c = dict(cfg, probabilistic=False)
-    return m1core(ps, net, c, inputs, False, None, noise, 'det', training)
+    return m1core(ps, stage + net, c, inputs, False, None, noise, stage + 'det', training)
 
 
-def m1_probabilistic(ps, cfg, inputs, noise, training=True, ds_in_prob='reference', with_infer=False):
-    """m1() probabilistic branch (R:networks.py:297-390): Q4 slicing, 4 live passes, KL, softmax."""
+def m1_probabilistic(ps, cfg, inputs, noise, training=True, ds_in_prob='reference', with_infer=False, stage=''):
+    """m1() probabilistic branch (R:networks.py:297-390): Q4 slicing, 4 live passes, KL, softmax.
+    stage: prefix of parameter names and noise keys (second stage of a cascade)."""
     nc = cfg['num_classes']
+    P = stage
     image = inputs[..., :-(nc - 1)]
     label = inputs[..., -(nc - 1) - 1:-1]          # Q4: this is the LAST IMAGE channel, not the label
     post_in = torch.cat([image, label], -1)
     core = dict(cfg, probabilistic=True,
                 deep_supervision=(cfg['deep_supervision'] and ds_in_prob == 'intended'))  # Q3
-    q_sample = m1core(ps, 'posterior', core, post_in, False, None, noise, 'q_sample', training, 'latents')
-    q_mean = m1core(ps, 'posterior', core, post_in, True, None, noise, 'q_mean', training, 'latents')
-    p_zq = m1core(ps, 'prior', core, image, False, q_sample['prob_used_latents'], noise, 'p_z_q', training,
+    q_sample = m1core(ps, P + 'posterior', core, post_in, False, None, noise, P + 'q_sample', training, 'latents')
+    q_mean = m1core(ps, P + 'posterior', core, post_in, True, None, noise, P + 'q_mean', training, 'latents')
+    p_zq = m1core(ps, P + 'prior', core, image, False, q_sample['prob_used_latents'], noise, P + 'p_z_q', training,
                   'latents')
-    p_zqm = m1core(ps, 'prior', core, image, False, q_mean['prob_used_latents'], noise, 'p_z_qmean',
+    p_zqm = m1core(ps, P + 'prior', core, image, False, q_mean['prob_used_latents'], noise, P + 'p_z_qmean',
                    training, 'full')
-    wl = ps.get('final_decoder/logits/kernel', (1, 1, 1, cfg['filters'][0], nc), 'kernel')
-    bl = ps.get('final_decoder/logits/bias', (nc,), 'bias')
+    wl = ps.get(P + 'final_decoder/logits/kernel', (1, 1, 1, cfg['filters'][0], nc), 'kernel')
+    bl = ps.get(P + 'final_decoder/logits/bias', (nc,), 'bias')
     train_conv = conv3d_same(p_zqm['prob_decoder_features'], wl, bl)
     kl = 0.0
     for q, p in zip(q_sample['prob_distributions'], p_zq['prob_distributions']):
@@ -528,22 +530,64 @@ def m1_probabilistic(ps, cfg, inputs, noise, training=True, ds_in_prob='referenc
         sm = torch.cat([sm, p_zqm['y_softmax'][..., nc:]], -1)   # empty slice in 'reference' mode (Q3)
     out['prob_softmax'] = sm
     if with_infer:
-        p_s = m1core(ps, 'prior', core, image, False, None, noise, 'p_sample', training, 'full')
+        p_s = m1core(ps, P + 'prior', core, image, False, None, noise, P + 'p_sample', training, 'full')
         out['prob_infer_conv'] = conv3d_same(p_s['prob_decoder_features'], wl, bl)
     out['passes'] = dict(q_sample=q_sample, q_mean=q_mean, p_z_q=p_zq, p_z_qmean=p_zqm)
     return out
 
 
-def m1_infer(ps, cfg, inputs, noise, pass_name='p_sample'):
+def m1_infer(ps, cfg, inputs, noise, pass_name='p_sample', stage=''):
     """get_detect_model() of a probabilistic model (R:networks.py:196-206): one prior pass with
     z ~ P at every level, dropout active only in 'monte-carlo' mode."""
     nc = cfg['num_classes']
     image = inputs[..., :-(nc - 1)]
     core = dict(cfg, probabilistic=True, deep_supervision=False)
-    p_s = m1core(ps, 'prior', core, image, False, None, noise, pass_name, False, 'full')
-    wl = ps.get('final_decoder/logits/kernel', (1, 1, 1, cfg['filters'][0], nc), 'kernel')
-    bl = ps.get('final_decoder/logits/bias', (nc,), 'bias')
+    p_s = m1core(ps, stage + 'prior', core, image, False, None, noise, stage + pass_name, False, 'full')
+    wl = ps.get(stage + 'final_decoder/logits/kernel', (1, 1, 1, cfg['filters'][0], nc), 'kernel')
+    bl = ps.get(stage + 'final_decoder/logits/bias', (nc,), 'bias')
     return torch.softmax(conv3d_same(p_s['prob_decoder_features'], wl, bl), -1)
+
+
+STAGE2 = 'stage2/'
+
+
+def m1_cascade(ps, cfg, image_1, image_2, noise, strategy='identity', training=True, ds_in_prob='reference'):
+    """Cascaded two-stage M1 (R:networks.py:109-193): stage 2 sees concat([stage-1 softmax[..., :nc-1], image_2])
+    (for nc = 2 that is the BACKGROUND probability, as the reference slices it), the two class-(nc-1) probabilities
+    are fused by decision_fusion (R:networks.py:209-223; `strategy` is the value of the `cascaded` argument, True
+    read as 'identity', Q8). Outputs as the Keras model: detection_1, detection_2 (+ KL_1, KL_2).
+    nc must be 2: Focal.loss over a 2-channel [1-p, p] prediction has no heads otherwise (losses.py:43-49)."""
+    nc = cfg['num_classes']
+    assert nc == 2, "the cascade's [1-p, p] outputs only make sense for two classes"
+    run = m1_probabilistic if cfg['probabilistic'] else m1_deterministic
+    kw = dict(ds_in_prob=ds_in_prob) if cfg['probabilistic'] else {}
+    key = 'prob_softmax' if cfg['probabilistic'] else 'y_softmax'
+    o1 = run(ps, cfg, image_1, noise, training, **kw)
+    sm1 = o1[key]
+    x2 = torch.cat([sm1[..., :nc - 1], image_2], -1)
+    o2 = run(ps, cfg, x2, noise, training, stage=STAGE2, **kw)
+    sm2 = o2[key]
+    prior_pred, joint_pred = decision_fusion(sm1[..., nc - 1], sm2[..., nc - 1], strategy)
+    out = dict(detection_1=prior_pred, detection_2=joint_pred, stage1=o1, stage2=o2)
+    if cfg['probabilistic']:
+        out['KL_1'], out['KL_2'] = o1['prob_kl'], o2['prob_kl']
+    return out
+
+
+def cascade_train_loss(ps, cfg, image_1, image_2, y_true, noise, strategy='identity', alpha=(0.75, 0.25), gamma=2.0,
+                       kl_weight=10.0, det_weights=(1.0, 1.0)):
+    """Keras objective of the cascaded model compiled with one Focal per detection output and one ELBO per KL
+    output: sum_i det_weights[i] * Focal(detection_i) + kl_weight * (KL_1 + KL_2) + sum(L2)."""
+    o = m1_cascade(ps, cfg, image_1, image_2, noise, strategy, True)
+    f1 = focal_loss(y_true, o['detection_1'], alpha, gamma)
+    f2 = focal_loss(y_true, o['detection_2'], alpha, gamma)
+    total = det_weights[0] * f1 + det_weights[1] * f2 + l2_penalty(ps, cfg)
+    res = dict(detection_1=o['detection_1'], detection_2=o['detection_2'], detection_1_loss=f1, detection_2_loss=f2)
+    if cfg['probabilistic']:
+        total = total + kl_weight * (elbo_loss(o['KL_1']) + elbo_loss(o['KL_2']))
+        res.update(KL_1=o['KL_1'], KL_2=o['KL_2'])
+    res['loss'] = total
+    return res
 
 
 # --------------------------------------------------------------------------------------------

@@ -209,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-// ---- multi-tile variant (m1_conv_desc.tune[0] == 3; EXPERIMENTAL, not selected by default, not yet run on a GPU)
+// ---- multi-tile variant (m1_conv_desc.tune[0] == 3: one of the variants the host's one-off autotuning times)
 // Launches with a handful of k-steps per tile (1x1x1 convolutions, the output phases of transposed
 // convolutions, few-channel layers: ~24 ms of the step at 20-400 TFLOP/s) are dominated by per-CTA fixed costs:
 // TMEM allocation, barrier initialisation, the first TMA round trip, the drain of the epilogue. Here a CTA owns
@@ -704,19 +704,33 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   }
   static const int g_multi = getenv("M1_CONV_MULTI") ? atoi(getenv("M1_CONV_MULTI")) : 0;
   if (d->tune[0] == 3 || g_multi) {
-    // EXPERIMENTAL multi-tile variant (see conv_tc_multi_kernel)
+    // multi-tile variant (see conv_tc_multi_kernel): the producer streams k-steps ACROSS tile boundaries, so the
+    // depth of the ring is chosen for memory latency (>= ~50 KB in flight per SM), not for the k-steps of one
+    // tile - with a ring as deep as one tile (1 stage for a 1x1x1 convolution) every tile would pay the full
+    // TMA round trip again, which is exactly what bounds the single-tile kernel on short-K launches.
     uint32_t acc_cols = 32;
     while ((int)acc_cols < pl.n_tile) acc_cols <<= 1;
+    const int ksteps_tile = std::max(1, ((taps + pl.nphase - 1) / pl.nphase) * (pl.k_total / pl.ck));
+    const int mgroup = std::min(pl.group, ksteps_tile);
+    int ctas_sm = std::min(3, std::max(1, 512 / (int)(2u * acc_cols)));          // 320 threads x 64 registers: <= 3
+    int mstages = (int)(((227u * 1024u) / ctas_sm - 2048u) / (pl.slot_bytes * mgroup));
+    mstages = std::min(mstages, 8);
+    M1_CHECK(mstages >= 2, "m1_conv3d: multi-tile variant needs >= 2 pipeline stages (slot %u bytes x %d)",
+             pl.slot_bytes, mgroup);
+    p.group = mgroup;
+    p.stages = mstages;
+    const uint32_t msmem = 2048u + (uint32_t)mstages * mgroup * pl.slot_bytes;
     const int total_tiles = d->batch * pl.td * pl.th * pl.tw;
     const int64_t ctas1 = (int64_t)total_tiles * pl.n_tiles * pl.nphase;
-    int per = (int)std::max<int64_t>(1, std::min<int64_t>(16, ctas1 / ((int64_t)ctx->num_sms * 8)));
+    // tiles per CTA: a few waves of CTAs over the machine, each long enough to amortise its set-up
+    int per = (int)std::max<int64_t>(1, std::min<int64_t>(32, ctas1 / ((int64_t)ctx->num_sms * ctas_sm * 2)));
     static int multi_set = 0;
     if (!multi_set) {
       M1_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       multi_set = 1;
     }
     dim3 mgrid((unsigned)((total_tiles + per - 1) / per), (unsigned)pl.n_tiles, (unsigned)pl.nphase);
-    conv_tc_multi_kernel<<<mgrid, kThreadsMulti, pl.smem_bytes, st>>>(p, per, total_tiles, acc_cols);
+    conv_tc_multi_kernel<<<mgrid, kThreadsMulti, msmem, st>>>(p, per, total_tiles, acc_cols);
     M1_LAUNCH_CHECK(ctx);
     return 0;
   }

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(TB) inorm_act_fwd_kernel(const T* __restrict__
 // K4 backward: red[n][c] = (sum g, sum g*xhat), g = dy * act'(y)
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename TG, int VW>
-__global__ void __launch_bounds__(TB) inorm_bwd_reduce_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(TB, 2) inorm_bwd_reduce_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int64_t voxels,
@@ -357,7 +357,7 @@ struct NormBwdRegs {
 };
 
 template <typename T, typename TG, int VW>
-__global__ void __launch_bounds__(TB) inorm_bwd_apply_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(TB, 2) inorm_bwd_apply_kernel(const TG* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
@@ -577,7 +577,7 @@ __device__ __forceinline__ GateRegs gate_regs(const GateArgs& a, int n, int C, i
 }
 
 template <typename T, int VW>
-__global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ raw3, const T* __restrict__ raw4,
+__global__ void __launch_bounds__(TB, 2) se_gate_fwd_kernel(const T* __restrict__ raw3, const T* __restrict__ raw4,
                                                         GateArgs a, DropArgs dr, int64_t voxels, int C,
                                                         T* __restrict__ out, __nv_bfloat16* __restrict__ out2,
                                                         int64_t rows_per_slab) {
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(TB) se_gate_fwd_kernel(const T* __restrict__ r
 
 // red[n][c] = { sum dx_, sum dx_*xh3, sum dr, sum dr*xh4, sum dz*x_*r } ; dgate[n][c] = the last one
 template <typename T, typename TG, int VW>
-__global__ void __launch_bounds__(TB) se_gate_bwd_reduce_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
+__global__ void __launch_bounds__(TB, 2) se_gate_bwd_reduce_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
                                                                const T* __restrict__ raw4, GateArgs a, DropArgs dr,
                                                                int64_t voxels, int C, int64_t rows_per_slab,
                                                                ReduceScratch rs, float* __restrict__ red5,
@@ -653,7 +653,7 @@ struct GateBwdRegs {
 };
 
 template <typename T, typename TG, int VW>
-__global__ void __launch_bounds__(TB) se_gate_bwd_apply_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
+__global__ void __launch_bounds__(TB, 2) se_gate_bwd_apply_kernel(const TG* __restrict__ dout, const T* __restrict__ raw3,
                                                               const T* __restrict__ raw4, GateArgs a, DropArgs dr,
                                                               const float* __restrict__ red5, int64_t voxels, int C,
                                                               float inv_v, TG* __restrict__ draw3,

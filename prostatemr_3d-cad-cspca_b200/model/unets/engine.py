@@ -200,14 +200,16 @@ class Engine:
         """uninitialised gradient tensor of an activation (bf16 for fp16 values, else the value type)"""
         return self.new(act.shape, grad_dtype(act.dtype))
 
-    def _timed(self, cat, flops, fn, label=None):
+    def _timed(self, cat, flops, fn, label=None, nbytes=0):
+        """bench.py's per-family profile: flops = ALGORITHMIC (reference-channel) FLOPs of the convolution launches,
+        nbytes = ALGORITHMIC bytes of the bandwidth kernels (tensor passes x elements x element size)"""
         if self.prof is None:
             return fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
         b.record()
-        self.prof.append((cat, flops, a, b, label))
+        self.prof.append((cat, flops, a, b, label, nbytes))
 
     def begin(self, record=True):
         self.tape = []
@@ -232,7 +234,7 @@ class Engine:
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
     def _gather(self, cat, mode, batch, in_dhw, out_dhw, k, s, pad, src_t, src_c, ws, wstr, bias, out_t, out_c,
-                acc, key, w_by_src=False, w_dtype=0):
+                acc, key, w_by_src=False, w_dtype=0, lflops=None):
         """One convolution-shaped launch family: outs[j] (+)= gather(concat(src)) * ws[j] (+ bias[j]).
         The tcgen05 engine takes it when every gathered tensor has a multiple of 16 channels; a
         concatenation that mixes such tensors with odd ones (the 1-3 channel latents, R:networks.py:653)
@@ -268,6 +270,8 @@ class Engine:
                     self.packs[pk] = ent
                 packed = ent[2]
             fl = 2 * vox * taps * int(sum(src_c[i0:i1])) * int(sum(out_c))
+            if lflops is not None:            # algorithmic FLOPs (reference channel counts), split over the runs
+                fl = int(lflops * sum(src_c[i0:i1]) / max(1, sum(src_c)))
             b = bias if first else None
             if packed is not None and self.autotune:
                 tk = ("conv", mode, batch, tuple(in_dhw), tuple(out_dhw), k, s, tuple(src_c[i0:i1]), tuple(out_c),
@@ -338,7 +342,7 @@ class Engine:
             return outs
         self._gather("conv_fwd", mode, batch, in_dhw, out_dhw, k, s, pad, [a.t for a in srcs], [a.c for a in srcs],
                      ws, wstr, bs, [o.t for o in outs], [co for _, co in layers], [False] * len(layers),
-                     ("fwd",) + tuple(n for n, _ in layers))
+                     ("fwd",) + tuple(n for n, _ in layers), lflops=2 * int(vox) * taps * lcin * sum(lco))
         if self.record:
             self._rec(lambda: self._conv_bwd(srcs, layers, outs, k, s, pad, in_dhw, out_dhw, transposed, ws, wstr,
                                              not feeds_norm),
@@ -373,15 +377,23 @@ class Engine:
                            tuple(srcs_t[0].shape[1:4])))
 
     def _tune_conv(self, d, srcs_t, ws, outs_t, packed):
-        """One-off per launch shape: time the two variants of the tcgen05 convolution engine (one TMA box per
-        filter tap / one halo tile shared by the in-plane taps) on scratch outputs and keep the faster."""
+        """One-off per launch shape: time the variants of the tcgen05 convolution engine on scratch outputs and keep
+        the fastest - 1: one TMA box per filter tap, one tile per CTA; 2: one halo tile shared by the in-plane taps
+        (stride-1 gathers with in-plane taps only); 3: multi-tile CTAs whose TMA ring streams across tile
+        boundaries (what short-K launches need: 1x1x1 convolutions, phases of transposed convolutions)."""
+        import os
+        cands = [1]
         d.tune[0] = 2
-        if not ops.conv3d_halo_engine(d):
+        if ops.conv3d_halo_engine(d):
+            cands.append(2)
+        if os.environ.get("M1_CONV_MULTI_TUNE", "1") == "1":
+            cands.append(3)
+        if len(cands) == 1:
             d.tune[0] = 0
             return 1
         scratch = [torch.empty_like(o) for o in outs_t]
         best, best_t = 1, float("inf")
-        for var in (1, 2):
+        for var in cands:
             d.tune[0] = var
             ts = []
             for _ in range(5):
@@ -392,7 +404,7 @@ class Engine:
                 b.synchronize()
                 ts.append(a.elapsed_time(b))
             t = sorted(ts[1:])[1]                    # second fastest of 4 warm runs: robust to one outlier either way
-            if t < best_t:
+            if t < best_t * (0.97 if var == 3 else 1.0):     # the multi-tile variant has to win clearly
                 best, best_t = var, t
         d.tune[0] = 0
         return best
@@ -450,8 +462,8 @@ class Engine:
                               out_dtype=_code(outs[live[0]].g.dtype), engine=auto)
             self._wgrad(d, xs, [outs[j].g for j in live],
                         [self.pg(layers[j][0] + "/kernel") for j in live],
-                        [self.pg(layers[j][0] + "/bias") for j in live] if bias_grad else None,
-                        2 * batch * int(np.prod(out_dhw)) * taps * cin * sum(cos), layers[live[0]][0])
+                        [self.pg(layers[j][0] + "/bias") for j in live] if bias_grad else None, lfl,
+                        layers[live[0]][0])
             # ---- dgrad: [dx_s for every gathered tensor] (+)= convT(dout_j, W_j): ONE launch per layer j whose
             # produced channels are split over the gradients of the concatenated tensors
             if need:
@@ -464,7 +476,8 @@ class Engine:
                     self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad,
                                  [outs[j].g for j in live], cos, wv, [(cin * c, 1, c) for c in cos], None,
                                  list(bufs), [a.c for a in srcs], list(accs),
-                                 ("dgrad",) + tuple(layers[j][0] for j in live), w_by_src=True, w_dtype=self.dgrad_w)
+                                 ("dgrad",) + tuple(layers[j][0] for j in live), w_by_src=True, w_dtype=self.dgrad_w,
+                                 lflops=lfl)
                 else:
                     for i, j in enumerate(live):
                         co = layers[j][1]
@@ -472,7 +485,8 @@ class Engine:
                         self._gather("conv_dgrad", CONV_TRANSPOSED, batch, out_dhw, in_dhw, k, s, pad, [outs[j].g],
                                      [co], wv, [(cin * co, 1, co)] * len(srcs), None, list(bufs),
                                      [a.c for a in srcs], list(accs) if i == 0 else [True] * len(srcs),
-                                     ("dgrad", layers[j][0]), w_dtype=self.dgrad_w if outs[j].g.dtype != torch.float32 else 0)
+                                     ("dgrad", layers[j][0]), w_dtype=self.dgrad_w if outs[j].g.dtype != torch.float32 else 0,
+                                     lflops=lfl * outs[j].lc // max(1, sum(outs[q].lc for q in live)))
         else:
             co = layers[0][1]
             dy = outs[0].g
@@ -483,7 +497,7 @@ class Engine:
                 xa = self.x16(a)
                 d = ops.conv_desc(CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [co], [a.c], [(co * cin, cin, 1)],
                                   act_dtype=_code(dy.dtype), out_dtype=_code(xa.dtype), engine=auto)
-                self._wgrad(d, [dy], [xa], [gk[off:]], None, 2 * batch * int(np.prod(in_dhw)) * taps * a.c * co,
+                self._wgrad(d, [dy], [xa], [gk[off:]], None, lfl * a.lc // max(1, sum(q.lc for q in srcs)),
                             layers[0][0] + "(T)")
                 off += a.c
             if bias_grad:
@@ -496,7 +510,8 @@ class Engine:
                     gbuf, acc = self.grad_buffer(a)
                     self._gather("conv_dgrad", CONV_FWD, batch, out_dhw, in_dhw, k, s, pad, [dy], [co],
                                  [ws[0].view(-1)[off:]], [(co * cin, cin, 1)], None, [gbuf], [a.c], [acc],
-                                 ("dgradT", layers[0][0], idx), w_dtype=self.dgrad_w)
+                                 ("dgradT", layers[0][0], idx), w_dtype=self.dgrad_w,
+                                 lflops=lfl * a.lc // max(1, sum(q.lc for q in srcs)))
                     off += a.c
         for o in outs:
             o.g = None
@@ -515,13 +530,15 @@ class Engine:
         def fwd():
             ops.inorm_stats(self.ctx, x.t, stats, IN_EPS)
             ops.inorm_act_fwd(self.ctx, x.t, stats, gamma, beta, slope, y.t, y.tw)
-        self._timed("inorm_fwd", 0, fwd)
+        es = x.t.element_size()
+        nel = x.t.numel()
+        self._timed("inorm_fwd", 0, fwd, nbytes=3 * nel * es)              # stats read + apply read + write
 
         def bwd():
             if y.g is None:
                 return
             gbuf, acc = self.grad_buffer(x)
-            self._timed("inorm_bwd", 0, lambda: ops.inorm_act_bwd(
+            self._timed("inorm_bwd", 0, nbytes=5 * nel * es, fn=lambda: ops.inorm_act_bwd(
                 self.ctx, y.g, x.t, stats, gamma, beta, slope, gbuf, acc, self.pg(name + "/gamma"),
                 self.pg(name + "/beta")))
             y.g = None
@@ -561,7 +578,9 @@ class Engine:
             ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
             ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
             ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t, out.tw)
-        self._timed("se_tail_fwd", 0, fwd)
+        nel, es = raw3.t.numel(), raw3.t.element_size()
+        # algorithmic passes: the two statistics reads + gate pass (2 reads, 1 write)
+        self._timed("se_tail_fwd", 0, fwd, nbytes=5 * nel * es)
 
         def bwd():
             if out.g is None:
@@ -583,7 +602,7 @@ class Engine:
                                       dpool, raw3.g, raw4.g, self.pg(name + "/norm3/gamma"),
                                       self.pg(name + "/norm3/beta"), self.pg(name + "/norm4/gamma"),
                                       self.pg(name + "/norm4/beta"))
-            self._timed("se_tail_bwd", 0, run)
+            self._timed("se_tail_bwd", 0, run, nbytes=8 * nel * es)       # 2 x 3 reads + 2 writes
             out.g = None
         if self.record:
             self._rec(bwd, [name + sfx for sfx in ("/norm3/gamma", "/norm3/beta", "/norm4/gamma", "/norm4/beta",
@@ -600,7 +619,9 @@ class Engine:
             return y
         psi = self.new((theta.shape[0],) + theta.grid, torch.float32)
         self.new_twin(y)
-        self._timed("attn_fwd", 0, lambda: ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t, y.tw))
+        nb_att = (theta.t.numel() + 2 * x.t.numel()) * x.t.element_size()
+        self._timed("attn_fwd", 0, lambda: ops.attn_fwd(self.ctx, theta.t, phi.t, wpsi, bpsi, x.t, psi, y.t, y.tw),
+                    nbytes=nb_att)
 
         def bwd():
             if y.g is None:
@@ -612,7 +633,7 @@ class Engine:
                 gx, acc = self.grad_buffer(x)
             else:
                 gx, acc = self.new_grad(x), False
-            self._timed("attn_bwd", 0, lambda: ops.attn_bwd(
+            self._timed("attn_bwd", 0, nbytes=2 * nb_att + x.t.numel() * x.t.element_size(), fn=lambda: ops.attn_bwd(
                 self.ctx, y.g, theta.t, phi.t, wpsi, psi, x.t, gx, acc, theta.g, dphi,
                 self.pg(name + "/conv3/kernel"), self.pg(name + "/conv3/bias")))
             if phi.g is None:

@@ -536,9 +536,29 @@ class M1(LoadableModel):
             g_bwd, g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             self.noise.step_dev, self._lr_dev = st['step'], st['lr']
             before = self.eng.ctx.launch_count()
+            import os
+            # Data parallel: first try to capture the BUCKETED all-reduce inside the backward graph - every bucket's
+            # NCCL call is issued (on torch's communication stream, forked from the capturing stream by events) as
+            # soon as the last kernel contributing to it has been enqueued, so the transfers overlap the remaining
+            # weight-gradient kernels exactly as in the eager path. If the capture of a collective is refused by
+            # this torch / NCCL build, fall back to one flat all-reduce between the two graphs.
+            st['dp_in_graph'] = (self.world_size > 1 and self.grad_sync is not None
+                                 and os.environ.get("M1_CUDA_GRAPH_DP", "overlap") == "overlap")
             try:
-                with torch.cuda.graph(g_bwd):
-                    st['out'] = self._train_step_eager(st['x'], st['y'], True, graphed=True)
+                try:
+                    self._graph_dp_overlap = st['dp_in_graph']
+                    with torch.cuda.graph(g_bwd):
+                        st['out'] = self._train_step_eager(st['x'], st['y'], True, graphed=True)
+                except Exception as e:                      # noqa: BLE001
+                    if not st['dp_in_graph']:
+                        raise
+                    print("m1b200: capturing the bucketed all-reduce in the CUDA graph failed (%s: %s) - one flat "
+                          "all-reduce between the graphs instead" % (type(e).__name__, str(e).splitlines()[0][:200]))
+                    torch.cuda.synchronize(self.device)
+                    st['dp_in_graph'] = self._graph_dp_overlap = False
+                    g_bwd = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_bwd):
+                        st['out'] = self._train_step_eager(st['x'], st['y'], True, graphed=True)
                 with torch.cuda.graph(g_upd, pool=g_bwd.pool()):
                     self._apply_update(st['out']['l2'], 1.0 / self.world_size, graphed=True)
             except Exception:
@@ -546,6 +566,7 @@ class M1(LoadableModel):
                 raise
             finally:
                 self.noise.step_dev, self._lr_dev = None, None
+                self._graph_dp_overlap = False
             st['graph'], st['graph_update'] = g_bwd, g_upd
             st['launches'] = self.eng.ctx.launch_count() - before
             self._gs = st
@@ -555,7 +576,7 @@ class M1(LoadableModel):
         st['step'].fill_(self.noise.step)
         st['lr'].fill_(self.optimizer.lr_t())
         st['graph'].replay()
-        if self.world_size > 1:
+        if self.world_size > 1 and not st.get('dp_in_graph'):
             import torch.distributed as dist
             dist.all_reduce(self.params.g, op=dist.ReduceOp.SUM,
                             group=self.grad_sync.group if self.grad_sync is not None else None)
@@ -623,7 +644,7 @@ class M1(LoadableModel):
                 eng.kl(ml_q, ml_p, scal[1:2])
                 eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
         eng._timed("losses", 0, losses)
-        if self.grad_sync is not None and not graphed:
+        if self.grad_sync is not None and (not graphed or getattr(self, "_graph_dp_overlap", False)):
             self.grad_sync.begin(self.params.g, eng.param_uses)
             eng.backward(self.grad_sync.param_done)
             self.grad_sync.finish()
@@ -774,12 +795,11 @@ class DetectModel:
     def __call__(self, x):
         return self.predict(x)
 
-    def predict(self, x, pass_name='p_sample'):
+    GRAPH_WARMUP = 2
+
+    def _predict_eager(self, x, pass_name):
         m = self.model
-        if m.eng is None:
-            raise RuntimeError("model not built on a GPU (m1b200 has no CPU fallback)")
         eng = m.eng
-        x = m._to_device(x)
         B = x.shape[0]
         eng.noise = m.noise
         eng.begin(record=False)
@@ -787,15 +807,70 @@ class DetectModel:
         nc = m.num_classes
         out = torch.empty((B,) + m.input_spatial_dims + (nc,), dtype=torch.float32, device=m.device)
         m._softmax_head(eng, lg, (1, 1, 1), out, 0)
-        if isinstance(m.noise, PhiloxNoise):
+        return out
+
+    def predict(self, x, pass_name='p_sample'):
+        """One (stochastic, in 'monte-carlo' mode) forward pass. Like the training step, the ~450 launches of a
+        pass are captured once into a CUDA graph over a static input buffer after GRAPH_WARMUP eager calls and
+        replayed; the Philox step counter lives in device memory (M1_CUDA_GRAPH=0: always eager). The returned
+        tensor of a replayed pass is the graph's static output buffer, overwritten by the next call."""
+        import os
+        m = self.model
+        if m.eng is None:
+            raise RuntimeError("model not built on a GPU (m1b200 has no CPU fallback)")
+        x = m._to_device(x)
+        philox = isinstance(m.noise, PhiloxNoise)
+        st = getattr(self, "_gs", None)
+        if st is not None and (tuple(st['x'].shape) != tuple(x.shape) or st['pass'] != pass_name):
+            st = self._gs = None
+            self._eager_calls = 0
+        if not philox or m.eng.prof is not None or os.environ.get("M1_CUDA_GRAPH", "1") == "0" \
+                or getattr(self, "_graph_failed", False):
+            out = self._predict_eager(x, pass_name)
+        elif st is None and getattr(self, "_eager_calls", 0) < self.GRAPH_WARMUP:
+            self._eager_calls = getattr(self, "_eager_calls", 0) + 1
+            out = self._predict_eager(x, pass_name)
+        else:
+            if st is None:
+                st = {'x': torch.empty_like(x), 'step': torch.zeros(1, dtype=torch.int64, device=m.device),
+                      'pass': pass_name}
+                st['x'].copy_(x)
+                st['step'].fill_(m.noise.step)
+                torch.cuda.synchronize(m.device)
+                g = torch.cuda.CUDAGraph()
+                m.noise.step_dev = st['step']
+                before = m.eng.ctx.launch_count()
+                try:
+                    with torch.cuda.graph(g):
+                        st['out'] = self._predict_eager(st['x'], pass_name)
+                except Exception:
+                    self._graph_failed = True
+                    raise
+                finally:
+                    m.noise.step_dev = None
+                st['graph'], st['launches'] = g, m.eng.ctx.launch_count() - before
+                self._gs = st
+            else:
+                st['x'].copy_(x, non_blocking=True)
+            st['step'].fill_(m.noise.step)
+            st['graph'].replay()
+            self.graph_replays = getattr(self, "graph_replays", 0) + 1
+            out = st['out']
+        if philox:
             m.noise.step += 1
         return out
+
+    @property
+    def launches_per_graph_pass(self):
+        st = getattr(self, "_gs", None)
+        return st['launches'] if st else None
 
     def predict_mc(self, x, passes=20):
         """Monte-Carlo dropout ensemble (BASELINE config 4): mean softmax of `passes` stochastic
         prior passes with fresh Philox streams (the loop itself is not in the reference: the flag
         UNET_PROBA_ITER of train_model.py:71 is unused there)."""
         m = self.model
+        x = m._to_device(x)
         mean = None
         for _ in range(passes):
             p = self.predict(x)

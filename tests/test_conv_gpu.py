@@ -180,7 +180,8 @@ def test_conv_wgrad_dgrad_simt(ctx, k, s):
 @pytest.mark.parametrize("dhw,cins,cout,k", [((4, 16, 16), [64, 32], 64, (3, 3, 3)),
                                              ((6, 20, 20), [128, 128, 64], 32, (1, 3, 3)),
                                              ((4, 16, 16), [32, 32, 32, 32, 32], 32, (1, 3, 3))])
-def test_conv_dgrad_tcgen05_multi_output(ctx, dhw, cins, cout, k):
+@pytest.mark.parametrize("variant", [0, 3])
+def test_conv_dgrad_tcgen05_multi_output(ctx, dhw, cins, cout, k, variant):
     """Data gradient of a stride-1 conv over a virtual concatenation: ONE tcgen05 launch whose produced
     channels are split over the gradients of the concatenated tensors (one pre-loaded: accumulate bit)."""
     from m1b200 import ops, _lib
@@ -203,6 +204,7 @@ def test_conv_dgrad_tcgen05_multi_output(ctx, dhw, cins, cout, k):
                       [(cin * cout, 1, cout)] * len(cins), accumulate=[True] + [False] * (len(cins) - 1),
                       act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
     assert ops.conv3d_tc_supported(d)
+    d.tune[0] = variant
     packed = ops.conv3d_pack_weights(ctx, d, wv)
     ops.conv3d(ctx, d, [dy.to(dev, torch.bfloat16).contiguous()], wv, None, bufs, packed)
     torch.cuda.synchronize()
@@ -270,7 +272,8 @@ def test_conv_fwd_strided_tcgen05(ctx, dhw, cins, couts, k, s):
                                               ((4, 8, 8), (3, 3, 3), (1, 2, 2), 128, 64),
                                               ((4, 10, 6), (1, 3, 3), (1, 2, 2), 64, 32),
                                               ((3, 5, 7), (3, 3, 3), (2, 2, 2), 32, 48)])
-def test_conv_transpose_tcgen05(ctx, dhw, k, s, cin, cout):
+@pytest.mark.parametrize("variant", [0, 3])
+def test_conv_transpose_tcgen05(ctx, dhw, k, s, cin, cout, variant):
     """Conv3DTranspose forward on the tensor cores: one launch, one output phase per blockIdx.z."""
     from m1b200 import _lib
     g = torch.Generator().manual_seed(6)
@@ -284,6 +287,7 @@ def test_conv_transpose_tcgen05(ctx, dhw, k, s, cin, cout):
     d = ops.conv_desc(_lib.CONV_TRANSPOSED, 2, dhw, out_dhw, k, s, pad, [cin], [cout], [(cout * cin, 1, cin)],
                       act_dtype=_lib.BF16, engine=_lib.ENGINE_TCGEN05)
     assert ops.conv3d_tc_supported(d)
+    d.tune[0] = variant
     wd, bd = w.to(dev).contiguous(), b.to(dev).contiguous()
     packed = ops.conv3d_pack_weights(ctx, d, [wd])
     out = torch.full((2, *out_dhw, cout), float('nan'), device=dev, dtype=torch.bfloat16)
@@ -552,12 +556,6 @@ def test_conv_wgrad_tcgen05_shift_mode(ctx, dhw, cins, couts, k):
         assert (dw.double().cpu() - ref).abs().max().item() < 2e-3 * scale
 
 
-MULTI = pytest.mark.skipif(__import__("os").environ.get("M1_TEST_EXPERIMENTAL") != "1",
-                           reason="experimental multi-tile conv variant (tune[0] = 3): written at the end of round 1 "
-                                  "without GPU time left to run it; enable with M1_TEST_EXPERIMENTAL=1")
-
-
-@MULTI
 @pytest.mark.parametrize("dhw,cins,couts,k", TC_CASES)
 def test_conv_fwd_tcgen05_multi_tile(ctx, dhw, cins, couts, k):
     from m1b200 import _lib
@@ -569,7 +567,6 @@ def test_conv_fwd_tcgen05_multi_tile(ctx, dhw, cins, couts, k):
         assert (g - r).abs().max().item() < 2e-2
 
 
-@MULTI
 @pytest.mark.parametrize("dhw,cins,couts,k,s", STRIDED_TC)
 def test_conv_fwd_strided_tcgen05_multi_tile(ctx, dhw, cins, couts, k, s):
     from m1b200 import _lib
