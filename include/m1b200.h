@@ -128,6 +128,15 @@ int64_t m1_conv3d_packed_bytes(const m1_conv_desc* d);
 int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* const* w,
                            void* w_packed, void* stream);
 
+/* All operand packs of a model in ONE launch (the re-pack that follows every optimizer step: ~350 packs). The plan
+ * holds device-side copies of the job table (weight pointers, strides, pack geometry, output pointer): create it once
+ * - outside any CUDA-graph capture - for fixed weight / pack buffers, run it every step, destroy it at the end. */
+typedef struct m1_pack_plan m1_pack_plan;
+int m1_pack_plan_create(m1_ctx* ctx, int njobs, const m1_conv_desc* const* descs, const float* const* const* ws,
+                        void* const* packed, m1_pack_plan** out);
+int m1_pack_plan_run(m1_ctx* ctx, const m1_pack_plan* plan, void* stream);
+int m1_pack_plan_destroy(m1_pack_plan* plan);
+
 /* ---- K3: weight gradient (Conv3DBackpropFilterV2 of autodiff) + BiasAddGrad ----------------
  * dW_j[tap, r, n] += sum_{batch,o} gathered(o,tap)[r] * dout_j[o, n]   (same strides as d->w_*)
  * dbias_j[n]     += sum dout_j[.., n]  (if dbias[j] != NULL).  Always accumulates (shared
@@ -172,12 +181,19 @@ int m1_se_squeeze(m1_ctx* ctx, const void* raw3, const float* stats3, const floa
                   float* pool, void* stream);
 /* gate = sigmoid(W7 . lrelu(W6 . pool + b6) + b7);  W6 [C][Cr], W7 [Cr][C] (Keras 1x1x1 kernels);
  * hidden [batch][Cr] is the pre-activation of conv6 (kept for backward). */
-int m1_se_excite_fwd(m1_ctx* ctx, const float* pool, const float* w6, const float* b6,
+/* stats3 / gamma3 / beta3 != NULL: the squeeze is folded in - pool is first computed (and written) from the
+ * statistics of raw3 as m1_se_squeeze does (one launch fewer per block). */
+int m1_se_excite_fwd(m1_ctx* ctx, float* pool, const float* w6, const float* b6,
                      const float* w7, const float* b7, int batch, int C, int Cr,
-                     float* hidden, float* gate, void* stream);
+                     float* hidden, float* gate, const float* stats3, const float* gamma3, const float* beta3,
+                     void* stream);
+/* red5 != NULL (the reductions of m1_se_gate_bwd_reduce): also accumulates the parameter gradients of norm3 / norm4
+ * (dgamma3 += A2, dbeta3 += A1 + dpool, dgamma4 += B2, dbeta4 += B1); m1_se_gate_bwd_apply is then called with NULL
+ * parameter-gradient pointers. */
 int m1_se_excite_bwd(m1_ctx* ctx, const float* dgate, const float* pool, const float* hidden,
                      const float* gate, const float* w6, const float* w7, int batch, int C,
                      int Cr, float* dpool, float* dw6, float* db6, float* dw7, float* db7,
+                     const float* red5, float* dgamma3, float* dbeta3, float* dgamma4, float* dbeta4,
                      void* stream);
 /* dropout source: u != NULL -> injected uniforms (same dtype fp32, one per element);
  * else Philox4x32-10(seed, stream_id, element index).  rate == 0 -> no dropout. */
@@ -270,6 +286,24 @@ int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype, const flo
                             int64_t voxels, int C, int nc, float* prob, int prob_c, int head_off,
                             float head_weight, float* loss_out, void* dfeat, int acc_dfeat, float* dw,
                             float* db, float grad_scale, void* stream);
+
+/* ---- cascaded two-stage model, R:networks.py:109-193,209-223 ---------------------------------------
+ * Backward of the final 1x1x1 logits convolution + softmax for an upstream gradient w.r.t. the PROBABILITIES (the
+ * stage-1 softmax feeds the second stage's input and the decision fusion): dlogit = p * (dprob - sum_k p_k dprob_k);
+ * dfeat (+)= W dlogit (stored as M1_GRAD_DTYPE(fdtype)); dw += feat x dlogit; db += dlogit.
+ * prob [rows][prob_c] (channels head_off .. head_off+nc), dprob [rows][nc] fp32. Returns 2 if (C, nc) has no
+ * instantiation. */
+int m1_logits_prob_bwd(m1_ctx* ctx, const void* feat, int fdtype, const float* w, const float* prob, int prob_c,
+                       int head_off, const float* dprob, int64_t rows, int C, int nc, void* dfeat, int acc_dfeat,
+                       float* dw, float* db, void* stream);
+/* decision_fusion (strategy as m1_decision_fusion) of the class-1 probabilities p1 = prob1[row][ch1] (row pitch pc1)
+ * and p2 = prob2[row][ch2] fused with Focal.FL on the joint prediction: det1 [rows][2] = [1-p1, p1], det2 = [1-j, j]
+ * (either may be NULL); if y_true != NULL: loss_out[0] += weight * mean_b sum FL(y, [1-j, j]) and dp1 / dp2 [rows]
+ * = grad_scale * weight / batch * d FL / d p1, p2 (NULL: not wanted). Two classes only. */
+int m1_fusion_focal(m1_ctx* ctx, const float* prob1, int pc1, int ch1, const float* prob2, int pc2, int ch2,
+                    int strategy, const void* y_true, int ydtype, const float* alpha, float gamma, int batch,
+                    int64_t voxels, float* det1, float* det2, float weight, float* loss_out, float* dp1, float* dp2,
+                    float grad_scale, void* stream);
 
 /* ---- K9: Keras Adam (amsgrad=True: train_model.py:113-120; amsgrad=0: the Keras default) + L2 regulariser
  * gradient.  g' = g*gscale + 2*l2*w ; m,v update; vhat = max(vhat, v) (amsgrad) or v;

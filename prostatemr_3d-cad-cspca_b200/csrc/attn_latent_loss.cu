@@ -576,6 +576,137 @@ __global__ void __launch_bounds__(TB) logits_focal_kernel(const T* __restrict__ 
   if (loss_out) grid_sum_add<TB>(acc[0], a.loss_scale, loss_out, gs, sm);
 }
 
+// ---------------------------------------------------------------------------------------------
+// cascade (R:networks.py:109-193): backward of logits conv + softmax for a gradient w.r.t. the PROBABILITIES, and the
+// decision fusion fused with the focal loss of the joint prediction
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename TG, int C, int NC>
+__global__ void __launch_bounds__(TB) logits_prob_bwd_kernel(const T* __restrict__ feat, const float* __restrict__ w,
+                                                            const float* __restrict__ prob, int prob_c, int head_off,
+                                                            const float* __restrict__ dprob, int64_t total,
+                                                            TG* __restrict__ dfeat, int acc_dfeat,
+                                                            float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sw[C * NC];
+  __shared__ float sdw[C * NC + NC];
+  for (int i = threadIdx.x; i < C * NC + NC; i += TB) {
+    if (i < C * NC) sw[i] = w[i];
+    sdw[i] = 0.f;
+  }
+  __syncthreads();
+  float accw[C * NC + NC];
+#pragma unroll
+  for (int i = 0; i < C * NC + NC; ++i) accw[i] = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    float p[NC], g[NC];
+    float dot = 0.f;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      p[n] = prob[i * prob_c + head_off + n];
+      g[n] = dprob[i * NC + n];
+      dot = fmaf(p[n], g[n], dot);
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      g[n] = p[n] * (g[n] - dot);                          // dL/dlogit_n
+      accw[C * NC + n] += g[n];
+    }
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      float t8[8];
+      load8<T>(feat + i * C + c, t8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[c + k] = t8[k];
+    }
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      float t8[8];
+      if (acc_dfeat) {
+        load8<TG>(dfeat + i * C + c, t8);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t8[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          t8[k] = fmaf(g[n], sw[(c + k) * NC + n], t8[k]);
+          accw[(c + k) * NC + n] = fmaf(f[c + k], g[n], accw[(c + k) * NC + n]);
+        }
+      }
+      store8<TG>(dfeat + i * C + c, t8);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C * NC + NC; ++i) {
+    const float v = warp_sum(accw[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[i], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * NC + NC; i += TB) {
+    if (i < C * NC) atomicAdd(dw + i, sdw[i]);
+    else atomicAdd(db + (i - C * NC), sdw[i]);
+  }
+}
+
+struct FusionArgs {
+  float alpha[2];
+  float gamma;
+  int pc1, ch1, pc2, ch2, strategy;
+  float loss_scale, grad_scale;
+};
+
+// j = fusion(p1, p2); det1 = [1-p1, p1], det2 = [1-j, j]; focal([1-j, j]) and d/dp1, d/dp2
+template <typename TY>
+__global__ void __launch_bounds__(TB) fusion_focal_kernel(const float* __restrict__ prob1, const float* __restrict__ prob2,
+                                                         const TY* __restrict__ y, FusionArgs a, int64_t total,
+                                                         float* __restrict__ det1, float* __restrict__ det2,
+                                                         float* __restrict__ loss_out, float* __restrict__ dp1,
+                                                         float* __restrict__ dp2, GridSum gs) {
+  __shared__ float sm[TB / 32];
+  float acc[1] = {0.f};
+  for (int64_t i = blockIdx.x * (int64_t)TB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB) {
+    const float pa = prob1[i * a.pc1 + a.ch1], pb = prob2[i * a.pc2 + a.ch2];
+    float j, dja, djb;
+    if (a.strategy == 0) {
+      j = pb; dja = 0.f; djb = 1.f;
+    } else if (a.strategy == 1) {
+      j = 1.f - (1.f - pa) * (1.f - pb); dja = 1.f - pb; djb = 1.f - pa;
+    } else {
+      const float num = pa * pb + 1e-9f, den = num + (1.f - pa) * (1.f - pb);
+      j = num / den;
+      dja = (pb * den - num * (2.f * pb - 1.f)) / (den * den);
+      djb = (pa * den - num * (2.f * pa - 1.f)) / (den * den);
+    }
+    if (det1) { det1[2 * i] = 1.f - pa; det1[2 * i + 1] = pa; }
+    if (det2) { det2[2 * i] = 1.f - j; det2[2 * i + 1] = j; }
+    if (y == nullptr) continue;
+    // Focal.FL on y_pred = [1-j, j] (losses.py:32-39): the renormalisation divides by exactly 1
+    const float q[2] = {1.f - j, j};
+    float fl = 0.f, gq[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float yt = ld_f<TY>(y + i * 2 + c);
+      const float qc = fminf(fmaxf(q[c], 1e-7f), 1.f - 1e-7f);
+      const float om = 1.f - qc;
+      const float pw = powf(om, a.gamma);
+      const float nl = -logf(qc);
+      const float wgt = a.alpha[c] * yt * yt;
+      fl = fmaf(wgt * pw, nl, fl);
+      const float inside = (q[c] >= 1e-7f && q[c] <= 1.f - 1e-7f) ? 1.f : 0.f;
+      const float dpw = a.gamma == 0.f ? 0.f : a.gamma * powf(om, a.gamma - 1.f);
+      gq[c] = wgt * inside * (-dpw * nl - pw / qc);
+    }
+    acc[0] += fl;
+    const float dj = a.grad_scale * (gq[1] - gq[0]);         // q0 = 1 - j, q1 = j
+    if (dp1) dp1[i] = dj * dja;
+    if (dp2) dp2[i] = dj * djb;
+  }
+  block_sum<1, TB>(acc, sm);
+  if (loss_out) grid_sum_add<TB>(acc[0], a.loss_scale, loss_out, gs, sm);
+}
+
 inline unsigned nblocks(const m1_ctx* ctx, int64_t total, int per = TB) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(total, per), (int64_t)ctx->num_sms * 16));
 }
@@ -760,4 +891,57 @@ extern "C" int m1_logits_softmax_focal(m1_ctx* ctx, const void* feat, int fdtype
 #undef M1_LF
   m1_set_error("m1_logits_softmax_focal: no instantiation for C=%d nc=%d", C, nc);
   return 2;
+}
+
+template <typename T, typename TG, int C, int NC>
+static void launch_logits_prob_bwd(m1_ctx* ctx, const void* feat, const float* w, const float* prob, int prob_c,
+                                   int head_off, const float* dprob, int64_t total, void* dfeat, int acc_dfeat,
+                                   float* dw, float* db, cudaStream_t st) {
+  logits_prob_bwd_kernel<T, TG, C, NC><<<nblocks(ctx, total), TB, 0, st>>>((const T*)feat, w, prob, prob_c, head_off, dprob,
+                                                                         total, (TG*)dfeat, acc_dfeat, dw, db);
+}
+
+extern "C" int m1_logits_prob_bwd(m1_ctx* ctx, const void* feat, int fdtype, const float* w, const float* prob,
+                                  int prob_c, int head_off, const float* dprob, int64_t rows, int C, int nc,
+                                  void* dfeat, int acc_dfeat, float* dw, float* db, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define M1_LP(CC, NN)                                                                                              \
+  if (C == CC && nc == NN) {                                                                                       \
+    M1_DISPATCH_VG(fdtype, T, TG, (launch_logits_prob_bwd<T, TG, CC, NN>(ctx, feat, w, prob, prob_c, head_off, dprob, \
+                                                                         rows, dfeat, acc_dfeat, dw, db, st)));    \
+    M1_LAUNCH_CHECK(ctx);                                                                                          \
+    return 0;                                                                                                      \
+  }
+  M1_LP(32, 2)
+  M1_LP(8, 2)
+  M1_LP(16, 2)
+#undef M1_LP
+  m1_set_error("m1_logits_prob_bwd: no instantiation for C=%d nc=%d", C, nc);
+  return 2;
+}
+
+extern "C" int m1_fusion_focal(m1_ctx* ctx, const float* prob1, int pc1, int ch1, const float* prob2, int pc2, int ch2,
+                               int strategy, const void* y_true, int ydtype, const float* alpha, float gamma, int batch,
+                               int64_t voxels, float* det1, float* det2, float weight, float* loss_out, float* dp1,
+                               float* dp2, float grad_scale, void* stream) {
+  M1_CHECK(strategy >= 0 && strategy <= 2, "m1_fusion_focal: unknown strategy %d", strategy);
+  M1_CHECK(ydtype == M1_F32 || ydtype == M1_BF16, "m1_fusion_focal: labels must be fp32 or bf16");
+  FusionArgs a;
+  a.alpha[0] = alpha ? alpha[0] : 0.f;
+  a.alpha[1] = alpha ? alpha[1] : 0.f;
+  a.gamma = gamma;
+  a.pc1 = pc1; a.ch1 = ch1; a.pc2 = pc2; a.ch2 = ch2; a.strategy = strategy;
+  a.loss_scale = weight / (float)batch;
+  a.grad_scale = grad_scale * weight / (float)batch;
+  const int64_t total = (int64_t)batch * voxels;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ydtype == M1_BF16)
+    fusion_focal_kernel<__nv_bfloat16><<<nblocks(ctx, total), TB, 0, st>>>(prob1, prob2, (const __nv_bfloat16*)y_true, a,
+                                                                          total, det1, det2, loss_out, dp1, dp2,
+                                                                          m1_grid_sum(ctx));
+  else
+    fusion_focal_kernel<float><<<nblocks(ctx, total), TB, 0, st>>>(prob1, prob2, (const float*)y_true, a, total, det1, det2,
+                                                                  loss_out, dp1, dp2, m1_grid_sum(ctx));
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
 }

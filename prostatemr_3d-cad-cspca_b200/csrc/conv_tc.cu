@@ -30,6 +30,7 @@
 #include "tc_epilogue.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace {
 using namespace tc;
@@ -379,30 +380,54 @@ struct PackArgs {
   int src_start[M1_MAX_SRC + 1];
   int nout, nsrc, w_by_src;
 };
+// value of element i of the [tap][n_total][k_total] pack
+__device__ __forceinline__ float pack_value(const PackArgs& a, int n_real, int n_total, int k_total, int64_t i) {
+  int r = (int)(i % k_total);
+  int n = (int)((i / k_total) % n_total);
+  const int tap = (int)(i / ((int64_t)k_total * n_total));
+  if (n >= n_real) return 0.f;
+  int j = 0;
+  while (j + 1 < a.nout && n >= a.out_start[j + 1]) ++j;
+  n -= a.out_start[j];
+  if (a.w_by_src) {
+    int s = 0;
+    while (s + 1 < a.nsrc && r >= a.src_start[s + 1]) ++s;
+    r -= a.src_start[s];
+    return a.w[j * a.nsrc + s][tap * a.st[s] + r * a.sr[s] + n * a.so[s]];
+  }
+  return a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
+}
+
 template <typename TW>
 __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, int n_real, int n_total, int k_total,
                                     int taps, TW* __restrict__ out) {
   const int64_t total = (int64_t)taps * n_total * k_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int r = (int)(i % k_total);
-    int n = (int)((i / k_total) % n_total);
-    const int tap = (int)(i / ((int64_t)k_total * n_total));
-    float v = 0.f;
-    if (n < n_real) {
-      int j = 0;
-      while (j + 1 < a.nout && n >= a.out_start[j + 1]) ++j;
-      n -= a.out_start[j];
-      if (a.w_by_src) {
-        int s = 0;
-        while (s + 1 < a.nsrc && r >= a.src_start[s + 1]) ++s;
-        r -= a.src_start[s];
-        v = a.w[j * a.nsrc + s][tap * a.st[s] + r * a.sr[s] + n * a.so[s]];
-      } else {
-        v = a.w[j][tap * a.st[j] + r * a.sr[j] + n * a.so[j]];
-      }
-    }
-    st_f<TW>(out + i, v);
+       i += (int64_t)gridDim.x * blockDim.x)
+    st_f<TW>(out + i, pack_value(a, n_real, n_total, k_total, i));
+}
+
+// ---- all packs of a model in ONE launch (the re-pack after every optimizer step: ~350 packs) ----------------
+struct PackJob {
+  PackArgs a;
+  int n_real, n_total, k_total, f16;
+  int64_t total;
+  void* out;
+};
+constexpr int kPackItems = 8;     // elements per thread
+
+__global__ void __launch_bounds__(256) pack_batched_kernel(const PackJob* __restrict__ jobs,
+                                                           const int* __restrict__ block_job,
+                                                           const int64_t* __restrict__ block_first) {
+  const PackJob& J = jobs[block_job[blockIdx.x]];
+  const int64_t base = block_first[blockIdx.x] + threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < kPackItems; ++it) {
+    const int64_t i = base + (int64_t)it * 256;
+    if (i >= J.total) break;
+    const float v = pack_value(J.a, J.n_real, J.n_total, J.k_total, i);
+    if (J.f16) st_f<__half>(reinterpret_cast<__half*>(J.out) + i, v);
+    else st_f<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(J.out) + i, v);
   }
 }
 
@@ -521,6 +546,30 @@ extern "C" int64_t m1_conv3d_packed_bytes(const m1_conv_desc* d) {
   return (int64_t)taps * pl.n_total * pl.k_total * 2;
 }
 
+static void fill_pack_args(const m1_conv_desc* d, const float* const* w, PackArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->nout = d->nout;
+  a->nsrc = d->nsrc;
+  a->w_by_src = d->w_by_src;
+  int acc = 0;
+  for (int j = 0; j < d->nout; ++j) {
+    a->out_start[j] = acc;
+    acc += d->out_c[j];
+  }
+  a->out_start[d->nout] = acc;
+  acc = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    a->src_start[s] = acc;
+    acc += d->src_c[s];
+  }
+  a->src_start[d->nsrc] = acc;
+  for (int j = 0; j < M1_MAX_OUT; ++j) {
+    a->st[j] = d->w_stride_tap[j]; a->sr[j] = d->w_stride_red[j]; a->so[j] = d->w_stride_out[j];
+  }
+  const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
+  for (int i = 0; i < nw; ++i) a->w[i] = w[i];
+}
+
 extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const float* const* w,
                                       void* w_packed, void* stream) {
   Plan pl;
@@ -529,27 +578,7 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
   const int64_t total = (int64_t)taps * pl.n_total * pl.k_total;
   const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 8);
   PackArgs a;
-  memset(&a, 0, sizeof(a));
-  a.nout = d->nout;
-  a.nsrc = d->nsrc;
-  a.w_by_src = d->w_by_src;
-  int acc = 0;
-  for (int j = 0; j < d->nout; ++j) {
-    a.out_start[j] = acc;
-    acc += d->out_c[j];
-  }
-  a.out_start[d->nout] = acc;
-  acc = 0;
-  for (int s = 0; s < d->nsrc; ++s) {
-    a.src_start[s] = acc;
-    acc += d->src_c[s];
-  }
-  a.src_start[d->nsrc] = acc;
-  for (int j = 0; j < M1_MAX_OUT; ++j) {
-    a.st[j] = d->w_stride_tap[j]; a.sr[j] = d->w_stride_red[j]; a.so[j] = d->w_stride_out[j];
-  }
-  const int nw = d->w_by_src ? d->nout * d->nsrc : d->nout;
-  for (int i = 0; i < nw; ++i) a.w[i] = w[i];
+  fill_pack_args(d, w, &a);
   if (m1_conv_w_dtype(d) == M1_F16)
     pack_weights_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pl.n_real, pl.n_total, pl.k_total, taps,
                                                                         reinterpret_cast<__half*>(w_packed));
@@ -557,6 +586,63 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
     pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         a, pl.n_real, pl.n_total, pl.k_total, taps, reinterpret_cast<__nv_bfloat16*>(w_packed));
   M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+struct m1_pack_plan {
+  PackJob* jobs;
+  int* block_job;
+  int64_t* block_first;
+  int nblocks;
+};
+
+extern "C" int m1_pack_plan_create(m1_ctx* ctx, int njobs, const m1_conv_desc* const* descs,
+                                   const float* const* const* ws, void* const* packed, m1_pack_plan** out) {
+  M1_CHECK(ctx && out && njobs > 0, "m1_pack_plan_create: bad arguments");
+  std::vector<PackJob> jobs((size_t)njobs);
+  std::vector<int> bj;
+  std::vector<int64_t> bf;
+  for (int q = 0; q < njobs; ++q) {
+    Plan pl;
+    M1_CHECK(make_plan(descs[q], &pl), "m1_pack_plan_create: job %d is not a tcgen05 launch", q);
+    PackJob& J = jobs[(size_t)q];
+    fill_pack_args(descs[q], ws[q], &J.a);
+    const int taps = descs[q]->kernel[0] * descs[q]->kernel[1] * descs[q]->kernel[2];
+    J.n_real = pl.n_real; J.n_total = pl.n_total; J.k_total = pl.k_total;
+    J.f16 = m1_conv_w_dtype(descs[q]) == M1_F16;
+    J.total = (int64_t)taps * pl.n_total * pl.k_total;
+    J.out = packed[q];
+    for (int64_t first = 0; first < J.total; first += 256 * kPackItems) {
+      bj.push_back(q);
+      bf.push_back(first);
+    }
+  }
+  m1_pack_plan* p = new m1_pack_plan();
+  p->nblocks = (int)bj.size();
+  M1_CUDA(cudaMalloc(&p->jobs, jobs.size() * sizeof(PackJob)));
+  M1_CUDA(cudaMalloc(&p->block_job, bj.size() * sizeof(int)));
+  M1_CUDA(cudaMalloc(&p->block_first, bf.size() * sizeof(int64_t)));
+  M1_CUDA(cudaMemcpy(p->jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  M1_CUDA(cudaMemcpy(p->block_job, bj.data(), bj.size() * sizeof(int), cudaMemcpyHostToDevice));
+  M1_CUDA(cudaMemcpy(p->block_first, bf.data(), bf.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+extern "C" int m1_pack_plan_run(m1_ctx* ctx, const m1_pack_plan* plan, void* stream) {
+  M1_CHECK(ctx && plan, "m1_pack_plan_run: NULL argument");
+  pack_batched_kernel<<<(unsigned)plan->nblocks, 256, 0, (cudaStream_t)stream>>>(plan->jobs, plan->block_job,
+                                                                                 plan->block_first);
+  M1_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int m1_pack_plan_destroy(m1_pack_plan* plan) {
+  if (!plan) return 0;
+  cudaFree(plan->jobs);
+  cudaFree(plan->block_job);
+  cudaFree(plan->block_first);
+  delete plan;
   return 0;
 }
 

@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(TB, 2) inorm_bwd_reduce_kernel(const TG* __res
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int64_t voxels,
                                                              int C, float slope, int64_t rows_per_slab,
-                                                             ReduceScratch rs, float* __restrict__ red) {
+                                                             ReduceScratch rs, float* __restrict__ red,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   static_assert(sizeof(T) == sizeof(TG), "value and gradient storage must have the same width");
   extern __shared__ float smem[];
   const int n = blockIdx.y;
@@ -348,7 +349,13 @@ __global__ void __launch_bounds__(TB, 2) inorm_bwd_reduce_kernel(const TG* __res
           acc[1][i] = fmaf(gg, xh, acc[1][i]);
         }
       },
-      [&](int c, const float (&t)[2]) { out[2 * c] = t[0]; out[2 * c + 1] = t[1]; });
+      [&](int c, const float (&t)[2]) {
+        out[2 * c] = t[0];
+        out[2 * c + 1] = t[1];
+        // dbeta += sum g, dgamma += sum g * xhat: one atomic per (sample, channel) - no extra launch
+        if (dbeta) atomicAdd(dbeta + c, t[0]);
+        if (dgamma) atomicAdd(dgamma + c, t[1]);
+      });
 }
 
 struct NormBwdRegs {
@@ -425,15 +432,29 @@ __global__ void se_squeeze_kernel(const float* __restrict__ stats3, const float*
 }
 
 // one block per sample; C <= 2048, Cr <= 256
-__global__ void __launch_bounds__(TB) se_excite_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ w6,
+__global__ void __launch_bounds__(TB) se_excite_fwd_kernel(float* __restrict__ pool, const float* __restrict__ w6,
                                                           const float* __restrict__ b6, const float* __restrict__ w7,
                                                           const float* __restrict__ b7, int C, int Cr,
-                                                          float* __restrict__ hidden, float* __restrict__ gate) {
+                                                          float* __restrict__ hidden, float* __restrict__ gate,
+                                                          const float* __restrict__ stats3,
+                                                          const float* __restrict__ gamma3,
+                                                          const float* __restrict__ beta3) {
   extern __shared__ float sm[];  // pool[C] | act[Cr]
   float* sp = sm;
   float* sa = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += TB) sp[c] = pool[(int64_t)n * C + c];
+  for (int c = threadIdx.x; c < C; c += TB) {
+    float v;
+    if (stats3 != nullptr) {      // squeeze folded in: pool = GAP(norm3(raw3)) from the statistics (se_squeeze_kernel)
+      const int64_t i = (int64_t)n * C + c;
+      const float mean = stats3[2 * i], a = stats3[2 * i + 1] * gamma3[c];
+      v = fmaf(mean, a, beta3[c] - mean * a);
+      pool[i] = v;
+    } else {
+      v = pool[(int64_t)n * C + c];
+    }
+    sp[c] = v;
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < Cr; j += TB) {
     float h = b6[j];
@@ -455,7 +476,10 @@ __global__ void __launch_bounds__(TB) se_excite_bwd_kernel(const float* __restri
                                                           const float* __restrict__ w6, const float* __restrict__ w7,
                                                           int C, int Cr, float* __restrict__ dpool,
                                                           float* __restrict__ dw6, float* __restrict__ db6,
-                                                          float* __restrict__ dw7, float* __restrict__ db7) {
+                                                          float* __restrict__ dw7, float* __restrict__ db7,
+                                                          const float* __restrict__ red5, float* __restrict__ dgamma3,
+                                                          float* __restrict__ dbeta3, float* __restrict__ dgamma4,
+                                                          float* __restrict__ dbeta4) {
   extern __shared__ float sm[];  // dpre7[C] | act[Cr] | dhid[Cr] | pool[C]
   float* sd7 = sm;
   float* sa = sm + C;
@@ -489,6 +513,15 @@ __global__ void __launch_bounds__(TB) se_excite_bwd_kernel(const float* __restri
     float dp = 0.f;
     for (int j = 0; j < Cr; ++j) dp = fmaf(w6[(int64_t)c * Cr + j], sdh[j], dp);
     dpool[(int64_t)n * C + c] = dp;
+    if (red5 != nullptr) {
+      // parameter gradients of norm3 / norm4 from the reductions of the gate backward (one atomic per sample):
+      // norm3: dgamma += A2, dbeta += A1 + dpool ; norm4: dgamma += B2, dbeta += B1
+      const float* r = red5 + ((int64_t)n * C + c) * 5;
+      atomicAdd(dgamma3 + c, r[1]);
+      atomicAdd(dbeta3 + c, r[0] + dp);
+      atomicAdd(dgamma4 + c, r[3]);
+      atomicAdd(dbeta4 + c, r[2]);
+    }
   }
 }
 
@@ -784,7 +817,7 @@ extern "C" int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, cons
   if (reduce_scratch(ctx, grid.x, batch, 2, C, &rs)) return 1;
   DISPATCH_T_VW4(dtype, C, (inorm_bwd_reduce_kernel<T, TG, VW><<<grid, TB, reduce_smem(2, C, VW), st>>>(
                               reinterpret_cast<const TG*>(dy), reinterpret_cast<const T*>(x), stats, gamma, beta,
-                              voxels, C, slope, rows, rs, red)));
+                              voxels, C, slope, rows, rs, red, dgamma, dbeta)));
   M1_LAUNCH_CHECK(ctx);
   {
     const int64_t rows8 = slab_rows(ctx, batch, voxels, 8);
@@ -794,10 +827,6 @@ extern "C" int m1_inorm_act_bwd(m1_ctx* ctx, const void* dy, const void* x, cons
                                voxels, C, slope, 1.f / (float)voxels, reinterpret_cast<TG*>(dx), accumulate, rows8)));
   }
   M1_LAUNCH_CHECK(ctx);
-  if (dgamma || dbeta) {
-    param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, 2, 1, 0, batch, C, nullptr, dgamma, dbeta);
-    M1_LAUNCH_CHECK(ctx);
-  }
   return 0;
 }
 
@@ -811,20 +840,24 @@ extern "C" int m1_se_squeeze(m1_ctx* ctx, const void* raw3, const float* stats3,
   return 0;
 }
 
-extern "C" int m1_se_excite_fwd(m1_ctx* ctx, const float* pool, const float* w6, const float* b6,
+extern "C" int m1_se_excite_fwd(m1_ctx* ctx, float* pool, const float* w6, const float* b6,
                                 const float* w7, const float* b7, int batch, int C, int Cr, float* hidden,
-                                float* gate, void* stream) {
+                                float* gate, const float* stats3, const float* gamma3, const float* beta3,
+                                void* stream) {
   se_excite_fwd_kernel<<<batch, TB, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool, w6, b6, w7, b7, C, Cr,
-                                                                                     hidden, gate);
+                                                                                     hidden, gate, stats3, gamma3, beta3);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 extern "C" int m1_se_excite_bwd(m1_ctx* ctx, const float* dgate, const float* pool, const float* hidden,
                                 const float* gate, const float* w6, const float* w7, int batch, int C, int Cr,
-                                float* dpool, float* dw6, float* db6, float* dw7, float* db7, void* stream) {
+                                float* dpool, float* dw6, float* db6, float* dw7, float* db7, const float* red5,
+                                float* dgamma3, float* dbeta3, float* dgamma4, float* dbeta4, void* stream) {
+  M1_CHECK(red5 == nullptr || (dgamma3 && dbeta3 && dgamma4 && dbeta4),
+           "m1_se_excite_bwd: red5 given without the four norm parameter gradients");
   se_excite_bwd_kernel<<<batch, TB, (2 * C + 2 * Cr) * sizeof(float), (cudaStream_t)stream>>>(
-      dgate, pool, hidden, gate, w6, w7, C, Cr, dpool, dw6, db6, dw7, db7);
+      dgate, pool, hidden, gate, w6, w7, C, Cr, dpool, dw6, db6, dw7, db7, red5, dgamma3, dbeta3, dgamma4, dbeta4);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -884,9 +917,14 @@ extern "C" int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* r
   }
   M1_LAUNCH_CHECK(ctx);
   // norm3: dgamma += sum_n A2, dbeta += sum_n (A1 + dpool) ; norm4: dgamma += sum_n B2, dbeta += sum_n B1
-  param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, 5, 1, 0, batch, C, dpool, dgamma3, dbeta3);
-  M1_LAUNCH_CHECK(ctx);
-  param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, 5, 3, 2, batch, C, nullptr, dgamma4, dbeta4);
-  M1_LAUNCH_CHECK(ctx);
+  // (NULL pointers: m1_se_excite_bwd already accumulated them from red5 - two launches fewer per block)
+  if (dgamma3 || dbeta3) {
+    param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, 5, 1, 0, batch, C, dpool, dgamma3, dbeta3);
+    M1_LAUNCH_CHECK(ctx);
+  }
+  if (dgamma4 || dbeta4) {
+    param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, 5, 3, 2, batch, C, nullptr, dgamma4, dbeta4);
+    M1_LAUNCH_CHECK(ctx);
+  }
   return 0;
 }

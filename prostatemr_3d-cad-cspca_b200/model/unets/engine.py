@@ -350,9 +350,18 @@ class Engine:
         return outs
 
     def refresh_packs(self):
-        """Re-derive the bf16 operand packs from the fp32 master weights (after an optimizer step)."""
-        for d, ws, packed in self.packs.values():
-            ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
+        """Re-derive the 16-bit operand packs from the fp32 master weights (after an optimizer step): ONE launch for
+        all packs (m1_pack_plan); the plan is rebuilt whenever a new pack has appeared (never during graph capture)."""
+        if not self.packs:
+            return
+        plan = getattr(self, "_pack_plan", None)
+        if plan is None or plan.n != len(self.packs):
+            if torch.cuda.is_current_stream_capturing():
+                for d, ws, packed in self.packs.values():
+                    ops.conv3d_pack_weights_into(self.ctx, d, ws, packed)
+                return
+            plan = self._pack_plan = ops.PackPlan(self.ctx, list(self.packs.values()))
+        plan.run()
 
     # (max voxels per K brick, taps sharing a dY tile [0 = kw if it fits], stage cap, M tiles per CTA)
     WG_CANDIDATES = ((128, 0, 2, 1), (128, 1, 2, 1), (64, 0, 2, 1), (64, 1, 2, 1), (128, 0, 3, 1), (64, 0, 3, 1),
@@ -575,8 +584,7 @@ class Engine:
         def fwd():
             ops.inorm_stats(self.ctx, raw3.t, st3, IN_EPS)
             ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
-            ops.se_squeeze(self.ctx, raw3.t, st3, g3, b3, pool)
-            ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate)
+            ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate, st3, g3, b3)     # squeeze folded in
             ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t, out.tw)
         nel, es = raw3.t.numel(), raw3.t.element_size()
         # algorithmic passes: the two statistics reads + gate pass (2 reads, 1 write)
@@ -597,11 +605,11 @@ class Engine:
                                        dgate)
                 ops.se_excite_bwd(self.ctx, dgate, pool, hidden, gate, w6, w7, dpool,
                                   self.pg(name + "/conv6/kernel"), self.pg(name + "/conv6/bias"),
-                                  self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"))
+                                  self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"), red,
+                                  self.pg(name + "/norm3/gamma"), self.pg(name + "/norm3/beta"),
+                                  self.pg(name + "/norm4/gamma"), self.pg(name + "/norm4/beta"))
                 ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
-                                      dpool, raw3.g, raw4.g, self.pg(name + "/norm3/gamma"),
-                                      self.pg(name + "/norm3/beta"), self.pg(name + "/norm4/gamma"),
-                                      self.pg(name + "/norm4/beta"))
+                                      dpool, raw3.g, raw4.g, None, None, None, None)
             self._timed("se_tail_bwd", 0, run, nbytes=8 * nel * es)       # 2 x 3 reads + 2 writes
             out.g = None
         if self.record:

@@ -235,6 +235,16 @@ class M1(LoadableModel):
       build       False -> host-only object (configuration + parameter inventory, no GPU needed)
     """
 
+    def __new__(cls, *args, **kwargs):
+        """M1(..., cascaded='identity' | 'noisy-or' | 'bayes' | True) is the two-stage model of
+        R:networks.py:109-193: the object returned is a CascadedM1 (same API, two single-stage M1 inside)."""
+        if cls is M1:
+            cascaded = kwargs.get('cascaded', args[14] if len(args) > 14 else False)
+            if cascaded is not False:
+                from .cascade import CascadedM1
+                return object.__new__(CascadedM1)
+        return object.__new__(cls)
+
     @store_config_args
     def __init__(self,
                  input_spatial_dims,
@@ -265,11 +275,7 @@ class M1(LoadableModel):
         assert ndims == 3, 'the sm_100a kernels implement the 3-D model (the only one M1Core can build)'
         assert ds_in_prob in ('reference', 'intended')
         assert precision in ('fp16', 'bf16', 'fp32'), "precision must be 'fp16', 'bf16' or 'fp32'"
-        if cascaded is not False:
-            raise NotImplementedError(
-                "cascaded two-stage M1 (R:networks.py:109-193) is not wired yet: the m1_decision_fusion kernel and "
-                "its oracle exist, the second stage's input concat and the gradient through the stage-1 softmax "
-                "do not (SURVEY.md section 8(f), rank n4); build the two stages as separate M1 objects meanwhile")
+        assert cascaded is False, "cascaded models are built by M1.__new__ as CascadedM1 (model/unets/cascade.py)"
         self.name = name
         self.input_spatial_dims = tuple(int(d) for d in input_spatial_dims)
         self.input_channels, self.num_classes = int(input_channels), int(num_classes)
@@ -371,7 +377,7 @@ class M1(LoadableModel):
         print('-' * 85)
 
     # ---- graph wiring (R:networks.py:266-390) ------------------------------------------------------
-    def _inputs(self, eng, batch, x, trace):
+    def _inputs(self, eng, batch, x, trace, needs_grad=False):
         """Model input -> activation tensors. Probabilistic (Q4, R:networks.py:300-301):
         image = inputs[..., :-(nc-1)], label = inputs[..., -(nc-1)-1:-1] - for nc=2, C=4 the 'label' is
         image channel 2, NOT channel 3; the slicing is reproduced exactly."""
@@ -382,11 +388,11 @@ class M1(LoadableModel):
             """(B,D,H,W,pad16(lc)) activation, zero beyond the real channels (tensor-core granularity)"""
             pc = eng.padc(lc)
             if trace:
-                return eng.input((batch,) + D + (pc,), lc=lc)
+                return eng.input((batch,) + D + (pc,), needs_grad=needs_grad, lc=lc)
             t = eng.new((batch,) + D + (pc,), zero=pc != lc)
             for src_off, dst_off, n in copies:
                 ops.copy_channels(eng.ctx, x, src_off, t, dst_off, n)
-            return eng.input(t, lc=lc)
+            return eng.input(t, needs_grad=needs_grad, lc=lc)
 
         if not self.probabilistic:
             return [padded(C, [(0, 0, C)])], None
@@ -403,13 +409,14 @@ class M1(LoadableModel):
         intended deep-supervision wiring makes the prior core produce outputs of its own."""
         return bool(self.compute_dead_branches or (self.probabilistic and self.prior.deep_supervision))
 
-    def _graph(self, eng, batch, training, trace=False, x=None, dead=None):
-        """One training-graph forward. Returns dict(heads=[(logits Act, up)], kl_pairs=[(ml_q, ml_p)])."""
-        img, lab = self._inputs(eng, batch, x, trace)
+    def _graph(self, eng, batch, training, trace=False, x=None, dead=None, input_needs_grad=False):
+        """One training-graph forward. Returns dict(heads=[(logits Act, up)], kl_pairs=[(ml_q, ml_p)], inputs=[Acts]).
+        input_needs_grad: also differentiate w.r.t. the model input (second stage of a cascade)."""
+        img, lab = self._inputs(eng, batch, x, trace, input_needs_grad)
         if not self.probabilistic:
             o = self.core(eng, img, pass_name='det', training=training)
             heads = [(o['logits'], (1, 1, 1))] + (o.get('ds_logits') or [])
-            return dict(heads=heads, kl_pairs=[])
+            return dict(heads=heads, kl_pairs=[], inputs=list(img))
         post_in = lab                 # [image || label] already concatenated by _inputs
         q_sample = self.posterior(eng, post_in, False, None, 'q_sample', training, 'latents')
         q_mean = self.posterior(eng, post_in, True, None, 'q_mean', training, 'latents')
@@ -420,7 +427,7 @@ class M1(LoadableModel):
                            need_logits=dead)
         train_conv = self.final_decoder(eng, p_zqm['prob_decoder_features'])
         heads = [(train_conv, (1, 1, 1))] + (p_zqm.get('ds_logits') or [])
-        return dict(heads=heads,
+        return dict(heads=heads, inputs=list(img) + list(post_in),
                     kl_pairs=list(zip(q_sample['prob_distributions'], p_zq['prob_distributions'])))
 
     def _infer_graph(self, eng, batch, trace=False, x=None, pass_name='p_sample'):
@@ -608,42 +615,56 @@ class M1(LoadableModel):
                 return out
         return self._train_step_eager(x, y, apply_update)
 
-    def _train_step_eager(self, x, y, apply_update=True, graphed=False):
+    def _forward_train(self, x, input_needs_grad=False):
+        """forward of the training graph: (graph dict, detection tensor [B,D,H,W,nc*heads] fp32, loss scalars)"""
         eng = self.eng
         B = x.shape[0]
         eng.noise = self.noise
         eng.begin(record=True)
         self.params.g.zero_()
-        g = self._graph(eng, B, training=True, x=x)
-        if self.train_flops_per_volume is None:
-            self.train_flops_per_volume = 3 * eng.conv_flops // B
-        nc = self.num_classes
-        heads = g['heads']
-        det = torch.empty((B,) + self.input_spatial_dims + (nc * len(heads),), dtype=torch.float32,
+        g = self._graph(eng, B, training=True, x=x, input_needs_grad=input_needs_grad)
+        det = torch.empty((B,) + self.input_spatial_dims + (self.num_classes * len(g['heads']),), dtype=torch.float32,
                           device=self.device)
         scal = torch.zeros(4, dtype=torch.float32, device=self.device)   # focal, kl, l2, unused
+        return g, det, scal
+
+    def _seed_losses(self, g, y, det, scal, w_f, w_kl, with_focal=True):
+        """softmax of every head into det; focal loss + its gradient seeds (with_focal), KL + its seeds.
+        Loss terms of a replica are scaled 1/R (MirroredStrategy + Keras SUM_OVER_BATCH_SIZE)."""
+        eng, nc = self.eng, self.num_classes
+        heads = g['heads']
+        inv_r = 1.0 / self.world_size
+        for hi, (lg, up) in enumerate(heads):
+            if not with_focal:
+                self._softmax_head(eng, lg, up, det, nc * hi)
+                continue
+            if isinstance(lg, LazyHead):
+                fresh = lg.feat.g is None
+                gbuf, acc = eng.grad_buffer(lg.feat)
+                if lg.feat.c == lg.feat.lc and ops.logits_softmax_focal(
+                        eng.ctx, lg.feat.t, lg.w, lg.b, y, self.focal.alpha, float(self.focal.gamma), det,
+                        nc * hi, 1.0 / len(heads), scal[0:1], gbuf, acc, eng.pg(lg.name + "/kernel"),
+                        eng.pg(lg.name + "/bias"), w_f * inv_r):
+                    continue
+                if fresh:
+                    lg.feat.g = None
+                lg = lg.materialize(eng)
+            gbuf, _ = eng.grad_buffer(lg, zero=True)
+            ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
+                              1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
+        for ml_q, ml_p in g['kl_pairs']:
+            eng.kl(ml_q, ml_p, scal[1:2])
+            eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
+
+    def _train_step_eager(self, x, y, apply_update=True, graphed=False):
+        eng = self.eng
+        B = x.shape[0]
+        g, det, scal = self._forward_train(x)
+        if self.train_flops_per_volume is None:
+            self.train_flops_per_volume = 3 * eng.conv_flops // B
         inv_r = 1.0 / self.world_size
         w_f, w_kl = self.loss_weights
-        def losses():
-            for hi, (lg, up) in enumerate(heads):
-                if isinstance(lg, LazyHead):
-                    fresh = lg.feat.g is None
-                    gbuf, acc = eng.grad_buffer(lg.feat)
-                    if lg.feat.c == lg.feat.lc and ops.logits_softmax_focal(
-                            eng.ctx, lg.feat.t, lg.w, lg.b, y, self.focal.alpha, float(self.focal.gamma), det,
-                            nc * hi, 1.0 / len(heads), scal[0:1], gbuf, acc, eng.pg(lg.name + "/kernel"),
-                            eng.pg(lg.name + "/bias"), w_f * inv_r):
-                        continue
-                    if fresh:
-                        lg.feat.g = None
-                    lg = lg.materialize(eng)
-                gbuf, _ = eng.grad_buffer(lg, zero=True)
-                ops.softmax_focal(eng.ctx, lg.t, y, self.focal.alpha, float(self.focal.gamma), up, det, nc * hi,
-                                  1.0 / len(heads), scal[0:1], gbuf, w_f * inv_r)
-            for ml_q, ml_p in g['kl_pairs']:
-                eng.kl(ml_q, ml_p, scal[1:2])
-                eng.kl_seed_grad(ml_q, ml_p, w_kl * self.elbo.beta * inv_r)
-        eng._timed("losses", 0, losses)
+        eng._timed("losses", 0, lambda: self._seed_losses(g, y, det, scal, w_f, w_kl))
         if self.grad_sync is not None and (not graphed or getattr(self, "_graph_dp_overlap", False)):
             self.grad_sync.begin(self.params.g, eng.param_uses)
             eng.backward(self.grad_sync.param_done)

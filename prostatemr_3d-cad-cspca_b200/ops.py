@@ -149,18 +149,22 @@ def se_squeeze(ctx, raw3, stats3, gamma3, beta3, pool):
                               n, v, c, ptr(pool), current_stream()))
 
 
-def se_excite_fwd(ctx, pool, w6, b6, w7, b7, hidden, gate):
+def se_excite_fwd(ctx, pool, w6, b6, w7, b7, hidden, gate, stats3=None, gamma3=None, beta3=None):
+    """stats3 / gamma3 / beta3 given: the squeeze (pool from the statistics of raw3) is folded into this launch"""
     n, c = pool.shape
     cr = hidden.shape[-1]
     check(lib().m1_se_excite_fwd(ctx.handle, ptr(pool), ptr(w6), ptr(b6), ptr(w7), ptr(b7), n, c, cr,
-                                 ptr(hidden), ptr(gate), current_stream()))
+                                 ptr(hidden), ptr(gate), ptr(stats3), ptr(gamma3), ptr(beta3), current_stream()))
 
 
-def se_excite_bwd(ctx, dgate, pool, hidden, gate, w6, w7, dpool, dw6, db6, dw7, db7):
+def se_excite_bwd(ctx, dgate, pool, hidden, gate, w6, w7, dpool, dw6, db6, dw7, db7, red5=None, dg3=None, db3=None,
+                  dg4=None, db4=None):
+    """red5 + the four norm parameter gradients given: they are accumulated here (se_gate_bwd_apply then gets None)"""
     n, c = pool.shape
     cr = hidden.shape[-1]
     check(lib().m1_se_excite_bwd(ctx.handle, ptr(dgate), ptr(pool), ptr(hidden), ptr(gate), ptr(w6), ptr(w7),
-                                 n, c, cr, ptr(dpool), ptr(dw6), ptr(db6), ptr(dw7), ptr(db7), current_stream()))
+                                 n, c, cr, ptr(dpool), ptr(dw6), ptr(db6), ptr(dw7), ptr(db7), ptr(red5), ptr(dg3),
+                                 ptr(db3), ptr(dg4), ptr(db4), current_stream()))
 
 
 def se_gate_fwd(ctx, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, out, out_bf16=None):
@@ -302,3 +306,58 @@ def logits_softmax_focal(ctx, feat, w, bias, y_true, alpha, gamma, prob, head_of
         return False
     check(rc)
     return True
+
+
+# ---- cascade ---------------------------------------------------------------------------------------
+def logits_prob_bwd(ctx, feat, w, prob, head_off, dprob, dfeat, acc_dfeat, dw, db):
+    """backward of logits conv + softmax for a gradient w.r.t. the probabilities (m1_logits_prob_bwd)"""
+    n, v, c = _nvc(feat)
+    nc = w.shape[-1]
+    rc = lib().m1_logits_prob_bwd(ctx.handle, ptr(feat), dtype_code(feat), ptr(w), ptr(prob), prob.shape[-1], head_off,
+                                  ptr(dprob), n * v, c, nc, ptr(dfeat), 1 if acc_dfeat else 0, ptr(dw), ptr(db),
+                                  current_stream())
+    if rc == 2:
+        return False
+    check(rc)
+    return True
+
+
+def fusion_focal(ctx, prob1, ch1, prob2, ch2, strategy, y_true, alpha, gamma, det1, det2, weight, loss_out, dp1, dp2,
+                 grad_scale):
+    """decision fusion + focal loss of the joint prediction + d/dp1, d/dp2 (m1_fusion_focal)"""
+    n = prob1.shape[0]
+    v = prob1.numel() // (n * prob1.shape[-1])
+    al = (C.c_float * 2)(*[float(a) for a in alpha]) if alpha is not None else None
+    check(lib().m1_fusion_focal(ctx.handle, ptr(prob1), prob1.shape[-1], ch1, ptr(prob2), prob2.shape[-1], ch2, strategy,
+                                ptr(y_true), dtype_code(y_true) if y_true is not None else F32,
+                                C.cast(al, C.c_void_p) if al is not None else None, gamma, n, v, ptr(det1), ptr(det2),
+                                weight, ptr(loss_out), ptr(dp1), ptr(dp2), grad_scale, current_stream()))
+
+
+class PackPlan:
+    """m1_pack_plan: every tensor-core operand pack of a model re-derived from the fp32 master weights in ONE launch.
+    jobs: [(ConvDesc, [fp32 weight views], packed tensor)]. Create outside CUDA-graph capture; run() is capturable."""
+
+    def __init__(self, ctx, jobs):
+        n = len(jobs)
+        self.ctx, self.n = ctx, n
+        self._keep = jobs                                                  # the device buffers must outlive the plan
+        desc_ptrs = (C.c_void_p * n)(*[C.addressof(d) for d, _, _ in jobs])
+        ws_arrays = [ptr_array([ptr(w) for w in ws]) for _, ws, _ in jobs]
+        ws_ptrs = (C.c_void_p * n)(*[C.cast(a, C.c_void_p).value for a in ws_arrays])
+        packed = (C.c_void_p * n)(*[ptr(pk) for _, _, pk in jobs])
+        h = C.c_void_p()
+        check(lib().m1_pack_plan_create(ctx.handle, n, C.cast(desc_ptrs, C.POINTER(ConvDesc)),
+                                        C.cast(ws_ptrs, C.POINTER(C.c_void_p)), C.cast(packed, C.POINTER(C.c_void_p)),
+                                        C.byref(h)))
+        self.handle = h
+
+    def run(self):
+        check(lib().m1_pack_plan_run(self.ctx.handle, self.handle, current_stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().m1_pack_plan_destroy(self.handle)
+        except Exception:      # noqa: BLE001 - interpreter shutdown
+            pass

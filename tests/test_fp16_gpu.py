@@ -96,8 +96,8 @@ def test_se_tail_fp16(ctx, C, red, rate):
     ops.inorm_stats(ctx, d4, st4)
     poold, hidden, gated = (torch.empty((2, C), device=DEV), torch.empty((2, Cr), device=DEV),
                             torch.empty((2, C), device=DEV))
-    ops.se_squeeze(ctx, d3, st3, D['g3'], D['b3'], poold)
-    ops.se_excite_fwd(ctx, poold, D['w6'], D['b6'], D['w7'], D['b7'], hidden, gated)
+    # the production sequence: squeeze folded into the excite launch (pool from the statistics of raw3)
+    ops.se_excite_fwd(ctx, poold, D['w6'], D['b6'], D['w7'], D['b7'], hidden, gated, st3, D['g3'], D['b3'])
     ud = u.to(DEV)
     drop = ops.make_dropout(rate, ud)
     out = torch.empty_like(d3)
@@ -110,10 +110,12 @@ def test_se_tail_fp16(ctx, C, red, rate):
     ops.se_gate_bwd_reduce(ctx, dd, d3, d4, st3, st4, D['g3'], D['b3'], D['g4'], D['b4'], gated, drop, red5, dgate)
     G = {k: torch.zeros_like(v) for k, v in D.items()}
     dpool = torch.empty((2, C), device=DEV)
-    ops.se_excite_bwd(ctx, dgate, poold, hidden, gated, D['w6'], D['w7'], dpool, G['w6'], G['b6'], G['w7'], G['b7'])
+    # ... and the norm3 / norm4 parameter gradients accumulated by the excite backward (no param_grad launches)
+    ops.se_excite_bwd(ctx, dgate, poold, hidden, gated, D['w6'], D['w7'], dpool, G['w6'], G['b6'], G['w7'], G['b7'],
+                      red5, G['g3'], G['b3'], G['g4'], G['b4'])
     dr3, dr4 = torch.empty(shape, device=DEV, dtype=B), torch.empty(shape, device=DEV, dtype=B)
     ops.se_gate_bwd_apply(ctx, dd, d3, d4, st3, st4, D['g3'], D['b3'], D['g4'], D['b4'], gated, drop, red5, dpool,
-                          dr3, dr4, G['g3'], G['b3'], G['g4'], G['b4'])
+                          dr3, dr4, None, None, None, None)
     torch.cuda.synchronize()
     _close(dr3, r3.grad, 1e-2, 'draw3')
     _close(dr4, r4.grad, 1e-2, 'draw4')
@@ -300,6 +302,29 @@ def test_pointwise_heads_fp16(ctx, C, N):
     ops.conv3d(ctx, dd, [dyd], [wd], None, [dx])
     torch.cuda.synchronize()
     _close(dx, x.grad, 1e-2, 'head dx')
+
+
+def test_batched_weight_repack_equals_per_pack(ctx):
+    """m1_pack_plan (every operand pack of the model in ONE launch) writes exactly what the per-pack launches write"""
+    from m1b200 import ops
+    model, cfg, x, y = _build('fp16')
+    model.set_noise(None, seed=3)
+    model.train_step(x, y)                       # creates the packs (fp16 forward packs, bf16 data-gradient packs)
+    eng = model.eng
+    assert len(eng.packs) > 100
+    dtypes = {pk.dtype for _, _, pk in eng.packs.values()}
+    assert dtypes == {torch.float16, torch.bfloat16}, dtypes
+    for _, _, pk in eng.packs.values():
+        pk.zero_()
+    eng.refresh_packs()
+    assert eng._pack_plan is not None and eng._pack_plan.n == len(eng.packs)
+    torch.cuda.synchronize()
+    batched = [pk.clone() for _, _, pk in eng.packs.values()]
+    for (d, ws, pk), ref in zip(eng.packs.values(), batched):
+        pk.zero_()
+        ops.conv3d_pack_weights_into(ctx, d, ws, pk)
+        torch.cuda.synchronize()
+        assert torch.equal(pk.view(torch.int16), ref.view(torch.int16))
 
 
 # ---- determinism of the forward reductions ---------------------------------------------------------------------
