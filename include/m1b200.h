@@ -229,8 +229,8 @@ int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* raw3, const 
                          const float* beta3, const float* gamma4, const float* beta4,
                          const float* gate, const m1_dropout* drop, const float* red,
                          const float* dpool, int dtype, int batch, int64_t voxels, int C,
-                         void* draw3, void* draw4, float* dgamma3, float* dbeta3,
-                         float* dgamma4, float* dbeta4, void* stream);
+                         void* draw3, void* draw4, int accumulate /* draw3 / draw4 += (several gates share raw3 / raw4) */,
+                         float* dgamma3, float* dbeta3, float* dgamma4, float* dbeta4, void* stream);
 
 /* ---- K6: additive attention gate, R:network_blocks.py:106-130 -------------------------------
  * psi = sigmoid(w_psi . lrelu(theta + up(phi)) + b_psi) on theta's grid (up = nearest, integer

@@ -690,7 +690,8 @@ __global__ void __launch_bounds__(TB, 2) se_gate_bwd_apply_kernel(const TG* __re
                                                               const T* __restrict__ raw4, GateArgs a, DropArgs dr,
                                                               const float* __restrict__ red5, int64_t voxels, int C,
                                                               float inv_v, TG* __restrict__ draw3,
-                                                              TG* __restrict__ draw4, int64_t rows_per_slab) {
+                                                              TG* __restrict__ draw4, int accumulate,
+                                                              int64_t rows_per_slab) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * voxels * C;
   const void* const src[3] = {raw3 + base, raw4 + base, dout + base};
@@ -724,6 +725,13 @@ __global__ void __launch_bounds__(TB, 2) se_gate_bwd_apply_kernel(const TG* __re
                       // the GAP path adds dpool/V to dx_, a per-(n,c) constant that the norm backward removes again
                       o3[k] = w.q3.a[k] * (dx_ - g.c[0][k] - xh3 * g.c[1][k]);
                       o4[k] = w.q4.a[k] * (dres - g.c[2][k] - xh4 * g.c[3][k]);
+                    }
+                    if (accumulate) {       // raw3 / raw4 shared by several gate kernels (one trunk, several dropouts)
+                      float p3[8], p4[8];
+                      ldv<TG, VW>(draw3 + e, p3);
+                      ldv<TG, VW>(draw4 + e, p4);
+#pragma unroll
+                      for (int k = 0; k < VW; ++k) { o3[k] += p3[k]; o4[k] += p4[k]; }
                     }
                     stv<TG, VW>(draw3 + e, o3);
                     stv<TG, VW>(draw4 + e, o4);
@@ -902,8 +910,8 @@ extern "C" int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* r
                                     const float* beta3, const float* gamma4, const float* beta4,
                                     const float* gate, const m1_dropout* drop, const float* red,
                                     const float* dpool, int dtype, int batch, int64_t voxels, int C, void* draw3,
-                                    void* draw4, float* dgamma3, float* dbeta3, float* dgamma4, float* dbeta4,
-                                    void* stream) {
+                                    void* draw4, int accumulate, float* dgamma3, float* dbeta3, float* dgamma4,
+                                    float* dbeta4, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   GateArgs a{stats3, stats4, gamma3, beta3, gamma4, beta4, gate};
   DropArgs dr = make_drop(drop);
@@ -913,7 +921,7 @@ extern "C" int m1_se_gate_bwd_apply(m1_ctx* ctx, const void* dout, const void* r
     DISPATCH_T_VW4(dtype, C, (se_gate_bwd_apply_kernel<T, TG, VW><<<grid, TB, 0, st>>>(
                                reinterpret_cast<const TG*>(dout), reinterpret_cast<const T*>(raw3),
                                reinterpret_cast<const T*>(raw4), a, dr, red, voxels, C, 1.f / (float)voxels,
-                               reinterpret_cast<TG*>(draw3), reinterpret_cast<TG*>(draw4), rows)));
+                               reinterpret_cast<TG*>(draw3), reinterpret_cast<TG*>(draw4), accumulate, rows)));
   }
   M1_LAUNCH_CHECK(ctx);
   // norm3: dgamma += sum_n A2, dbeta += sum_n (A1 + dpool) ; norm4: dgamma += sum_n B2, dbeta += sum_n B1

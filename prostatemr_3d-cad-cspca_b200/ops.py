@@ -182,12 +182,12 @@ def se_gate_bwd_reduce(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, dr
 
 
 def se_gate_bwd_apply(ctx, dout, raw3, raw4, st3, st4, g3, b3, g4, b4, gate, drop, red, dpool, draw3, draw4,
-                      dg3, db3, dg4, db4):
+                      dg3, db3, dg4, db4, accumulate=False):
     n, v, c = _nvc(raw3)
     check(lib().m1_se_gate_bwd_apply(ctx.handle, ptr(dout), ptr(raw3), ptr(raw4), ptr(st3), ptr(st4), ptr(g3),
                                      ptr(b3), ptr(g4), ptr(b4), ptr(gate), C.byref(drop), ptr(red), ptr(dpool),
-                                     dtype_code(raw3), n, v, c, ptr(draw3), ptr(draw4), ptr(dg3), ptr(db3),
-                                     ptr(dg4), ptr(db4), current_stream()))
+                                     dtype_code(raw3), n, v, c, ptr(draw3), ptr(draw4), 1 if accumulate else 0, ptr(dg3),
+                                     ptr(db3), ptr(dg4), ptr(db4), current_stream()))
 
 
 # ---- K6 attention gate -----------------------------------------------------------------------
