@@ -407,27 +407,67 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, int n_re
     st_f<TW>(out + i, pack_value(a, n_real, n_total, k_total, i));
 }
 
-// ---- all packs of a model in ONE launch (the re-pack after every optimizer step: ~350 packs) ----------------
+// ---- all packs of a model in ONE launch (the re-pack after every optimizer step: ~350 packs, ~128 M elements)
+// A block re-packs one (tap, 32 produced channels, 64 K positions) tile through shared memory: the fp32 master
+// weights are read along whichever of their two inner dimensions is contiguous (Conv3D kernels: produced channel
+// fastest -> a transpose; Conv3DTranspose kernels and the data-gradient packs: reduction index fastest), the 16-bit
+// pack is written K-contiguous, 128 bytes per warp row. All index arithmetic per tile, none per element.
 struct PackJob {
   PackArgs a;
   int n_real, n_total, k_total, f16;
-  int64_t total;
+  int taps;
   void* out;
 };
-constexpr int kPackItems = 8;     // elements per thread
+constexpr int kPackK = 64, kPackN = 32;
 
-__global__ void __launch_bounds__(256) pack_batched_kernel(const PackJob* __restrict__ jobs,
-                                                           const int* __restrict__ block_job,
-                                                           const int64_t* __restrict__ block_first) {
+__device__ __forceinline__ float pack_value_at(const PackArgs& a, int tap, int r, int n) {
+  int j = 0;
+  while (j + 1 < a.nout && n >= a.out_start[j + 1]) ++j;
+  n -= a.out_start[j];
+  if (a.w_by_src) {
+    int s = 0;
+    while (s + 1 < a.nsrc && r >= a.src_start[s + 1]) ++s;
+    r -= a.src_start[s];
+    return __ldg(a.w[j * a.nsrc + s] + (tap * a.st[s] + r * a.sr[s] + n * a.so[s]));
+  }
+  return __ldg(a.w[j] + (tap * a.st[j] + r * a.sr[j] + n * a.so[j]));
+}
+
+__global__ void __launch_bounds__(256) pack_tiled_kernel(const PackJob* __restrict__ jobs,
+                                                         const int* __restrict__ block_job,
+                                                         const int* __restrict__ block_tile) {
+  __shared__ float tile[kPackN][kPackK + 1];
   const PackJob& J = jobs[block_job[blockIdx.x]];
-  const int64_t base = block_first[blockIdx.x] + threadIdx.x;
+  int t = block_tile[blockIdx.x];
+  const int kt = (J.k_total + kPackK - 1) / kPackK, nt = (J.n_total + kPackN - 1) / kPackN;
+  const int k0 = (t % kt) * kPackK;
+  t /= kt;
+  const int n0 = (t % nt) * kPackN;
+  const int tap = t / nt;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (J.a.so[0] == 1) {          // produced channel contiguous in the master weights: a warp reads 32 n of one k
+    for (int kk = ty; kk < kPackK; kk += 8) {
+      const int k = k0 + kk, n = n0 + tx;
+      tile[tx][kk] = (k < J.k_total && n < J.n_real) ? pack_value_at(J.a, tap, k, n) : 0.f;
+    }
+  } else {                       // reduction index contiguous: a warp reads 2 x 32 k of one n
+    for (int nn = ty; nn < kPackN; nn += 8) {
+      const int n = n0 + nn;
 #pragma unroll
-  for (int it = 0; it < kPackItems; ++it) {
-    const int64_t i = base + (int64_t)it * 256;
-    if (i >= J.total) break;
-    const float v = pack_value(J.a, J.n_real, J.n_total, J.k_total, i);
-    if (J.f16) st_f<__half>(reinterpret_cast<__half*>(J.out) + i, v);
-    else st_f<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(J.out) + i, v);
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + tx + 32 * h;
+        tile[nn][tx + 32 * h] = (k < J.k_total && n < J.n_real) ? pack_value_at(J.a, tap, k, n) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  for (int nn = ty; nn < kPackN; nn += 8) {
+    const int n = n0 + nn, k = k0 + 2 * tx;
+    if (n >= J.n_total || k >= J.k_total) continue;         // k_total is a multiple of 16: pairs never straddle
+    const int64_t i = ((int64_t)tap * J.n_total + n) * J.k_total + k;
+    const float v0 = tile[nn][2 * tx], v1 = tile[nn][2 * tx + 1];
+    const uint32_t pk = J.f16 ? pack2<__half>(v0, v1) : pack2<__nv_bfloat16>(v0, v1);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(J.out) + i) = pk;
   }
 }
 
@@ -592,7 +632,7 @@ extern "C" int m1_conv3d_pack_weights(m1_ctx* ctx, const m1_conv_desc* d, const 
 struct m1_pack_plan {
   PackJob* jobs;
   int* block_job;
-  int64_t* block_first;
+  int* block_tile;
   int nblocks;
 };
 
@@ -600,39 +640,39 @@ extern "C" int m1_pack_plan_create(m1_ctx* ctx, int njobs, const m1_conv_desc* c
                                    const float* const* const* ws, void* const* packed, m1_pack_plan** out) {
   M1_CHECK(ctx && out && njobs > 0, "m1_pack_plan_create: bad arguments");
   std::vector<PackJob> jobs((size_t)njobs);
-  std::vector<int> bj;
-  std::vector<int64_t> bf;
+  std::vector<int> bj, bt;
   for (int q = 0; q < njobs; ++q) {
     Plan pl;
     M1_CHECK(make_plan(descs[q], &pl), "m1_pack_plan_create: job %d is not a tcgen05 launch", q);
     PackJob& J = jobs[(size_t)q];
     fill_pack_args(descs[q], ws[q], &J.a);
-    const int taps = descs[q]->kernel[0] * descs[q]->kernel[1] * descs[q]->kernel[2];
+    J.taps = descs[q]->kernel[0] * descs[q]->kernel[1] * descs[q]->kernel[2];
     J.n_real = pl.n_real; J.n_total = pl.n_total; J.k_total = pl.k_total;
     J.f16 = m1_conv_w_dtype(descs[q]) == M1_F16;
-    J.total = (int64_t)taps * pl.n_total * pl.k_total;
     J.out = packed[q];
-    for (int64_t first = 0; first < J.total; first += 256 * kPackItems) {
+    M1_CHECK(((uintptr_t)packed[q] & 3) == 0, "m1_pack_plan_create: pack %d not 4-byte aligned", q);
+    const int tiles = J.taps * ((pl.n_total + kPackN - 1) / kPackN) * ((pl.k_total + kPackK - 1) / kPackK);
+    for (int t = 0; t < tiles; ++t) {
       bj.push_back(q);
-      bf.push_back(first);
+      bt.push_back(t);
     }
   }
   m1_pack_plan* p = new m1_pack_plan();
   p->nblocks = (int)bj.size();
   M1_CUDA(cudaMalloc(&p->jobs, jobs.size() * sizeof(PackJob)));
   M1_CUDA(cudaMalloc(&p->block_job, bj.size() * sizeof(int)));
-  M1_CUDA(cudaMalloc(&p->block_first, bf.size() * sizeof(int64_t)));
+  M1_CUDA(cudaMalloc(&p->block_tile, bt.size() * sizeof(int)));
   M1_CUDA(cudaMemcpy(p->jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
   M1_CUDA(cudaMemcpy(p->block_job, bj.data(), bj.size() * sizeof(int), cudaMemcpyHostToDevice));
-  M1_CUDA(cudaMemcpy(p->block_first, bf.data(), bf.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  M1_CUDA(cudaMemcpy(p->block_tile, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice));
   *out = p;
   return 0;
 }
 
 extern "C" int m1_pack_plan_run(m1_ctx* ctx, const m1_pack_plan* plan, void* stream) {
   M1_CHECK(ctx && plan, "m1_pack_plan_run: NULL argument");
-  pack_batched_kernel<<<(unsigned)plan->nblocks, 256, 0, (cudaStream_t)stream>>>(plan->jobs, plan->block_job,
-                                                                                 plan->block_first);
+  pack_tiled_kernel<<<(unsigned)plan->nblocks, 256, 0, (cudaStream_t)stream>>>(plan->jobs, plan->block_job,
+                                                                                plan->block_tile);
   M1_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -641,7 +681,7 @@ extern "C" int m1_pack_plan_destroy(m1_pack_plan* plan) {
   if (!plan) return 0;
   cudaFree(plan->jobs);
   cudaFree(plan->block_job);
-  cudaFree(plan->block_first);
+  cudaFree(plan->block_tile);
   delete plan;
   return 0;
 }

@@ -101,6 +101,13 @@ class PhiloxNoise:
         return out
 
 
+class SETrunk:
+    """dropout-independent part of an SE tail (Engine.se_trunk): the two raw conv outputs, their statistics, the
+    squeeze / excite results and the parameter views"""
+    __slots__ = ("raw3", "raw4", "name", "c", "cr", "g3", "b3", "g4", "b4", "w6", "b6", "w7", "b7",
+                 "st3", "st4", "pool", "hidden", "gate")
+
+
 class LazyHead:
     """A final 1x1x1 logits convolution that has not been launched yet: the loss kernel fuses it (K8 reads
     the decoder features directly and emits d(features), dW, db); `materialize` is the unfused fallback."""
@@ -150,6 +157,11 @@ class Engine:
         self.conv_flops = 0        # algorithmic MACs*2 of the convolutions launched (forward only)
         self.bwd_flops = 0         # ... of the data-gradient and weight-gradient launches actually executed
         self.trace_log = []        # TRACE mode: one record per convolution launch (tools/list_launches.py, tests)
+        import os
+        # passes that share their input compute the dropout-free head of the encoder once (M1_SHARE_TRUNK=0: as the
+        # reference graph, every pass on its own - same results up to the rounding order of the summed gradients)
+        self.share_trunk = os.environ.get("M1_SHARE_TRUNK", "1") != "0"
+        self.shared = {}
 
     # ---- helpers -----------------------------------------------------------------------------
     def new(self, shape, dtype=None, zero=False):
@@ -217,6 +229,7 @@ class Engine:
         self.conv_flops = 0
         self.bwd_flops = 0
         self.param_uses = {}
+        self.shared = {}           # per-step cache of sub-graphs shared between passes (M1Core: stem + serse1 trunk)
 
     def _rec(self, fn, names):
         """record a backward closure and the parameters whose gradients it contributes to"""
@@ -558,37 +571,56 @@ class Engine:
     # ---- K5 SE tail: norm3/norm4 + squeeze + excite + gate*residual + lrelu + dropout -----------
     def se_tail(self, raw3, raw4, name, reduction, drop):
         """drop: None or (pass_name, site, rate)."""
+        return self.se_gate(self.se_trunk(raw3, raw4, name, reduction), drop)
+
+    def se_trunk(self, raw3, raw4, name, reduction):
+        """Everything of the SE tail that does not depend on the dropout draw: statistics of raw3 / raw4 (norm3,
+        norm4), squeeze, excite. Several `se_gate` calls may follow on one trunk (passes of the probabilistic model
+        that share their input differ only in the dropout mask applied to the block output)."""
         c = raw3.c
         cr = c // reduction
-        g3 = self.p(name + "/norm3/gamma", (c,), "gamma")
-        b3 = self.p(name + "/norm3/beta", (c,), "beta")
-        g4 = self.p(name + "/norm4/gamma", (c,), "gamma")
-        b4 = self.p(name + "/norm4/beta", (c,), "beta")
-        w6 = self.p(name + "/conv6/kernel", (1, 1, 1, c, cr), "se_kernel")
-        b6 = self.p(name + "/conv6/bias", (cr,), "se_bias")
-        w7 = self.p(name + "/conv7/kernel", (1, 1, 1, cr, c), "se_kernel")
-        b7 = self.p(name + "/conv7/bias", (c,), "se_bias")
+        tr = SETrunk()
+        tr.raw3, tr.raw4, tr.name, tr.c, tr.cr = raw3, raw4, name, c, cr
+        tr.g3 = self.p(name + "/norm3/gamma", (c,), "gamma")
+        tr.b3 = self.p(name + "/norm3/beta", (c,), "beta")
+        tr.g4 = self.p(name + "/norm4/gamma", (c,), "gamma")
+        tr.b4 = self.p(name + "/norm4/beta", (c,), "beta")
+        tr.w6 = self.p(name + "/conv6/kernel", (1, 1, 1, c, cr), "se_kernel")
+        tr.b6 = self.p(name + "/conv6/bias", (cr,), "se_bias")
+        tr.w7 = self.p(name + "/conv7/kernel", (1, 1, 1, cr, c), "se_kernel")
+        tr.b7 = self.p(name + "/conv7/bias", (c,), "se_bias")
+        if self.tracing:
+            return tr
+        n = raw3.shape[0]
+        f32 = torch.float32
+        tr.st3, tr.st4 = self.new((n, c, 2), f32), self.new((n, c, 2), f32)
+        tr.pool, tr.hidden, tr.gate = self.new((n, c), f32), self.new((n, cr), f32), self.new((n, c), f32)
+
+        def fwd():
+            ops.inorm_stats(self.ctx, raw3.t, tr.st3, IN_EPS)
+            ops.inorm_stats(self.ctx, raw4.t, tr.st4, IN_EPS)
+            ops.se_excite_fwd(self.ctx, tr.pool, tr.w6, tr.b6, tr.w7, tr.b7, tr.hidden, tr.gate, tr.st3, tr.g3,
+                              tr.b3)                                                   # squeeze folded in
+        nel, es = raw3.t.numel(), raw3.t.element_size()
+        self._timed("se_tail_fwd", 0, fwd, nbytes=2 * nel * es)          # the two statistics reads
+        return tr
+
+    def se_gate(self, tr, drop):
+        """out = dropout(lrelu(norm3(raw3) * gate * norm4(raw4))) on a trunk; drop: None or (pass_name, site, rate)."""
+        raw3, raw4, name = tr.raw3, tr.raw4, tr.name
         out = Act(raw3.shape, raw3.dtype, self.new(raw3.shape, raw3.dtype))
         if self.tracing:
             return out
-        n = raw3.shape[0]
+        n, c = raw3.shape[0], tr.c
         f32 = torch.float32
-        st3, st4 = self.new((n, c, 2), f32), self.new((n, c, 2), f32)
-        pool, hidden, gate = self.new((n, c), f32), self.new((n, cr), f32), self.new((n, c), f32)
         self.new_twin(out)
         if drop is not None and drop[2] > 0.0:
             dr, keep_alive = self.noise.dropout(self, drop[0], drop[1], raw3.shape, drop[2])
         else:
             dr, keep_alive = ops.make_dropout(0.0), None
-
-        def fwd():
-            ops.inorm_stats(self.ctx, raw3.t, st3, IN_EPS)
-            ops.inorm_stats(self.ctx, raw4.t, st4, IN_EPS)
-            ops.se_excite_fwd(self.ctx, pool, w6, b6, w7, b7, hidden, gate, st3, g3, b3)     # squeeze folded in
-            ops.se_gate_fwd(self.ctx, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, out.t, out.tw)
         nel, es = raw3.t.numel(), raw3.t.element_size()
-        # algorithmic passes (SURVEY 8(d)): the two statistics reads + gate pass (2 reads, 1 write)
-        self._timed("se_tail_fwd", 0, fwd, nbytes=5 * nel * es)
+        self._timed("se_tail_fwd", 0, nbytes=3 * nel * es, fn=lambda: ops.se_gate_fwd(          # 2 reads, 1 write
+            self.ctx, raw3.t, raw4.t, tr.st3, tr.st4, tr.g3, tr.b3, tr.g4, tr.b4, tr.gate, dr, out.t, out.tw))
 
         def bwd():
             if out.g is None:
@@ -596,21 +628,25 @@ class Engine:
             _ = keep_alive
             red = self.new((n, c, 5), f32)
             dgate, dpool = self.new((n, c), f32), self.new((n, c), f32)
-            assert raw3.g is None and raw4.g is None
-            raw3.g = self.new_grad(raw3)
-            raw4.g = self.new_grad(raw4)
+            # a second gate on the same trunk adds to the gradients the first one left in raw3.g / raw4.g
+            acc = raw3.g is not None
+            assert acc == (raw4.g is not None)
+            if not acc:
+                raw3.g = self.new_grad(raw3)
+                raw4.g = self.new_grad(raw4)
 
             def run():
-                ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
-                                       dgate)
-                ops.se_excite_bwd(self.ctx, dgate, pool, hidden, gate, w6, w7, dpool,
+                ops.se_gate_bwd_reduce(self.ctx, out.g, raw3.t, raw4.t, tr.st3, tr.st4, tr.g3, tr.b3, tr.g4, tr.b4,
+                                       tr.gate, dr, red, dgate)
+                ops.se_excite_bwd(self.ctx, dgate, tr.pool, tr.hidden, tr.gate, tr.w6, tr.w7, dpool,
                                   self.pg(name + "/conv6/kernel"), self.pg(name + "/conv6/bias"),
                                   self.pg(name + "/conv7/kernel"), self.pg(name + "/conv7/bias"), red,
                                   self.pg(name + "/norm3/gamma"), self.pg(name + "/norm3/beta"),
                                   self.pg(name + "/norm4/gamma"), self.pg(name + "/norm4/beta"))
-                ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, st3, st4, g3, b3, g4, b4, gate, dr, red,
-                                      dpool, raw3.g, raw4.g, None, None, None, None)
-            self._timed("se_tail_bwd", 0, run, nbytes=8 * nel * es)       # 2 x 3 reads + 2 writes
+                ops.se_gate_bwd_apply(self.ctx, out.g, raw3.t, raw4.t, tr.st3, tr.st4, tr.g3, tr.b3, tr.g4, tr.b4,
+                                      tr.gate, dr, red, dpool, raw3.g, raw4.g, None, None, None, None,
+                                      accumulate=acc)
+            self._timed("se_tail_bwd", 0, run, nbytes=(10 if acc else 8) * nel * es)   # 2 x 3 reads + 2 writes (+ 2)
             out.g = None
         if self.record:
             self._rec(bwd, [name + sfx for sfx in ("/norm3/gamma", "/norm3/beta", "/norm4/gamma", "/norm4/beta",

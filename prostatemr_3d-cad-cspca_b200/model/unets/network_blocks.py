@@ -19,6 +19,10 @@ class SEResNetBottleNeck:
         self.reduction, self.name = reduction, name
 
     def __call__(self, eng, srcs, drop=None):
+        return eng.se_gate(self.trunk(eng, srcs), drop)
+
+    def trunk(self, eng, srcs):
+        """the block up to (not including) the gate kernel: everything that does not depend on the dropout draw"""
         f, n = self.filters, self.name
         cin = sum(a.lc for a in srcs)
         if cin == f:
@@ -32,7 +36,7 @@ class SEResNetBottleNeck:
         raw2, = eng.conv([a], [(n + "/conv2", f // 4)], (3, 3, 3), pad_out=[True], feeds_norm=True)
         b = eng.inorm_act(raw2, n + "/norm2", LRELU)
         raw3, = eng.conv([b], [(n + "/conv3", f)], (1, 1, 1), feeds_norm=True)
-        return eng.se_tail(raw3, raw4, n, self.reduction, drop)
+        return eng.se_trunk(raw3, raw4, n, self.reduction)
 
 
 class GridAttentionBlock3D:

@@ -85,10 +85,20 @@ class M1Core:
         need = lambda lvl: (not partial) or (3 - lvl) < last_lat  # noqa: E731 - is uconv{lvl}_ needed?
         out = {}
         # stem (R:networks.py:574-576)
-        raw, = eng.conv(inputs, [(n('conve0'), F[0])], K[0], S[0], feeds_norm=True)
-        x = eng.inorm_act(raw, n('norme0'), LRELU)
+        # The stem and the first encoder block up to its dropout see nothing stochastic: two passes of one network
+        # over the SAME input tensors (q_sample / q_mean, p_z_q / p_z_qmean) compute them once and differ from the
+        # gate kernel of serse1 on (its dropout mask); their gradients meet again in raw3.g / raw4.g / x.g.
+        key = (net, 'stem+serse1') + tuple(id(a) for a in inputs)
+        hit = eng.shared.get(key) if eng.share_trunk else None
+        if hit is None:
+            raw, = eng.conv(inputs, [(n('conve0'), F[0])], K[0], S[0], feeds_norm=True)
+            x = eng.inorm_act(raw, n('norme0'), LRELU)
+            trunk1 = self.serse[1].trunk(eng, [x])
+            eng.shared[key] = (x, trunk1, inputs)
+        else:
+            x, trunk1, _ = hit
         # encoder (R:networks.py:579-582); the dropouts are fused into the SE gate kernel
-        conv1 = self.serse[1](eng, [x], drop('drope1'))
+        conv1 = eng.se_gate(trunk1, drop('drope1'))
         conv2 = self.serse[2](eng, [conv1], drop('drope2'))
         conv3 = self.serse[3](eng, [conv2], drop('drope3'))
         convm = self.serse[4](eng, [conv3], drop('drope4'))

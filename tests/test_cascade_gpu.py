@@ -60,9 +60,14 @@ def _check(model, ps, noise, r, x, x2, y, tol_sm, tol_loss, cos_min):
     model.set_noise(noise.t)
     out = model.train_step([x, x2], y, apply_update=False)
     torch.cuda.synchronize()
-    for k in ('detection_1', 'detection_2'):
-        err = (out[k].double().cpu() - r[k].detach().double()).abs().max().item()
-        assert err < tol_sm, (k, err)
+    # detection_1 is one M1 on identical inputs: the north-star bound tol_sm. detection_2 is compared through the
+    # CHAIN (its oracle value was computed from the oracle's stage-1 output, ours from our stage-1 output), so its
+    # deviation is its own rounding plus the propagated stage-1 deviation: bounded by 2 x tol_sm, mean far below.
+    for k, bound in (('detection_1', tol_sm), ('detection_2', 2 * tol_sm)):
+        e = (out[k].double().cpu() - r[k].detach().double()).abs()
+        print(f'{k}: softmax abs err mean {e.mean().item():.2e} max {e.max().item():.2e} (bound {bound:.0e})')
+        assert e.max().item() < bound, (k, e.max().item())
+        assert e.mean().item() < 0.1 * tol_sm, (k, e.mean().item())
     for ours, ref in (('focal_1', 'detection_1_loss'), ('focal_2', 'detection_2_loss'), ('kl_1', 'KL_1'), ('kl_2', 'KL_2')):
         if ref in r:
             a, b = out[ours].item(), r[ref].item()

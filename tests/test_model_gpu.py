@@ -123,6 +123,34 @@ def test_deterministic_train_step_fp32(ctx, dense, ds):
     _compare(model, ps, noise, r, x, y, tol_sm=1e-4, tol_loss=1e-3, cos_min=0.9999, per_tensor_cos=0.999)
 
 
+@pytest.mark.parametrize("precision,arch", [('fp32', TINY), ('fp16', MID)])
+def test_shared_trunk_equals_per_pass_graph(ctx, precision, arch):
+    """The stem and serse1 up to its dropout are computed once for the two passes of a network that read the same
+    input (Engine.share_trunk). Against the reference graph (every pass on its own, share_trunk=False) the forward
+    values are BIT-identical (same kernels on the same operands) and the gradients agree up to the rounding order
+    of the sums (one backward through the trunk on the summed gradient instead of two backward passes)."""
+    outs, grads, launches = [], [], []
+    for share in (True, False):
+        model, cfg, x, y = _build(arch, (8, 32, 32), 2, precision, True, True, True)
+        model.eng.share_trunk = share
+        model.set_noise(seed=7)
+        before = ctx.launch_count()
+        out = model.train_step(x, y, apply_update=False)
+        torch.cuda.synchronize()
+        launches.append(ctx.launch_count() - before)
+        outs.append({k: v.clone() for k, v in out.items()})
+        grads.append(model.gradients())
+    assert launches[0] < launches[1]
+    assert torch.equal(outs[0]['detection'], outs[1]['detection'])
+    assert outs[0]['focal'].item() == outs[1]['focal'].item() and outs[0]['kl'].item() == outs[1]['kl'].item()
+    a = torch.cat([grads[0][n].double().flatten() for n in grads[0]])
+    b = torch.cat([grads[1][n].double().flatten() for n in grads[0]])
+    cos = (a @ b).item() / (a.norm().item() * b.norm().item())
+    rel = (a - b).norm().item() / b.norm().item()
+    print(f'shared vs per-pass trunk ({precision}): grad cosine {cos:.7f} rel-l2 {rel:.2e}')
+    assert cos > (0.999999 if precision == 'fp32' else 0.999) and rel < (1e-4 if precision == 'fp32' else 3e-2)
+
+
 def test_probabilistic_train_step_bf16_tcgen05(ctx):
     """bf16 activations, tcgen05 tensor-core convolutions wherever the shape allows.
 

@@ -19,14 +19,16 @@ README_CFG = dict(filters=(32, 64, 128, 256, 512),
                   se_reduction=(8, 8, 8, 8, 8), att_sub_samp=((1, 1, 1),) * 4)
 
 
-def trace(batch=8, dims=(20, 160, 160), dead=False):
+def trace(batch=8, dims=(20, 160, 160), dead=False, share=True):
     """list of launch records (Engine.trace_log) of one training step of the cfg-2 model. dead=True also lists the
     prior net's sersd0 + logits, which the reference builds but whose output only feeds an empty slice (Q3): the
-    product does not execute them (SURVEY 8(d) counts them: 837.65 GMAC forward; executed: 806.58 GMAC)."""
+    product does not execute them (SURVEY 8(d) counts them: 837.65 GMAC forward; live graph: 806.58 GMAC; executed
+    with the stem + serse1 trunk shared between the passes that read the same input: 797.61 GMAC)."""
     m = unets.networks.M1(dims, 4, 2, dropout_mode='monte-carlo', dense_skip=True, deep_supervision=True,
                           probabilistic=True, prob_latent_dims=(3, 2, 1, 0), summary=False, build=False,
                           **README_CFG)
     eng = Engine(ParamTable(), 'bf16', device=None)
+    eng.share_trunk = share      # False: every pass computes its own stem + serse1 (the reference graph)
     m._graph(eng, batch=batch, training=True, trace=True, dead=dead)
     return eng.trace_log
 
