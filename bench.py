@@ -437,7 +437,8 @@ def run_ours(args):
                 else "fallback 1.4 PFLOP/s sustained / 6.65 TB/s (B200_PROFILING.md)")
     breakdown = {k: {"launches": v[2] // args.steps, "ms_per_step": v[1] / args.steps,
                      "tflops": (v[0] / 1e12) / (v[1] / 1e3) if v[1] > 0 and v[0] > 0 else None,
-                     "gbs": (v[3] / 1e9) / (v[1] / 1e3) if v[1] > 0 and v[3] > 0 else None} for k, v in cats.items()}
+                     "gbs": (v[3] / 1e9) / (v[1] / 1e3) if v[1] > 0 and v[3] > 0 and not k.startswith("conv_")
+                     else None} for k, v in cats.items()}
     total_ms = sum(v[1] for v in cats.values())
     traffic = {}
     try:      # per-launch DRAM bytes of the dominant kernels, from the committed ncu --set full capture
@@ -454,6 +455,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "traffic": tr.get("dram_bytes_per_launch"),
                     "traffic_note": tr.get("note"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch_avg": cats[dom][3] / n if cats[dom][3] else None,
                     "share_of_step": t_ms / total_ms, "flop_per_launch_avg": fl / n,
                     "flops": "algorithmic: reference channel counts, only the launches actually executed",
                     "timed_with": "CUDA events around every launch family in an eager re-run of the same %d steps "
@@ -463,7 +465,7 @@ def run_ours(args):
                     "conv_path_tflops_whole_step": (flops_step * args.steps / 1e12) / (ms / 1e3),
                     "conv_path_frac_whole_step": (flops_step * args.steps / 1e12) / (ms / 1e3) / peak_tf,
                     "breakdown": breakdown}
-        bw_cats = {k: v for k, v in cats.items() if v[3] > 0}
+        bw_cats = {k: v for k, v in cats.items() if v[3] > 0 and not k.startswith("conv_")}
         if bw_cats:
             bdom = max(bw_cats, key=lambda k: bw_cats[k][1])
             _, t_b, n_b, nb = cats[bdom]

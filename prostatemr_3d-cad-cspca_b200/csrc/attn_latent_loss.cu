@@ -5,6 +5,7 @@
 //   K8  softmax + Focal.FL / Focal.loss          R:networks.py:388-390,751-755; losses.py:32-49
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -294,6 +295,200 @@ __global__ void __launch_bounds__(TB) attn_bwd_psi_vec_kernel(
     dsum = warp_sum(dsum);
     if (lane == 0) atomicAdd(&sdw[F], dsum);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F; i += TB) atomicAdd(dw_psi + i, sdw[i]);
+  if (threadIdx.x == 0) atomicAdd(db_psi, sdw[F]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6, fused variants for gates without sub-sampling (att_sub_samp = (1,1,1): theta lives on x's grid - every gate of
+// the benchmarked configuration). ONE pass per direction instead of two kernels each:
+//   forward   reads theta, x (+ the 128-4096 x smaller phi), writes y (+ twin) and psi
+//   backward  reads dy, x, theta (+ dx when accumulating), writes dx and dtheta, adds dphi / dw_psi / db_psi
+// grid = (chunks of the H*W plane, batch * D): all index arithmetic is 32-bit and per plane (the old kernels spent
+// more instructions on 64-bit div/mod chains than on the data); UNR voxels per thread are loaded before any is used;
+// the psi-weight gradient lives in registers for the whole block and is folded once at its end.
+// ---------------------------------------------------------------------------------------------
+struct AttnGeo {
+  int D, H, W, Dg, Hg, Wg, sd, sh, sw;
+};
+// 8 consecutive elements as loaded (unconverted): the UNR voxels of a thread wait in 4 registers per tensor, not 8
+template <typename T> struct Raw8 {
+  uint32_t w[sizeof(T) * 2];
+  __device__ __forceinline__ void load(const T* p) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    if constexpr (sizeof(T) == 4) {
+      const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
+      w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = cvt2<T>(w[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+  }
+};
+template <int G> struct AttnUnr { static constexpr int v = G <= 8 ? 4 : (G == 16 ? 2 : 1); };
+
+template <typename T, int G>
+__global__ void __launch_bounds__(TB, 2) attn_fwd_fused_kernel(const T* __restrict__ theta, const T* __restrict__ phi,
+                                                           const float* __restrict__ w_psi,
+                                                           const float* __restrict__ b_psi, const T* __restrict__ x,
+                                                           AttnGeo g, int nchunks, float* __restrict__ psi,
+                                                           T* __restrict__ y, __nv_bfloat16* __restrict__ y2) {
+  constexpr int F = 8 * G, VPI = TB / G, UNR = AttnUnr<G>::v;
+  const int lg = threadIdx.x % G, vs = threadIdx.x / G;
+  const int slab = blockIdx.y, z = slab % g.D, n = slab / g.D;
+  const int HW = g.H * g.W;
+  const int64_t vbase = (int64_t)slab * HW;
+  const int gslab = (n * g.Dg + min(z / g.sd, g.Dg - 1)) * g.Hg;
+  float w8[8];
+  load8<float>(w_psi + lg * 8, w8);
+  const float bias = b_psi[0];
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int hw0 = chunk * (VPI * UNR) + vs;
+    Raw8<T> rt[UNR], rx[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int hw = hw0 + u * VPI;
+      if (hw < HW) {
+        rt[u].load(theta + (vbase + hw) * F + lg * 8);
+        rx[u].load(x + (vbase + hw) * F + lg * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int hw = hw0 + u * VPI;
+      const bool ok = hw < HW;
+      float s = 0.f;
+      if (ok) {
+        const int yy = hw / g.W, xx = hw - yy * g.W;
+        const int64_t gv = (int64_t)(gslab + min(yy / g.sh, g.Hg - 1)) * g.Wg + min(xx / g.sw, g.Wg - 1);
+        float p8[8], t8[8];
+        load8<T>(phi + gv * F + lg * 8, p8);
+        rt[u].get(t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(lrelu(t8[i] + p8[i], M1_LRELU_SLOPE), w8[i], s);
+      }
+      s = group_sum(s, G);
+      if (ok) {
+        const float p = 1.f / (1.f + __expf(-(s + bias)));
+        float o[8];
+        rx[u].get(o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= p;
+        store8<T>(y + (vbase + hw) * F + lg * 8, o);
+        if (y2) store8<__nv_bfloat16>(y2 + (vbase + hw) * F + lg * 8, o);
+        if (lg == 0) psi[vbase + hw] = p;
+      }
+    }
+  }
+}
+
+template <typename T, typename TG, int G>
+__global__ void __launch_bounds__(TB, 2) attn_bwd_fused_kernel(const TG* __restrict__ dy, const T* __restrict__ theta,
+                                                           const T* __restrict__ phi, const float* __restrict__ w_psi,
+                                                           const float* __restrict__ psi, const T* __restrict__ x,
+                                                           AttnGeo g, int nchunks, TG* __restrict__ dx, int acc_dx,
+                                                           TG* __restrict__ dtheta, float* __restrict__ dphi,
+                                                           float* __restrict__ dw_psi, float* __restrict__ db_psi) {
+  constexpr int F = 8 * G, VPI = TB / G, UNR = AttnUnr<G>::v;
+  __shared__ float sdw[F + 1];
+  for (int i = threadIdx.x; i <= F; i += TB) sdw[i] = 0.f;
+  __syncthreads();
+  const int lg = threadIdx.x % G, vs = threadIdx.x / G, lane = threadIdx.x & 31;
+  const int slab = blockIdx.y, z = slab % g.D, n = slab / g.D;
+  const int HW = g.H * g.W;
+  const int64_t vbase = (int64_t)slab * HW;
+  const int gslab = (n * g.Dg + min(z / g.sd, g.Dg - 1)) * g.Hg;
+  float w8[8], dwp[8], dbs = 0.f;
+  load8<float>(w_psi + lg * 8, w8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dwp[i] = 0.f;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int hw0 = chunk * (VPI * UNR) + vs;
+    Raw8<TG> rd[UNR];
+    Raw8<T> rx[UNR], rt[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int hw = hw0 + u * VPI;
+      if (hw < HW) {
+        const int64_t e = (vbase + hw) * F + lg * 8;
+        rd[u].load(dy + e);
+        rx[u].load(x + e);
+        rt[u].load(theta + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int hw = hw0 + u * VPI;
+      const bool ok = hw < HW;
+      const int64_t e = (vbase + hw) * F + lg * 8;
+      float dpsi = 0.f, p = 0.f, d8[8];
+      int64_t gv = -1;
+      if (ok) {
+        float x8[8];
+        rd[u].get(d8);
+        rx[u].get(x8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dpsi = fmaf(d8[i], x8[i], dpsi);
+        p = psi[vbase + hw];
+        const int yy = hw / g.W, xx = hw - yy * g.W;
+        gv = (int64_t)(gslab + min(yy / g.sh, g.Hg - 1)) * g.Wg + min(xx / g.sw, g.Wg - 1);
+      }
+      dpsi = group_sum(dpsi, G);
+      const float ds = dpsi * p * (1.f - p);
+      float dth[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dth[i] = 0.f;
+      if (ok) {
+        float o[8], p8[8], t8[8];
+        if (acc_dx) load8<TG>(dx + e, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = acc_dx ? fmaf(d8[i], p, o[i]) : d8[i] * p;
+        store8<TG>(dx + e, o);
+        load8<T>(phi + gv * F + lg * 8, p8);
+        rt[u].get(t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pre = t8[i] + p8[i];
+          dth[i] = ds * w8[i] * (pre > 0.f ? 1.f : M1_LRELU_SLOPE);
+          dwp[i] = fmaf(ds, lrelu(pre, M1_LRELU_SLOPE), dwp[i]);
+        }
+        store8<TG>(dtheta + e, dth);
+        if (lg == 0) dbs += ds;
+      }
+      // phi gradient: the voxel groups of a warp usually sit below ONE gating voxel (the gating grid is 4-16 x
+      // coarser along w) - fold them with shuffles, one atomic per channel; otherwise one per voxel and channel
+      if constexpr (G < 32) {
+        const int64_t gv0 = __shfl_sync(0xffffffffu, gv, 0);
+        const bool same = __all_sync(0xffffffffu, gv == gv0);
+        if (same) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            for (int o = G; o < 32; o <<= 1) dth[i] += __shfl_xor_sync(0xffffffffu, dth[i], o);
+          if (lane < G && gv >= 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dphi + gv * F + lg * 8 + i, dth[i]);
+          }
+        } else if (ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(dphi + gv * F + lg * 8 + i, dth[i]);
+        }
+      } else if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dphi + gv * F + lg * 8 + i, dth[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&sdw[lg * 8 + i], dwp[i]);
+  if (lg == 0) atomicAdd(&sdw[F], dbs);
   __syncthreads();
   for (int i = threadIdx.x; i < F; i += TB) atomicAdd(dw_psi + i, sdw[i]);
   if (threadIdx.x == 0) atomicAdd(db_psi, sdw[F]);
@@ -712,6 +907,34 @@ inline unsigned nblocks(const m1_ctx* ctx, int64_t total, int per = TB) {
 }
 inline Grid3 g3(const int32_t* p) { return Grid3{p[0], p[1], p[2]}; }
 
+// ---- fused attention kernels: geometry, grid, lane-group dispatch
+inline bool attn_fused_on() {
+  static const int on = getenv("M1_ATTN_FUSED") ? atoi(getenv("M1_ATTN_FUSED")) : 1;
+  return on != 0;
+}
+inline AttnGeo attn_geo(const Grid3& t, const Grid3& g) {
+  return AttnGeo{t.d, t.h, t.w, g.d, g.h, g.w, t.d / g.d, t.h / g.h, t.w / g.w};
+}
+inline dim3 attn_fused_grid(const m1_ctx* ctx, const AttnGeo& geo, int batch, int G, int* nchunks) {
+  const int unr = G <= 8 ? 4 : (G == 16 ? 2 : 1);
+  const int per = (TB / G) * unr;                                 // voxels per block iteration
+  *nchunks = (geo.H * geo.W + per - 1) / per;
+  const int slabs = batch * geo.D;
+  const int gx = std::max(1, std::min(*nchunks, (ctx->num_sms * 16 + slabs - 1) / slabs));
+  return dim3((unsigned)gx, (unsigned)slabs);
+}
+#define M1_ATTN_G(G, LAUNCH)        \
+  do {                              \
+    switch (G) {                    \
+      case 1: LAUNCH(1); break;     \
+      case 2: LAUNCH(2); break;     \
+      case 4: LAUNCH(4); break;     \
+      case 8: LAUNCH(8); break;     \
+      case 16: LAUNCH(16); break;   \
+      default: LAUNCH(32); break;   \
+    }                               \
+  } while (0)
+
 }  // namespace
 
 extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, const float* w_psi,
@@ -728,6 +951,18 @@ extern "C" int m1_attn_fwd(m1_ctx* ctx, const void* theta, const void* phi, cons
   const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
   const int G = F / 8;
   const bool vec = F % 8 == 0 && Cx % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0;
+  if (vec && Cx == F && T3.d == X3.d && T3.h == X3.h && T3.w == X3.w && attn_fused_on()) {
+    const AttnGeo geo = attn_geo(T3, G3);
+    int nchunks;
+    const dim3 grid = attn_fused_grid(ctx, geo, batch, G, &nchunks);
+#define M1_ATTN_FWD(GG)                                                                                          \
+  M1_DISPATCH_T(dtype, T, (attn_fwd_fused_kernel<T, GG><<<grid, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, \
+                                                                            b_psi, (const T*)x, geo, nchunks, psi, (T*)y, y2)))
+    M1_ATTN_G(G, M1_ATTN_FWD);
+#undef M1_ATTN_FWD
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   if (vec) {
     const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
     M1_DISPATCH_T(dtype, T, (attn_psi_vec_kernel<T><<<pb, TB, 0, st>>>((const T*)theta, (const T*)phi, w_psi, b_psi, tv,
@@ -756,6 +991,19 @@ extern "C" int m1_attn_bwd(m1_ctx* ctx, const void* dy, const void* theta, const
   const int64_t total = (int64_t)batch * X3.d * X3.h * X3.w * Cx;
   const int G = F / 8;
   const bool vec = F % 8 == 0 && Cx == F && G >= 1 && G <= 32 && (G & (G - 1)) == 0;
+  if (vec && T3.d == X3.d && T3.h == X3.h && T3.w == X3.w && attn_fused_on()) {
+    const AttnGeo geo = attn_geo(T3, G3);
+    int nchunks;
+    const dim3 grid = attn_fused_grid(ctx, geo, batch, G, &nchunks);
+#define M1_ATTN_BWD(GG)                                                                                              \
+  M1_DISPATCH_VG(dtype, T, TG, (attn_bwd_fused_kernel<T, TG, GG><<<grid, TB, 0, st>>>(                                \
+                                  (const TG*)dy, (const T*)theta, (const T*)phi, w_psi, psi, (const T*)x, geo, nchunks, \
+                                  (TG*)dx, acc_dx, (TG*)dtheta, dphi, dw_psi, db_psi)))
+    M1_ATTN_G(G, M1_ATTN_BWD);
+#undef M1_ATTN_BWD
+    M1_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   if (vec) {
     const unsigned pb = nblocks(ctx, tv, TB / G), sb = nblocks(ctx, total / 8);
     const size_t sm = (F + 1) * sizeof(float);

@@ -294,9 +294,14 @@ class Engine:
                     var = self._tune_conv(d, list(src_t[i0:i1]), sub_w, list(out_t), packed)
                     self.tuned[tk] = var
                 d.tune[0] = var
+            # algorithmic bytes: every gathered and produced tensor once (+ the old contents of accumulating outputs)
+            nb = 0 if self.prof is None else (
+                sum(t.numel() * t.element_size() for t in src_t[i0:i1]) +
+                sum(t.numel() * t.element_size() * (2 if a else 1) for t, a in zip(out_t, a_flags)) +
+                sum(w.numel() * 2 for w in ([] if w_by_src else ws)))
             self._timed(cat + ("_tcgen05" if packed is not None else "_simt"), fl,
                         lambda: ops.conv3d(self.ctx, d, list(src_t[i0:i1]), sub_w, b, list(out_t), packed),
-                        label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)))
+                        label=(key, tuple(src_c[i0:i1]), tuple(out_c), tuple(out_dhw), tuple(k), tuple(s)), nbytes=nb)
             first = False
 
     def conv(self, srcs, layers, k, s=(1, 1, 1), transposed=False, out_dtype=None, pad_out=None, feeds_norm=False):
@@ -393,8 +398,10 @@ class Engine:
                 cfg = self._tune_wgrad(d, srcs_t, douts_t, dws)
                 self.tuned[key] = cfg
             d.tune[0], d.tune[1], d.tune[2], d.tune[3] = cfg
-        self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl,
-                    lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
+        nb = 0 if self.prof is None else (sum(t.numel() * t.element_size() for t in list(srcs_t) + list(douts_t)) +
+                                          sum(w.numel() * 8 for w in dws))
+        self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl, nbytes=nb,
+                    fn=lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
                            tuple(srcs_t[0].shape[1:4])))
 
