@@ -319,6 +319,35 @@ int m1_adam_amsgrad_dev(m1_ctx* ctx, float* w, const float* g, float* m, float* 
                         int64_t n, const float* lr_t_dev, float beta1, float beta2, float eps, float l2,
                         float gscale, float* l2_sq_out, int amsgrad, void* stream);
 
+/* ---- K10: train-time augmentations on the device ------------------------------------------------
+ * tf2.5/scripts/model/augmentations.py:36-378 (`augment_tensors`: zoom_4D_tensor, axial_4D_hflip, rotate_4D_tensor,
+ * translate_4D_tensor, channel_shift_4D_tensor, gamma_shift_4D_tensor, sim_poor_scan_4D_tensor,
+ * gaussian_noise_4D_tensor), which the reference maps over the tf.data pipeline on the host CPUs
+ * (train_model.py:181). One launch per transform over a whole batch (B, D, H, W, C) fp32; every sample has its own
+ * m1_aug_plan (device array of `batch` plans, drawn by the host: model/augmentations.py draw_plans). `in` and `out`
+ * must not alias; samples whose transform is switched off are copied. D plays the batch role of TensorFlow's 4-D
+ * image ops. M1_AUG_NOISE reads eps ~ N(0,1) of shape (B, D, H, W, 3); M1_AUG_POOR_SCAN needs H == W (the
+ * reference resizes to (H, H)). */
+typedef struct {
+  int32_t zoom_on, zoom_scale;                       /* resize to scale x scale, keep the bottom-right H x W window */
+  int32_t flip_on;
+  int32_t rot_on, rot_pad, rot_crop_h, rot_crop_w;   /* SYMMETRIC pad, rotate about the centre, central crop offsets */
+  float rot_cos, rot_sin, rot_xoff, rot_yoff;        /* tfa.image.rotate: in = (cos x - sin y + xoff, sin x + cos y + yoff) */
+  int32_t tr_on, tr_top, tr_bottom, tr_right, tr_left;
+  int32_t cs_on, cs_channel, cs_top, cs_bottom, cs_right, cs_left;
+  int32_t gamma_on[3];
+  float gamma;
+  int32_t poor_on[3];
+  int32_t noise_on;
+  float noise_std;
+} m1_aug_plan;
+typedef enum {
+  M1_AUG_ZOOM = 0, M1_AUG_FLIP = 1, M1_AUG_ROTATE = 2, M1_AUG_TRANSLATE = 3, M1_AUG_CHANNEL_SHIFT = 4,
+  M1_AUG_GAMMA = 5, M1_AUG_POOR_SCAN = 6, M1_AUG_NOISE = 7
+} m1_aug_op;
+int m1_augment(m1_ctx* ctx, int op, const float* in, float* out, const float* eps, const m1_aug_plan* plans,
+               int batch, int D, int H, int W, int C, void* stream);
+
 /* ---- small utilities used by the host ------------------------------------------------------- */
 int m1_cast(m1_ctx* ctx, const void* src, int sdtype, void* dst, int ddtype, int64_t n,
             void* stream);

@@ -40,6 +40,22 @@ class Dropout(C.Structure):
                 ("rate", C.c_float), ("step", C.c_void_p), ("mask", C.c_void_p)]
 
 
+class AugPlan(C.Structure):
+    """m1_aug_plan of include/m1b200.h"""
+    _fields_ = [("zoom_on", C.c_int32), ("zoom_scale", C.c_int32), ("flip_on", C.c_int32),
+                ("rot_on", C.c_int32), ("rot_pad", C.c_int32), ("rot_crop_h", C.c_int32), ("rot_crop_w", C.c_int32),
+                ("rot_cos", C.c_float), ("rot_sin", C.c_float), ("rot_xoff", C.c_float), ("rot_yoff", C.c_float),
+                ("tr_on", C.c_int32), ("tr_top", C.c_int32), ("tr_bottom", C.c_int32), ("tr_right", C.c_int32),
+                ("tr_left", C.c_int32),
+                ("cs_on", C.c_int32), ("cs_channel", C.c_int32), ("cs_top", C.c_int32), ("cs_bottom", C.c_int32),
+                ("cs_right", C.c_int32), ("cs_left", C.c_int32),
+                ("gamma_on", C.c_int32 * 3), ("gamma", C.c_float), ("poor_on", C.c_int32 * 3),
+                ("noise_on", C.c_int32), ("noise_std", C.c_float)]
+
+
+AUG_ZOOM, AUG_FLIP, AUG_ROTATE, AUG_TRANSLATE, AUG_CHANNEL_SHIFT, AUG_GAMMA, AUG_POOR_SCAN, AUG_NOISE = range(8)
+
+
 class M1Error(RuntimeError):
     pass
 

@@ -73,6 +73,12 @@ struct WgParams {
   uint32_t a_desc_hi, b_desc_hi;
   uint32_t a_lbo, b_lbo;         // >> 4
   int splits;
+  // THIN launches (one or a few (tap group, M, N) tiles, hundreds of split-K CTAs): every CTA would add its 128 x N
+  // tile onto the SAME few thousand addresses - measured: 96 us of a 102 us 128->128 1x1x1 weight gradient remain
+  // with the loads switched off (M1_WG_NOLOAD), i.e. it is the ~300-way same-address reduction traffic in L2, not
+  // the data. Such launches store their partial tiles [split][base CTA][128][cols] (plain coalesced stores) and
+  // wgrad_reduce_kernel folds the splits, 8 interleaved groups of them per output element.
+  float* partial;
   int dbg_noload;                // experiment: producer arrives without loading (MMA-issue-rate probe)
   int64_t bricks_total;
   float* dw[M1_MAX_OUT];
@@ -259,6 +265,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
         uint32_t v[8];
         tmem_ld8(lane_addr + (uint32_t)((mi * p.tpg + tp) * p.n_tile + j), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p.partial != nullptr) {
+          const int cols = p.mpg * p.tpg * p.n_tile;
+          float* q = p.partial + (((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + r) * cols +
+                     (mi * p.tpg + tp) * p.n_tile + j;
+          *reinterpret_cast<uint4*>(q) = make_uint4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<uint4*>(q + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+          continue;
+        }
         if (!row_ok) continue;
         int n = n0 + j;                       // 8-column groups never straddle two dY tensors (channels % 16 == 0)
         if (n >= p.co) continue;
@@ -277,6 +291,55 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
                  : "memory");
   }
+}
+
+// dW += the partial tiles of the splits. grid = (base CTAs, chunks of (row, 4-column) elements, split groups): a
+// thread sums every gridDim.z-th split of its element and adds the result with ONE atomic per value - gridDim.z-way
+// instead of splits-way contention. The address logic mirrors the epilogue of wgrad_tc_kernel.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgParams p, int base_ctas) {
+  const int cols = p.mpg * p.tpg * p.n_tile, c4 = cols / 4;
+  const int idx = blockIdx.y * 256 + threadIdx.x;
+  if (idx >= 128 * c4) return;
+  const int r = idx / c4, c = (idx % c4) * 4;
+  const int m_sub = (p.nblocks + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  const int m_tiles = (m_sub + p.mpg - 1) / p.mpg;
+  const int n_tiles = (p.co + p.n_tile - 1) / p.n_tile;
+  int t = blockIdx.x;
+  const int nt = t % n_tiles; t /= n_tiles;
+  const int mt = t % m_tiles; t /= m_tiles;
+  const int group = t;
+  const int groups_per_row = p.kw / p.tpg;
+  const int kw0 = p.taps_in_m ? 0 : (group % groups_per_row) * p.tpg;
+  const int kh_i = p.taps_in_m ? 0 : (group / groups_per_row) % p.kh;
+  const int kd_i = p.taps_in_m ? 0 : group / (groups_per_row * p.kh);
+  const int acc = c / p.n_tile, j = c % p.n_tile, mi = acc / p.tpg, tp = acc % p.tpg;
+  if (mi >= min(p.mpg, m_sub - mt * p.mpg)) return;
+  const int blk0 = (mt * p.mpg + mi) * p.blocks_per_tile;
+  const int nblk = min(p.blocks_per_tile, p.nblocks - blk0);
+  if (r / p.ck >= nblk) return;
+  const int rblk = blk0 + r / p.ck;
+  const int rglob = (int)p.blk_goff[rblk] + r % p.ck;
+  const int tap = p.taps_in_m ? (int)p.blk_tap[rblk] : (kd_i * p.kh + kh_i) * p.kw + kw0 + tp;
+  int n = nt * p.n_tile + j;
+  if (n >= p.co) return;
+  int o = 0;
+  while (o + 1 < p.nout && n >= p.out_start[o + 1]) ++o;
+  n -= p.out_start[o];
+  const int64_t per = (p.bricks_total + p.splits - 1) / p.splits;
+  const int nsplit = (int)min((int64_t)p.splits, (p.bricks_total + per - 1) / per);     // splits that own bricks
+  const float* q = p.partial + ((int64_t)blockIdx.x * 128 + r) * cols + c;
+  const int64_t stride = (int64_t)base_ctas * 128 * cols;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int sp = blockIdx.z; sp < nsplit; sp += gridDim.z) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(q + sp * stride));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  float* dst = p.dw[o] + tap * p.st[o] + (int64_t)rglob * p.sr[o] + (int64_t)n * p.so[o];
+  atomicAdd(dst, s.x);
+  atomicAdd(dst + p.so[o], s.y);
+  atomicAdd(dst + 2 * p.so[o], s.z);
+  atomicAdd(dst + 3 * p.so[o], s.w);
 }
 
 struct WgPlan {
@@ -557,6 +620,12 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
     }
   }
   p.splits = (int)splits;
+  {
+    static const int g_scr = getenv("M1_WG_SCRATCH") ? atoi(getenv("M1_WG_SCRATCH")) : 1;
+    const size_t bytes = (size_t)splits * base_ctas * 128 * ((size_t)pl.mpg * pl.tpg * pl.n_tile) * sizeof(float);
+    const bool thin = base_ctas <= 8 && splits >= 8;
+    p.partial = (g_scr && bytes <= ctx->partial_bytes && (thin || g_scr >= 2)) ? ctx->partial : nullptr;
+  }
   static const int g_noload = getenv("M1_WG_NOLOAD") ? atoi(getenv("M1_WG_NOLOAD")) : 0;
   p.dbg_noload = g_noload;
 
@@ -568,5 +637,11 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   dim3 grid((unsigned)base_ctas, (unsigned)splits);
   wgrad_tc_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
   M1_LAUNCH_CHECK(ctx);
+  if (p.partial != nullptr) {
+    const int chunks = (128 * (pl.mpg * pl.tpg * pl.n_tile / 4) + 255) / 256;
+    const int groups_z = (int)std::min<int64_t>(8, splits);
+    wgrad_reduce_kernel<<<dim3((unsigned)base_ctas, (unsigned)chunks, (unsigned)groups_z), 256, 0, st>>>(p, (int)base_ctas);
+    M1_LAUNCH_CHECK(ctx);
+  }
   return 0;
 }

@@ -39,6 +39,8 @@ class BucketedGradSync:
         self.works = []
         self.fired = []
         self.flat = None
+        self.pre_fire = None       # called before a bucket's all-reduce is issued (Engine.join_side: weight
+                                   # gradients launched on the engine's side stream must have been joined)
 
     def begin(self, flat_grad, uses):
         """uses: {param name: number of backward closures that touch it this step}."""
@@ -54,6 +56,8 @@ class BucketedGradSync:
     def _fire(self, b):
         s, e = self.buckets[b]
         self.fired.append(b)
+        if self.pre_fire is not None:
+            self.pre_fire()
         if self.world_size > 1:
             self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group,
                                               async_op=True))

@@ -162,6 +162,13 @@ class Engine:
         # reference graph, every pass on its own - same results up to the rounding order of the summed gradients)
         self.share_trunk = os.environ.get("M1_SHARE_TRUNK", "1") != "0"
         self.shared = {}
+        # Weight gradients on a SIDE stream: dW of a layer and the data gradient of the same layer only share inputs,
+        # so the weight-gradient kernel (often a thin, latency-bound launch that leaves most SMs idle) runs
+        # concurrently with the rest of the backward walk and is joined before anything consumes the parameter
+        # gradients (bucket all-reduce, optimizer). The side stream has its own m1_ctx (scratch buffers); the tensors
+        # a side launch reads are kept alive until the join. Captured into the step's CUDA graph as a fork / join.
+        self.side_on = os.environ.get("M1_WGRAD_STREAM", "1") != "0"
+        self.side, self.ctx_side, self._side_keep, self._side_dirty = None, None, [], False
 
     # ---- helpers -----------------------------------------------------------------------------
     def new(self, shape, dtype=None, zero=False):
@@ -244,6 +251,33 @@ class Engine:
                 for n in names:
                     on_param_done(n)
         self.tape = []
+        self.join_side()
+
+    # ---- side stream of the weight gradients ------------------------------------------------------
+    def _on_side(self, keep, fn):
+        """run fn(ctx) on the side stream after everything enqueued so far on the current stream"""
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.device)
+            self.ctx_side = _lib.Context(torch.device(self.device).index or 0)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn(self.ctx_side)
+        self._side_keep.extend(keep)
+        self._side_dirty = True
+
+    def join_side(self):
+        """the current stream waits for the side stream; the tensors its launches read may be released afterwards"""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side_dirty = False
+        self._side_keep = []
+
+    def launch_total(self):
+        return self.ctx.launch_count() + (self.ctx_side.launch_count() if self.ctx_side is not None else 0)
 
     # ---- K1/K2/K3 convolutions -----------------------------------------------------------------
     def _gather(self, cat, mode, batch, in_dhw, out_dhw, k, s, pad, src_t, src_c, ws, wstr, bias, out_t, out_c,
@@ -400,6 +434,10 @@ class Engine:
             d.tune[0], d.tune[1], d.tune[2], d.tune[3] = cfg
         nb = 0 if self.prof is None else (sum(t.numel() * t.element_size() for t in list(srcs_t) + list(douts_t)) +
                                           sum(w.numel() * 8 for w in dws))
+        if self.side_on and self.prof is None and on_tc:
+            self._on_side(list(srcs_t) + list(douts_t),
+                          lambda c: ops.conv3d_wgrad(c, d, srcs_t, douts_t, dws, dbs))
+            return
         self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl, nbytes=nb,
                     fn=lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),

@@ -552,7 +552,7 @@ class M1(LoadableModel):
             # the flat gradient buffer: 256 MB, ~1 ms over NVLink, against ~85 ms of kernels).
             g_bwd, g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             self.noise.step_dev, self._lr_dev = st['step'], st['lr']
-            before = self.eng.ctx.launch_count()
+            before = self.eng.launch_total()
             import os
             # Data parallel: first try to capture the BUCKETED all-reduce inside the backward graph - every bucket's
             # NCCL call is issued (on torch's communication stream, forked from the capturing stream by events) as
@@ -585,7 +585,7 @@ class M1(LoadableModel):
                 self.noise.step_dev, self._lr_dev = None, None
                 self._graph_dp_overlap = False
             st['graph'], st['graph_update'] = g_bwd, g_upd
-            st['launches'] = self.eng.ctx.launch_count() - before
+            st['launches'] = self.eng.launch_total() - before
             self._gs = st
         else:
             st['x'].copy_(x, non_blocking=True)
@@ -676,6 +676,7 @@ class M1(LoadableModel):
         w_f, w_kl = self.loss_weights
         eng._timed("losses", 0, lambda: self._seed_losses(g, y, det, scal, w_f, w_kl))
         if self.grad_sync is not None and (not graphed or getattr(self, "_graph_dp_overlap", False)):
+            self.grad_sync.pre_fire = eng.join_side
             self.grad_sync.begin(self.params.g, eng.param_uses)
             eng.backward(self.grad_sync.param_done)
             self.grad_sync.finish()

@@ -361,3 +361,12 @@ class PackPlan:
                 lib().m1_pack_plan_destroy(self.handle)
         except Exception:      # noqa: BLE001 - interpreter shutdown
             pass
+
+
+# ---- K10 augmentations ---------------------------------------------------------------------------
+def augment(ctx, op, x, out, plans_dev, eps=None):
+    """m1_augment: one transform (_lib.AUG_*) over the batch x (B, D, H, W, C) fp32 -> out; plans_dev: uint8 device
+    tensor holding `B` packed m1_aug_plan structs; eps: (B, D, H, W, 3) fp32 for AUG_NOISE."""
+    b, d, h, w, c = x.shape
+    check(lib().m1_augment(ctx.handle, int(op), ptr(x), ptr(out), ptr(eps), ptr(plans_dev), b, d, h, w, c,
+                           current_stream()))

@@ -33,6 +33,10 @@ SHAPES = {
     'serse2': ((20, 80, 80), [64], [32, 128], (3, 3, 3), (1, 2, 2), False),
     'convtd1': ((20, 40, 40), [128], [64], (3, 3, 3), (1, 2, 2), True),
     'convtd0': ((20, 80, 80), [64], [32], (1, 3, 3), (1, 2, 2), True),
+    'convtd2': ((10, 20, 20), [256], [128], (3, 3, 3), (2, 2, 2), True),
+    'att2_c1': ((20, 40, 40), [128], [128], (1, 1, 1), (1, 1, 1), False),
+    'conv3_r2': ((20, 40, 40), [32], [128], (1, 1, 1), (1, 1, 1), False),
+    'conv3_r1': ((20, 80, 80), [16], [64], (1, 1, 1), (1, 1, 1), False),
 }
 
 
