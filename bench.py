@@ -255,7 +255,10 @@ def workload_config(args, world):
             "global_batch": args.batch * world, "parallelism": "dp%d" % world,
             "precision": "%s activation values and tensor-core weights, %s activation gradients, fp32 accumulation / "
                          "statistics / parameters" % (args.precision, "bf16" if args.precision != "fp32" else "fp32"),
-            "step_launch": "whole step captured once into CUDA graphs and replayed (M1_CUDA_GRAPH=0: eager)",
+            "step_launch": "whole step captured once into CUDA graphs and replayed (M1_CUDA_GRAPH=0: eager); weight "
+                           "gradients on a side stream inside the graph",
+            "shared_work": ("stem + serse1 up to its dropout computed once for the two passes of each network that read "
+                            "the same input; FLOP numerators count executed launches only") if c['full'] else None,
             "l2_flush": "not needed: every step streams >10 GB of activations, far above the 126 MB L2",
             "filters": list(README_CFG['filters']), "att_sub_samp": [list(s) for s in c['sub']],
             "prob_latent_dims": [3, 2, 1, 0] if c['full'] else None}

@@ -207,12 +207,18 @@ class Engine:
         return act.tw
 
     def x16(self, act):
-        """the tensor a tensor-core weight gradient reads for activation `act`: its bf16 twin in fp16 mode"""
+        """the tensor a tensor-core weight gradient reads for activation `act`: its bf16 twin in fp16 mode. A twin that
+        no producing kernel wrote (Conv3DTranspose outputs, the network input) is cast here - on the side stream of
+        the weight gradients when that is on: only they ever read twins."""
         if not self.twins or act.dtype != torch.float16:
             return act.t
         if act.tw is None:
             act.tw = self.new(act.shape, torch.bfloat16)
-            ops.cast(self.ctx, act.t, act.tw)
+            src, dst = act.t, act.tw
+            if self.side_on and self.prof is None:
+                self._on_side([src, dst], lambda c: ops.cast(c, src, dst))
+            else:
+                ops.cast(self.ctx, src, dst)
         return act.tw
 
     def new_grad(self, act):
@@ -438,6 +444,8 @@ class Engine:
             self._on_side(list(srcs_t) + list(douts_t),
                           lambda c: ops.conv3d_wgrad(c, d, srcs_t, douts_t, dws, dbs))
             return
+        if self.twins and any(t.dtype == torch.bfloat16 for t in srcs_t):
+            self.join_side()   # a main-stream weight gradient that reads a twin the side stream may just have cast
         self._timed("conv_wgrad_tcgen05" if on_tc else "conv_wgrad_simt", fl, nbytes=nb,
                     fn=lambda: ops.conv3d_wgrad(self.ctx, d, srcs_t, douts_t, dws, dbs),
                     label=(label, tuple(t.shape[-1] for t in srcs_t), tuple(t.shape[-1] for t in douts_t),
@@ -568,7 +576,11 @@ class Engine:
                             layers[0][0] + "(T)")
                 off += a.c
             if bias_grad:
-                ops.bias_grad(self.ctx, dy, self.pg(layers[0][0] + "/bias"))
+                gb = self.pg(layers[0][0] + "/bias")
+                if self.side_on and self.prof is None:           # reads dy only: next to the weight gradients
+                    self._on_side([dy], lambda c: ops.bias_grad(c, dy, gb))
+                else:
+                    ops.bias_grad(self.ctx, dy, gb)
             # ---- dgrad: dx_s[i, ci] (+)= sum_k dy[i*s + k - pad, co] * Wt[k, co, off + ci] (strided FWD gather);
             # tensors with odd channel counts (latents) go to the CUDA cores, aligned ones to tcgen05
             if need:
