@@ -444,8 +444,9 @@ def run_ours(args):
                      else None} for k, v in cats.items()}
     total_ms = sum(v[1] for v in cats.values())
     traffic = {}
-    try:      # per-launch DRAM bytes of the dominant kernels, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+    try:      # per-launch DRAM bytes of the dominant kernels, from the committed ncu --set full capture (of the c2 step)
+        if args.config == "c2" and args.dims == tuple(CONFIGS["c2"]["dims"]) and args.batch == CONFIGS["c2"]["batch"]:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
     except (OSError, ValueError):
         pass
     conv_cats = {k: v for k, v in cats.items() if k.startswith("conv_") and v[0] > 0}

@@ -63,8 +63,6 @@ struct TcParams {
   uint32_t idesc;
   uint32_t desc_hi;            // upper 32 bits of the UMMA shared-memory descriptors
   EpiOut epi;
-  int epi_tma;                 // EXPERIMENTAL: shared-memory C tile + TMA stores instead of per-thread stores
-  CUtensorMap tmOut[M1_MAX_OUT];
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -191,15 +189,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     int cb, ce;
     epi_cols(warp, p.n_tile, &cb, &ce);
-    if (p.epi_tma) {
-      // every stage of the ring has been consumed when bar_accum fires: the C tile reuses that shared memory
-      epilogue_row_smem(p.epi, lane_addr, n0, cb, ce, r, tiles, ksteps == 0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) epilogue_tma_stores(p.epi, p.tmOut, n0, p.n_tile, tiles, w0, h0, d0, n_img);
-    } else {
-      epilogue_row(p.epi, lane_addr, n0, cb, ce, valid, vox, ksteps == 0);
-    }
+    epilogue_row(p.epi, lane_addr, n0, cb, ce, valid, vox, ksteps == 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -815,19 +805,7 @@ int m1_conv3d_tc(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs,
   for (int j = 0; j < d->nout; ++j)
     M1_CHECK(((uintptr_t)outs[j] & 15) == 0, "m1_conv3d: produced tensor %d not 16-byte aligned", j);
 
-  // EXPERIMENTAL TMA-store epilogue (single-tile kernel, produced grid traversed with unit stride)
-  static const int g_epi_tma = getenv("M1_EPI_TMA") ? atoi(getenv("M1_EPI_TMA")) : 0;
-  uint32_t smem_bytes = pl.smem_bytes;
-  if (g_epi_tma && os[0] == 1 && os[1] == 1 && os[2] == 1 && pl.nphase == 1 && d->tune[0] != 3 &&
-      epi_fill_chunks(&p.epi, d, pl.n_tile)) {
-    p.epi_tma = 1;
-    for (int j = 0; j < d->nout; ++j) {
-      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_dtype, d->out_c[j], d->out_dhw[2], d->out_dhw[1],
-                                 d->out_dhw[0], d->batch, p.epi.cs[j], pl.bw, pl.bh, pl.bd);
-      M1_CHECK(r == 0, "cuTensorMapEncodeTiled(store %d) failed: %d", j, r);
-    }
-    smem_bytes = std::max(smem_bytes, 2048u + 128u * (uint32_t)pl.n_tile * 2u);
-  }
+  const uint32_t smem_bytes = pl.smem_bytes;
   static const int g_multi = getenv("M1_CONV_MULTI") ? atoi(getenv("M1_CONV_MULTI")) : 0;
   if (d->tune[0] == 3 || g_multi) {
     // multi-tile variant (see conv_tc_multi_kernel): the producer streams k-steps ACROSS tile boundaries, so the

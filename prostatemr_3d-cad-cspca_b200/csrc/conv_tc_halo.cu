@@ -47,8 +47,6 @@ struct HaloParams {
   uint32_t idesc, desc_hi;
   EpiOut epi;
   int dbg;                     // timing experiments: 1 = no A loads, 2 = no B loads, 4 = no MMAs (results invalid)
-  int epi_tma;                 // EXPERIMENTAL (M1_EPI_TMA=1): C tile in shared memory + one TMA store per line
-  CUtensorMap tmOut[M1_MAX_OUT];
 };
 
 __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ HaloParams p) {
@@ -180,39 +178,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     int cb, ce;
     epi_cols(warp, p.n_tile, &cb, &ce);
-    if (p.epi_tma) {
-      // Sub-tile after sub-tile through ONE shared-memory C tile (the drained pipeline ring): rows q = line * P +
-      // column, so the bw valid voxels of a line are consecutive rows of every channel chunk - one store box
-      // (cs channels x bw voxels) per (chunk, line); halo rows are written to shared memory but never stored.
-      for (int g = 0; g < g_live; ++g) {
-        epilogue_row_smem(p.epi, lane_addr + (uint32_t)(g * p.n_tile), n0, cb, ce, q, tiles, iters == 0);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          for (int line = 0; line < p.bh; ++line) {
-            const int h = h0 + g * p.bh + line;
-            if (h >= p.H) break;
-            int lc = 0;
-            while (lc < p.n_tile && n0 + lc < p.epi.n_total) {
-              const int grp = min((n0 + lc) >> 3, kMaxGroups - 1);
-              const int o = p.epi.grp_out[grp], c = p.epi.grp_c[grp], cs = p.epi.cs[o];
-              tma_store_5d(&p.tmOut[o], tiles + (uint32_t)lc * 256u + (uint32_t)(line * p.P) * (uint32_t)(cs * 2), c, w0,
-                           h, d, n_img, (p.epi.accumulate >> o) & 1);
-              lc += cs;
-            }
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        __syncthreads();                                   // the C tile is free again for the next sub-tile
-      }
-    } else {
-      for (int g = 0; g < g_live; ++g) {
-        const int h = h0 + g * p.bh + lh;
-        const bool valid = lh < p.bh && lw < p.bw && h < p.H && w < p.W;
-        const int64_t vox = (((int64_t)n_img * p.D + d) * p.H + h) * p.W + w;
-        epilogue_row(p.epi, lane_addr + (uint32_t)(g * p.n_tile), n0, cb, ce, valid, vox, iters == 0);
-      }
+    for (int g = 0; g < g_live; ++g) {
+      const int h = h0 + g * p.bh + lh;
+      const bool valid = lh < p.bh && lw < p.bw && h < p.H && w < p.W;
+      const int64_t vox = (((int64_t)n_img * p.D + d) * p.H + h) * p.W + w;
+      epilogue_row(p.epi, lane_addr + (uint32_t)(g * p.n_tile), n0, cb, ce, valid, vox, iters == 0);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -418,18 +388,7 @@ int m1_conv3d_halo(m1_ctx* ctx, const m1_conv_desc* d, const void* const* srcs, 
     fprintf(stderr, "halo plan: ck %d G %d bh %d bw %d P %d L %d stages %d stage_bytes %u ctas/SM %d tmem %u grid %d x %d\n",
             pl.ck, pl.G, pl.bh, pl.bw, pl.P, pl.L, pl.stages, pl.stage_bytes, pl.ctas_per_sm, pl.tmem_cols,
             d->batch * D * pl.th * pl.tw, pl.n_tiles);
-  // EXPERIMENTAL TMA-store epilogue: one (cs channels x bw voxels) store box per line
-  static const int g_epi_tma = getenv("M1_EPI_TMA") ? atoi(getenv("M1_EPI_TMA")) : 0;
-  uint32_t smem_bytes = pl.smem_bytes;
-  if (g_epi_tma && epi_fill_chunks(&p.epi, d, pl.n_tile)) {
-    p.epi_tma = 1;
-    for (int j = 0; j < d->nout; ++j) {
-      int r = encode_ndhwc_store(encode, &p.tmOut[j], outs[j], d->out_dtype, d->out_c[j], W, H, D, d->batch, p.epi.cs[j],
-                                 pl.bw, 1, 1);
-      M1_CHECK(r == 0, "cuTensorMapEncodeTiled(halo store %d) failed: %d", j, r);
-    }
-    smem_bytes = std::max(smem_bytes, 2048u + 128u * (uint32_t)pl.n_tile * 2u);
-  }
+  const uint32_t smem_bytes = pl.smem_bytes;
   static int smem_set = 0;
   if (!smem_set) {
     M1_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -127,18 +127,4 @@ inline int encode_ndhwc(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-// un-swizzled 5-D map for TMA STORES of a (cs channels, bw, bh, bd, 1) brick of an NDHWC 16-bit tensor (the
-// element type matters here: cp.reduce.async.bulk.tensor adds in it)
-inline int encode_ndhwc_store(EncodeTiledFn encode, CUtensorMap* tm, const void* ptr, int dt, int C, int W, int H, int D,
-                              int N, int cs, int bw, int bh, int bd) {
-  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-  cuuint64_t c2 = (cuuint64_t)C * 2;
-  cuuint64_t strides[4] = {c2, c2 * W, c2 * W * H, c2 * W * H * D};
-  cuuint32_t box[5] = {(cuuint32_t)cs, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  return (int)encode(tm, tm_dtype(dt), 5, const_cast<void*>(ptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-}
-
 }  // namespace tc

@@ -21,7 +21,6 @@ struct EpiOut {
   int out_f16;                    // produced tensors are fp16 (else bf16)
   uint8_t grp_out[kMaxGroups];    // 8-column group -> produced tensor
   uint16_t grp_c[kMaxGroups];     // 8-column group -> first channel inside that tensor
-  uint8_t cs[M1_MAX_OUT];         // TMA-store epilogue: channels per store box of each produced tensor
 };
 
 // host: fill the group tables; returns false if the launch has too many produced channels
@@ -109,98 +108,6 @@ __device__ __forceinline__ void epilogue_row(const EpiOut& e, uint32_t taddr, in
       *reinterpret_cast<uint4*>(dst[h]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
-}
-
-// ---- TMA-store epilogue (EXPERIMENTAL, M1_EPI_TMA=1): the register epilogue above issues one 16-byte store per
-// thread and 8 columns - every warp store touches 32 different sectors and the LSU retires ~1 such sector per
-// 4 cycles, which bounds all short-K launches. Here the rows go to a shared-memory C tile instead: the columns
-// of the N tile are cut into chunks of cs[o] channels (never straddling a produced tensor), chunk k is a dense
-// [128 rows][cs] bf16 matrix at byte offset 256 * (first local column of the chunk) - exactly the source layout
-// of one un-swizzled cp.async.bulk.tensor store box (cs channels x brick) per chunk.
-__device__ __forceinline__ void epilogue_row_smem(const EpiOut& e, uint32_t taddr, int n0, int col_begin, int col_end,
-                                                  int row, uint32_t c_base, bool zero_acc) {
-  for (int j = col_begin; j < col_end; j += 16) {
-    uint32_t v[16];
-    tmem_ld16(taddr + (uint32_t)j, v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int lc = j + 8 * h, gcol = n0 + lc;
-      if (gcol >= e.n_total) continue;
-      const int grp = min(gcol >> 3, kMaxGroups - 1);
-      const int o = e.grp_out[grp], c = e.grp_c[grp], cs = e.cs[o];
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = zero_acc ? 0.f : __uint_as_float(v[8 * h + i]);
-      if (e.bias[o] != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(e.bias[o] + c);
-        const float4 b1 = *reinterpret_cast<const float4*>(e.bias[o] + c + 4);
-        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-      }
-      uint32_t pk[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        pk[i] = e.out_f16 ? pack2<__half>(f[2 * i], f[2 * i + 1]) : pack2<__nv_bfloat16>(f[2 * i], f[2 * i + 1]);
-      const int within = c % cs;                                   // channel inside its chunk
-      const uint32_t addr = c_base + (uint32_t)(lc - within) * 256u + (uint32_t)row * (uint32_t)(cs * 2) +
-                            (uint32_t)within * 2u;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                   "r"(pk[3])
-                   : "memory");
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3,
-                                             int c4, bool reduce_add) {
-  if (reduce_add) {
-    asm volatile(
-        "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tm),
-        "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tm),
-        "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-  }
-}
-
-// one thread: a store (or bf16 reduce-add for accumulating launches) per chunk of the N tile, brick origin
-// (w0, h0, d0) of volume n_img; waits until the shared-memory tile has been read
-__device__ __forceinline__ void epilogue_tma_stores(const EpiOut& e, const CUtensorMap* tm_out, int n0, int n_tile,
-                                                    uint32_t c_base, int w0, int h0, int d0, int n_img) {
-  int lc = 0;
-  while (lc < n_tile && n0 + lc < e.n_total) {
-    const int grp = min((n0 + lc) >> 3, kMaxGroups - 1);
-    const int o = e.grp_out[grp], c = e.grp_c[grp], cs = e.cs[o];
-    tma_store_5d(&tm_out[o], c_base + (uint32_t)lc * 256u, c, w0, h0, d0, n_img, (e.accumulate >> o) & 1);
-    lc += cs;
-  }
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// host: chunk width of every produced tensor = largest power of two <= 64 that divides its channel count and
-// every N-tile boundary falling inside it; false if a tensor would need chunks narrower than 8 channels
-inline bool epi_fill_chunks(EpiOut* e, const m1_conv_desc* d, int n_tile) {
-  int start = 0;
-  for (int j = 0; j < d->nout; ++j) {
-    int g = d->out_c[j];
-    for (int b = n_tile; b < start + d->out_c[j]; b += n_tile)
-      if (b > start) {
-        int a = b - start, x = g;
-        while (a) { const int t = x % a; x = a; a = t; }
-        g = x;
-      }
-    int cs = 64;
-    while (cs > 8 && g % cs) cs >>= 1;
-    if (g % cs) return false;
-    e->cs[j] = (uint8_t)cs;
-    start += d->out_c[j];
-  }
-  return true;
 }
 
 // column range of epilogue warp `warp` (0..7) for a tile of n_tile columns: warps 0-3 take the first half

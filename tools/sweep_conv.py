@@ -5,7 +5,7 @@ timed in isolation on the GPU for each variant of the tcgen05 engines:
   forward launch        tune[0] = 1 (one TMA box per tap), 2 (halo tile, if plannable), 3 (multi-tile, experimental)
   weight gradient       default tilings vs SHIFT mode (tune[1] = 2, if plannable)
 
-Run it once with and once without M1_EPI_TMA=1 to compare the register-store and the TMA-store epilogues.
+
 CUDA events, L2 flushed between iterations; prints ms per launch, launches per step and the per-step total of
 the best variant. Usage: sweep_conv.py [--iters N] [--batch B] [--min-ms X] [--what fwd,wgrad]"""
 import argparse
