@@ -37,7 +37,7 @@ extern "C" int m1_ctx_create(int device, m1_ctx** out) {
   if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = fn;
   c->scratch_bytes = 1 << 20;
   M1_CUDA(cudaMalloc(&c->scratch, c->scratch_bytes));
-  c->partial_bytes = 48u << 20;
+  c->partial_bytes = 160u << 20;     // deterministic-reduction partials / split-K partial tiles of the weight gradient
   M1_CUDA(cudaMalloc(&c->partial, c->partial_bytes));
   c->counter_bytes = 64u << 10;
   M1_CUDA(cudaMalloc(&c->counters, c->counter_bytes));

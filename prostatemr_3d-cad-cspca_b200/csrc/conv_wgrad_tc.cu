@@ -73,11 +73,11 @@ struct WgParams {
   uint32_t a_desc_hi, b_desc_hi;
   uint32_t a_lbo, b_lbo;         // >> 4
   int splits;
-  // THIN launches (one or a few (tap group, M, N) tiles, hundreds of split-K CTAs): every CTA would add its 128 x N
-  // tile onto the SAME few thousand addresses - measured: 96 us of a 102 us 128->128 1x1x1 weight gradient remain
-  // with the loads switched off (M1_WG_NOLOAD), i.e. it is the ~300-way same-address reduction traffic in L2, not
-  // the data. Such launches store their partial tiles [split][base CTA][128][cols] (plain coalesced stores) and
-  // wgrad_reduce_kernel folds the splits, 8 interleaved groups of them per output element.
+  // Split-K through partial tiles instead of atomics. With atomics every split adds its 128 x N tile onto the SAME
+  // addresses; for thin launches (one tile, ~300 splits) that same-address reduction traffic in L2 IS the kernel:
+  // 96 us of a 102 us 128->128 1x1x1 weight gradient remain with the loads switched off (M1_WG_NOLOAD). Launches
+  // whose partial tiles [split][base CTA][128][cols] fit the context scratch store them (plain coalesced stores)
+  // and wgrad_reduce_kernel folds the splits (1-8 interleaved groups of them per output element).
   float* partial;
   int dbg_noload;                // experiment: producer arrives without loading (MMA-issue-rate probe)
   int64_t bricks_total;
@@ -621,10 +621,13 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   }
   p.splits = (int)splits;
   {
-    static const int g_scr = getenv("M1_WG_SCRATCH") ? atoi(getenv("M1_WG_SCRATCH")) : 1;
+    static const int g_scr = getenv("M1_WG_SCRATCH") ? atoi(getenv("M1_WG_SCRATCH")) : 2;
     const size_t bytes = (size_t)splits * base_ctas * 128 * ((size_t)pl.mpg * pl.tpg * pl.n_tile) * sizeof(float);
+    // 1: thin launches only (<= 8 tiles, >= 8 splits); 2 (default): every split-K launch whose partial tiles fit the
+    // scratch - the transposed-convolution weight gradients (27 tiles x 10 splits) gain as much as the thin ones:
+    // 0.195 -> 0.144 ms; whole step 74.96 -> 73.95 ms in one A/B call
     const bool thin = base_ctas <= 8 && splits >= 8;
-    p.partial = (g_scr && bytes <= ctx->partial_bytes && (thin || g_scr >= 2)) ? ctx->partial : nullptr;
+    p.partial = (g_scr && bytes <= ctx->partial_bytes && (thin || (g_scr >= 2 && splits >= 2))) ? ctx->partial : nullptr;
   }
   static const int g_noload = getenv("M1_WG_NOLOAD") ? atoi(getenv("M1_WG_NOLOAD")) : 0;
   p.dbg_noload = g_noload;
@@ -639,7 +642,9 @@ int m1_conv3d_wgrad_tc(m1_ctx* ctx, const m1_conv_desc* d, int j0, int jn, const
   M1_LAUNCH_CHECK(ctx);
   if (p.partial != nullptr) {
     const int chunks = (128 * (pl.mpg * pl.tpg * pl.n_tile / 4) + 255) / 256;
-    const int groups_z = (int)std::min<int64_t>(8, splits);
+    // split groups per output element: enough threads to fill the machine (>= ~64 K), at most 8-way atomics
+    const int64_t threads1 = (int64_t)base_ctas * 128 * (pl.mpg * pl.tpg * pl.n_tile / 4);
+    const int groups_z = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, splits), (65536 + threads1 - 1) / threads1));
     wgrad_reduce_kernel<<<dim3((unsigned)base_ctas, (unsigned)chunks, (unsigned)groups_z), 256, 0, st>>>(p, (int)base_ctas);
     M1_LAUNCH_CHECK(ctx);
   }
