@@ -338,12 +338,18 @@ def run_ours(args):
     last = {}
     cascade_in = (lambda x: [x, x]) if c['cascaded'] else (lambda x: x)
     if mode == "train":
+        from m1b200.model.prefetch import DevicePrefetcher
+
+        def host_batches():                                   # the same pinned host batch, copied again every step
+            while True:
+                yield xh, yh
+        feed = iter(DevicePrefetcher(host_batches(), dev))     # tf.data .prefetch: batch i+1 is copied while step i runs
+
         def dev_step():
             model.train_step(cascade_in(xd), yd)
 
         def e2e_step():
-            x = xh.to(dev, non_blocking=True)
-            y = yh.to(dev, non_blocking=True)
+            x, y = next(feed)                                 # host -> device copy of THIS step's inputs (98 MB)
             r = model.train_step(cascade_in(x), y)
             last['result'] = model.total_loss(r).cpu()       # device -> host read of the step's result
         d2h = 4

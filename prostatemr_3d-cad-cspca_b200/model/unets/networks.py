@@ -724,6 +724,9 @@ class M1(LoadableModel):
             steps_per_epoch = steps_per_epoch or 1
         else:
             data = x
+        if self.eng is not None and not isinstance(data, (list, tuple)):
+            from ..prefetch import DevicePrefetcher          # train_model.py:183 .prefetch(): next batch copied ahead
+            data = DevicePrefetcher(data, self.device)
         it = iter(data)
         for cb in callbacks or []:
             getattr(cb, 'on_train_begin', lambda logs=None: None)()

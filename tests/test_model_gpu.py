@@ -336,3 +336,25 @@ def test_fit_and_save_load_roundtrip(ctx, tmp_path):
     assert all(np.array_equal(w1[k], w2[k]) for k in w1)
     assert m2.optimizer.iterations == model.optimizer.iterations == 6
     assert np.array_equal(m2.get_optimizer_state()['vhat'], model.get_optimizer_state()['vhat'])
+
+
+def test_device_prefetcher_feeds_fit(ctx):
+    """model.prefetch.DevicePrefetcher (the .prefetch() of train_model.py:183): batches arrive on the device, in order,
+    bit-identical to the host data, one step ahead on a copy stream; M1.fit wraps any non-list iterable in it."""
+    from m1b200.model.prefetch import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    host = [({'image': torch.randn(2, 4, 8, 8, 4, generator=g)}, {'detection': torch.rand(2, 4, 8, 8, 2, generator=g)})
+            for _ in range(5)]
+    pf = DevicePrefetcher(iter(host), 'cuda:0')
+    got = list(pf)
+    assert len(got) == 5 and pf.h2d_bytes == sum(b[0]['image'].numel() * 4 + b[1]['detection'].numel() * 4 for b in host)
+    for (hi, ht), (di, dt) in zip(host, got):
+        assert di['image'].is_cuda and torch.equal(di['image'].cpu(), hi['image'])
+        assert torch.equal(dt['detection'].cpu(), ht['detection'])
+    model, cfg, x, y = _build(TINY, (8, 32, 32), 2, 'fp32', True, True, True)
+
+    def gen():
+        for _ in range(4):
+            yield {'image': x}, {'detection': y}
+    hist = model.fit(x=gen(), epochs=1, steps_per_epoch=4, verbose=0)
+    assert len(hist['loss']) == 1 and math.isfinite(hist['loss'][0])
