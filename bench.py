@@ -401,7 +401,8 @@ def run_ours(args):
     if ncu_range:
         torch.cuda.profiler.stop()
     prof = [p for e in engines for p in e.prof]
-    flops_step = sum(e.conv_flops + e.bwd_flops for e in engines) * (c.get('passes', 1) if mode == "mc" else 1)
+    # (mc: the whole ensemble runs in one engine scope - shared trunk once + `passes` passes - and is counted as such)
+    flops_step = sum(e.conv_flops + e.bwd_flops for e in engines)
     for e in engines:
         e.prof = None
 

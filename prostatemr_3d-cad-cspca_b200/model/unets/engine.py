@@ -79,12 +79,13 @@ class PhiloxNoise:
         self.seed = int(seed) + 1000003 * int(rank)
         self.step = 0
         self.step_dev = None      # device step counter while a CUDA graph of the step is being captured
+        self.sub = 0              # offset on the step: pass i of a Monte-Carlo ensemble launched as ONE graph
 
     def _stream(self, pass_name, site):
         """Philox stream = step * 4096 + pass * 64 + site; under graph capture the step term is added on the
         device from step_dev (M1_PHILOX_STEP_STRIDE), so eager and replayed steps draw identical noise."""
         p = self.PASSES.index(pass_name) if pass_name in self.PASSES else len(self.PASSES)
-        step = 0 if self.step_dev is not None else self.step
+        step = (0 if self.step_dev is not None else self.step) + self.sub
         return (step * 64 + p) * 64 + self.SITES.index(site)
 
     def dropout(self, eng, pass_name, site, shape, rate):

@@ -440,9 +440,10 @@ class M1(LoadableModel):
         return dict(heads=heads, inputs=list(img) + list(post_in),
                     kl_pairs=list(zip(q_sample['prob_distributions'], p_zq['prob_distributions'])))
 
-    def _infer_graph(self, eng, batch, trace=False, x=None, pass_name='p_sample'):
-        """get_detect_model() graph (R:networks.py:196-206, :350,:355)."""
-        img, _ = self._inputs(eng, batch, x, trace)
+    def _infer_graph(self, eng, batch, trace=False, x=None, pass_name='p_sample', inputs=None):
+        """get_detect_model() graph (R:networks.py:196-206, :350,:355). inputs: activation list of an earlier call
+        (passes of a Monte-Carlo ensemble over ONE batch share the stem + serse1 trunk through Engine.shared)."""
+        img = inputs if inputs is not None else self._inputs(eng, batch, x, trace)[0]
         if not self.probabilistic:
             o = self.core(eng, img, pass_name='det', training=False)
             return o['logits']
@@ -898,22 +899,86 @@ class DetectModel:
 
     @property
     def launches_per_graph_pass(self):
-        st = getattr(self, "_gs", None)
+        """kernels inside the most recently used replayed graph (a single pass, or a whole ensemble)"""
+        st = getattr(self, "_gs_mc", None) or getattr(self, "_gs", None)
         return st['launches'] if st else None
 
-    def predict_mc(self, x, passes=20):
-        """Monte-Carlo dropout ensemble (BASELINE config 4): mean softmax of `passes` stochastic
-        prior passes with fresh Philox streams (the loop itself is not in the reference: the flag
-        UNET_PROBA_ITER of train_model.py:71 is unused there)."""
+    def _predict_mc_eager(self, x, passes, pass_name='p_sample'):
+        """`passes` stochastic passes over ONE batch in one engine scope: the input activations are built once, so
+        the stem + serse1 trunk (nothing stochastic before the first dropout) is computed once and shared; pass i
+        draws the Philox streams of step + i (PhiloxNoise.sub), exactly those of `passes` separate predict() calls."""
         m = self.model
-        x = m._to_device(x)
-        mean = None
-        for _ in range(passes):
-            p = self.predict(x)
-            if mean is None:
-                mean = torch.zeros_like(p)
-            ops.axpy(m.eng.ctx, p, 1.0 / passes, mean)
+        eng = m.eng
+        B = x.shape[0]
+        eng.noise = m.noise
+        eng.begin(record=False)
+        img = m._inputs(eng, B, x, False)[0]
+        nc = m.num_classes
+        mean = torch.zeros((B,) + m.input_spatial_dims + (nc,), dtype=torch.float32, device=m.device)
+        philox = isinstance(m.noise, PhiloxNoise)
+        try:
+            for i in range(passes):
+                if philox:
+                    m.noise.sub = i
+                lg = m._infer_graph(eng, B, pass_name=pass_name, inputs=img)
+                out = torch.empty_like(mean)
+                m._softmax_head(eng, lg, (1, 1, 1), out, 0)
+                ops.axpy(eng.ctx, out, 1.0 / passes, mean)
+        finally:
+            if philox:
+                m.noise.sub = 0
         return mean
+
+    def predict_mc(self, x, passes=20):
+        """Monte-Carlo dropout ensemble (BASELINE config 4): mean softmax of `passes` stochastic prior passes with
+        fresh Philox streams (the loop itself is not in the reference: the flag UNET_PROBA_ITER of train_model.py:71
+        is unused there). After GRAPH_WARMUP eager calls the WHOLE ensemble - shared trunk, `passes` passes, the
+        running mean - is captured once into one CUDA graph and replayed (M1_CUDA_GRAPH=0: always eager)."""
+        import os
+        m = self.model
+        if m.eng is None:
+            raise RuntimeError("model not built on a GPU (m1b200 has no CPU fallback)")
+        x = m._to_device(x)
+        philox = isinstance(m.noise, PhiloxNoise)
+        st = getattr(self, "_gs_mc", None)
+        if st is not None and (tuple(st['x'].shape) != tuple(x.shape) or st['passes'] != passes):
+            st = self._gs_mc = None
+            self._mc_eager_calls = 0
+        if not philox or m.eng.prof is not None or os.environ.get("M1_CUDA_GRAPH", "1") == "0" \
+                or getattr(self, "_graph_failed", False):
+            out = self._predict_mc_eager(x, passes)
+        elif st is None and getattr(self, "_mc_eager_calls", 0) < self.GRAPH_WARMUP:
+            self._mc_eager_calls = getattr(self, "_mc_eager_calls", 0) + 1
+            out = self._predict_mc_eager(x, passes)
+        else:
+            if st is None:
+                st = {'x': torch.empty_like(x), 'step': torch.zeros(1, dtype=torch.int64, device=m.device),
+                      'passes': passes}
+                st['x'].copy_(x)
+                st['step'].fill_(m.noise.step)
+                torch.cuda.synchronize(m.device)
+                g = torch.cuda.CUDAGraph()
+                m.noise.step_dev = st['step']
+                before = m.eng.launch_total()
+                try:
+                    with torch.cuda.graph(g):
+                        st['out'] = self._predict_mc_eager(st['x'], passes)
+                except Exception:
+                    self._graph_failed = True
+                    raise
+                finally:
+                    m.noise.step_dev = None
+                st['graph'], st['launches'] = g, m.eng.launch_total() - before
+                self._gs_mc = st
+            else:
+                st['x'].copy_(x, non_blocking=True)
+            st['step'].fill_(m.noise.step)
+            st['graph'].replay()
+            self.graph_replays = getattr(self, "graph_replays", 0) + 1
+            out = st['out']
+        if philox:
+            m.noise.step += passes
+        return out
 
 
 def m1(*args, **kwargs):
