@@ -141,7 +141,40 @@ struct ReduceScratch {
   unsigned int* counter;  // [batch], zero between launches
 };
 
-template <int K, int VW, int UNR, int NT, int ES, typename P, typename F, typename FIN>
+// PIPE: software-pipelined main loop - the raw loads of iteration i+1 are issued BEFORE iteration i is computed
+// (two register sets, ping-pong). The gate kernels spend ~500 instructions per iteration between load batches; ncu
+// shows them latency-bound (long-scoreboard stalls, issue slots 44 % busy at 25 % occupancy).
+template <int UNR, int NT, int ES, int VW, typename G>
+__device__ __forceinline__ void pipelined_rows(const void* const (&src)[NT], int64_t& r, int64_t& off, int64_t r1,
+                                               int lanes, int64_t step, G g) {
+  RawVec<ES, VW> A[UNR][NT], B[UNR][NT];
+  auto load = [&](RawVec<ES, VW> (&dst)[UNR][NT], int64_t o) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) dst[u][t].load(src[t], o + u * step);
+  };
+  auto full = [&](int64_t rr) { return rr + (int64_t)(UNR - 1) * lanes < r1; };
+  const int64_t dr = (int64_t)UNR * lanes, doff = UNR * step;
+  if (!full(r)) return;
+  load(A, off);
+  while (true) {
+    const bool nb = full(r + dr);
+    if (nb) load(B, off + doff);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) g(r + (int64_t)u * lanes, off + u * step, A[u]);
+    r += dr; off += doff;
+    if (!nb) break;
+    const bool na = full(r + dr);
+    if (na) load(A, off + doff);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) g(r + (int64_t)u * lanes, off + u * step, B[u]);
+    r += dr; off += doff;
+    if (!na) break;
+  }
+}
+
+template <int K, int VW, int UNR, int NT, int ES, bool PIPE = false, typename P, typename F, typename FIN>
 __device__ __forceinline__ void reduce_rows(const void* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
                                             float* smem, ReduceScratch rs, P prep, F f, FIN fin) {
   const int CG = C / VW;
@@ -167,14 +200,21 @@ __device__ __forceinline__ void reduce_rows(const void* const (&src)[NT], int64_
       const int64_t step = (int64_t)lanes * C;
       int64_t r = r0 + my_lane;
       int64_t off = r * C + cbase;
-      for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
-        RawVec<ES, VW> raw[UNR][NT];
+      if constexpr (PIPE) {
+        pipelined_rows<UNR, NT, ES, VW>(src, r, off, r1, lanes, step,
+                                        [&](int64_t row, int64_t, const RawVec<ES, VW> (&raw)[NT]) {
+                                          f(row, cbase, regs, raw, acc);
+                                        });
+      } else {
+        for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
+          RawVec<ES, VW> raw[UNR][NT];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u)
+          for (int u = 0; u < UNR; ++u)
 #pragma unroll
-          for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
+            for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, cbase, regs, raw[u], acc);
+          for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, cbase, regs, raw[u], acc);
+        }
       }
       for (; r < r1; r += lanes, off += step) {
         RawVec<ES, VW> raw[NT];
@@ -232,7 +272,7 @@ inline size_t reduce_smem(int K, int C, int VW) {
 
 // stream_rows: pure elementwise pass, F(row, element offset, cbase, regs, raw[NT]) computes and stores one row's
 // channel group (element offset = row * C + cbase inside the sample)
-template <int VW, int UNR, int NT, int ES, typename P, typename F>
+template <int VW, int UNR, int NT, int ES, bool PIPE = false, typename P, typename F>
 __device__ __forceinline__ void stream_rows(const void* const (&src)[NT], int64_t voxels, int C, int64_t rows_per_slab,
                                             P prep, F f) {
   const int CG = C / VW;
@@ -248,14 +288,21 @@ __device__ __forceinline__ void stream_rows(const void* const (&src)[NT], int64_
     const int64_t step = (int64_t)lanes * C;
     int64_t r = r0 + my_lane;
     int64_t off = r * C + cbase;
-    for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
-      RawVec<ES, VW> raw[UNR][NT];
+    if constexpr (PIPE) {
+      pipelined_rows<UNR, NT, ES, VW>(src, r, off, r1, lanes, step,
+                                      [&](int64_t row, int64_t o, const RawVec<ES, VW> (&raw)[NT]) {
+                                        f(row, o, cbase, regs, raw);
+                                      });
+    } else {
+      for (; r + (int64_t)(UNR - 1) * lanes < r1; r += (int64_t)UNR * lanes, off += UNR * step) {
+        RawVec<ES, VW> raw[UNR][NT];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u)
+        for (int u = 0; u < UNR; ++u)
 #pragma unroll
-        for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
+          for (int t = 0; t < NT; ++t) raw[u][t].load(src[t], off + u * step);
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, off + u * step, cbase, regs, raw[u]);
+        for (int u = 0; u < UNR; ++u) f(r + (int64_t)u * lanes, off + u * step, cbase, regs, raw[u]);
+      }
     }
     for (; r < r1; r += lanes, off += step) {
       RawVec<ES, VW> raw[NT];
@@ -870,6 +917,8 @@ __device__ __forceinline__ void drop_factors(const DropArgs& dr, int64_t e, floa
   }
 }
 
+constexpr bool kGatePipe = true;      // software-pipelined loads in the three gate kernels (see pipelined_rows)
+
 struct GateArgs {
   const float *stats3, *stats4, *gamma3, *beta3, *gamma4, *beta4, *gate;
 };
@@ -913,7 +962,7 @@ __global__ void __launch_bounds__(TB, 2) se_gate_fwd_kernel(const T* __restrict_
     if (out2) stv<__nv_bfloat16, VW>(out2 + e, o);
   };
   if constexpr (ST) stream_rows_staged<VW, 2, sizeof(T)>(src, voxels, C, rows_per_slab, stages, dsm, prep, body);
-  else stream_rows<VW, 4, 2, sizeof(T)>(src, voxels, C, rows_per_slab, prep, body);
+  else stream_rows<VW, 2, 2, sizeof(T), kGatePipe>(src, voxels, C, rows_per_slab, prep, body);
 }
 
 // red[n][c] = { sum dx_, sum dx_*xh3, sum dr, sum dr*xh4, sum dz*x_*r } ; dgate[n][c] = the last one
@@ -961,7 +1010,8 @@ __global__ void __launch_bounds__(TB, 2) se_gate_bwd_reduce_kernel(const TG* __r
   if constexpr (ST)
     reduce_rows_staged<5, VW, 3, sizeof(T)>(src, voxels, C, rows_per_slab, stages, dsm, rs, prep, body, fin);
   else
-    reduce_rows<5, VW, 4, 3, sizeof(T)>(src, voxels, C, rows_per_slab, reinterpret_cast<float*>(dsm), rs, prep, body, fin);
+    reduce_rows<5, VW, 2, 3, sizeof(T), kGatePipe>(src, voxels, C, rows_per_slab, reinterpret_cast<float*>(dsm), rs, prep, body,
+                                                    fin);
 }
 
 struct GateBwdRegs {
@@ -1022,7 +1072,7 @@ __global__ void __launch_bounds__(TB, 2) se_gate_bwd_apply_kernel(const TG* __re
     stv<TG, VW>(draw4 + e, o4);
   };
   if constexpr (ST) stream_rows_staged<VW, 3, sizeof(T)>(src, voxels, C, rows_per_slab, stages, dsm, prep, body);
-  else stream_rows<VW, 4, 3, sizeof(T)>(src, voxels, C, rows_per_slab, prep, body);
+  else stream_rows<VW, 2, 3, sizeof(T), kGatePipe>(src, voxels, C, rows_per_slab, prep, body);
 }
 
 inline int64_t slab_rows(const m1_ctx* ctx, int batch, int64_t voxels, int per_sm = 4) {
