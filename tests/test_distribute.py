@@ -33,7 +33,9 @@ def _worker(rank, world, port, q):
     # completion order of a backward walk: reverse layout order, shared weights finish on their 2nd use
     names = [sp.name for sp in sorted(P.specs.values(), key=lambda sp: sp.offset)]
     uses = {n: (2 if n.startswith('p') else 1) for n in names}
-    sync.begin(flat, uses)
+    joins = []
+    sync.pre_fire = lambda: joins.append(len(sync.fired))      # Engine.join_side in the product: once per bucket,
+    sync.begin(flat, uses)                                      # BEFORE its all-reduce is issued
     fired_before_finish = 0
     for rep in (0, 1):
         for n in reversed(names):
@@ -44,7 +46,7 @@ def _worker(rank, world, port, q):
     fired_before_finish = len(sync.fired)
     sync.finish()
     expect = torch.arange(P.total, dtype=torch.float32) * sum(r + 1 for r in range(world))
-    ok = torch.equal(flat, expect)
+    ok = torch.equal(flat, expect) and joins == list(range(1, len(sync.buckets) + 1))
     q.put((rank, ok, len(sync.buckets), fired_before_finish, sorted(sync.fired) == list(range(len(sync.buckets)))))
     dist.destroy_process_group()
 
