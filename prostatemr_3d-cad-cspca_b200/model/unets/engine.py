@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from ... import _lib, ops
-from ..._lib import BF16, CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, F16, F32, grad_dtype
+from ..._lib import CONV_FWD, CONV_TRANSPOSED, ENGINE_AUTO, ENGINE_SIMT, F32, grad_dtype
 
 LRELU = 0.1
 IN_EPS = 1e-3

@@ -8,7 +8,6 @@ Everything here is host logic: it decides WHICH sm_100a kernels run on WHICH buf
 Engine) - all arithmetic happens in libm1b200.so. Quirks Q1-Q9 of the reference are
 reproduced or shimmed exactly as documented next to each.
 """
-import math
 import time
 
 import numpy as np
@@ -18,7 +17,7 @@ from ... import ops
 from .. import initializers, regularizers
 from ..losses import EvidenceLowerBound, Focal
 from ..optimizers import Adam
-from .engine import LRELU, Act, Engine, InjectedNoise, LazyHead, PhiloxNoise
+from .engine import LRELU, Engine, InjectedNoise, LazyHead, PhiloxNoise
 from .modelio import LoadableModel, store_config_args
 from .network_blocks import GridAttentionBlock3D, SEResNetBottleNeck, StitchingProbDecoder
 from .params import ParamTable
